@@ -1,0 +1,253 @@
+// Context management, error reporting and host-side mixture preprocessing for libgse_b200.so.
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include "gse_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void gse_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* gse_last_error(void) { return g_err; }
+extern "C" int gse_abi_version(void) { return GSE_ABI_VERSION; }
+
+// ---- small dense helpers (double, row-major n x n, n <= 5) -------------------------------------
+static int chol_lower(const double* A, int n, double* L) {
+    for (int i = 0; i < n * n; ++i) L[i] = 0.0;
+    for (int j = 0; j < n; ++j) {
+        double d = A[j * n + j];
+        for (int k = 0; k < j; ++k) d -= L[j * n + k] * L[j * n + k];
+        if (!(d > 0.0)) return -1;
+        L[j * n + j] = sqrt(d);
+        for (int i = j + 1; i < n; ++i) {
+            double s = A[i * n + j];
+            for (int k = 0; k < j; ++k) s -= L[i * n + k] * L[j * n + k];
+            L[i * n + j] = s / L[j * n + j];
+        }
+    }
+    return 0;
+}
+
+// inverse and determinant by Gauss-Jordan with partial pivoting
+static int inv_det(const double* A, int n, double* inv, double* det) {
+    double a[25], b[25];
+    for (int i = 0; i < n * n; ++i) { a[i] = A[i]; b[i] = 0.0; }
+    for (int i = 0; i < n; ++i) b[i * n + i] = 1.0;
+    double dt = 1.0;
+    for (int c = 0; c < n; ++c) {
+        int p = c;
+        for (int r = c + 1; r < n; ++r) if (fabs(a[r * n + c]) > fabs(a[p * n + c])) p = r;
+        if (a[p * n + c] == 0.0) return -1;
+        if (p != c) {
+            for (int k = 0; k < n; ++k) {
+                double t = a[c * n + k]; a[c * n + k] = a[p * n + k]; a[p * n + k] = t;
+                t = b[c * n + k]; b[c * n + k] = b[p * n + k]; b[p * n + k] = t;
+            }
+            dt = -dt;
+        }
+        const double piv = a[c * n + c];
+        dt *= piv;
+        for (int k = 0; k < n; ++k) { a[c * n + k] /= piv; b[c * n + k] /= piv; }
+        for (int r = 0; r < n; ++r) {
+            if (r == c) continue;
+            const double f = a[r * n + c];
+            if (f == 0.0) continue;
+            for (int k = 0; k < n; ++k) { a[r * n + k] -= f * a[c * n + k]; b[r * n + k] -= f * b[c * n + k]; }
+        }
+    }
+    for (int i = 0; i < n * n; ++i) inv[i] = b[i];
+    *det = dt;
+    return 0;
+}
+
+static int check_mixture(const gse_mixture* m, int nx) {
+    GSE_REQUIRE(m != NULL, "mixture is NULL");
+    GSE_REQUIRE(m->nd >= 1 && m->nd <= GSE_MAX_ND, "mixture nd out of range");
+    GSE_REQUIRE(m->nx == nx, "mixture nx mismatch");
+    return GSE_OK;
+}
+
+// parameters are stored float32 by the reference (MultivariateGaussianSum.py:29-31)
+static double f32(double v) { return (double)(float)v; }
+
+int gse_build_sampler5(const gse_mixture* m, MixSampler5* out) {
+    int rc = check_mixture(m, GSE_NX);
+    if (rc) return rc;
+    memset(out, 0, sizeof(*out));
+    out->nd = m->nd;
+    double wsum = 0.0;
+    for (int d = 0; d < m->nd; ++d) wsum += f32(m->weights[d]);
+    GSE_REQUIRE(wsum > 0.0, "mixture weights sum to zero");
+    double acc = 0.0;
+    int diag = 1;
+    for (int d = 0; d < m->nd; ++d) {
+        acc += f32(m->weights[d]) / wsum;
+        out->cdf[d] = (float)acc;
+        double C[25], L[25];
+        for (int i = 0; i < 25; ++i) C[i] = f32(m->covs[d * 25 + i]);
+        if (chol_lower(C, 5, L) != 0) {
+            gse_set_error("state mixture component %d covariance is not positive definite", d);
+            return GSE_ELINALG;
+        }
+        int t = 0;
+        for (int i = 0; i < 5; ++i) {
+            out->mean[d][i] = (float)m->means[d * 5 + i];
+            for (int j = 0; j <= i; ++j) {
+                out->L[d][t++] = (float)L[i * 5 + j];
+                if (i != j && L[i * 5 + j] != 0.0) diag = 0;
+            }
+        }
+    }
+    out->cdf[m->nd - 1] = 1.0f;
+    for (int d = m->nd; d < GSE_MAX_ND; ++d) out->cdf[d] = 2.0f;
+    out->diag = diag;
+    return GSE_OK;
+}
+
+int gse_build_densityN(const gse_mixture* m, MixDensityN* out) {
+    GSE_REQUIRE(m != NULL, "mixture is NULL");
+    GSE_REQUIRE(m->nd >= 1 && m->nd <= GSE_MAX_ND, "mixture nd out of range");
+    GSE_REQUIRE(m->nx >= 1 && m->nx <= GSE_NX, "mixture nx out of range");
+    memset(out, 0, sizeof(*out));
+    const int n = m->nx;
+    out->nd = m->nd;
+    out->nx = n;
+    for (int d = 0; d < m->nd; ++d) {
+        double C[25], C32[25], P[25], P32[25], det, det32;
+        for (int i = 0; i < n * n; ++i) { C[i] = m->covs[d * n * n + i]; C32[i] = f32(C[i]); }
+        // inverse of the float64 input (MultivariateGaussianSum.py:33); constant from the float32
+        // copy (:36-37)
+        if (inv_det(C, n, P, &det) != 0 || inv_det(C32, n, P32, &det32) != 0 || !(det32 > 0.0)) {
+            gse_set_error("mixture component %d covariance is singular", d);
+            return GSE_ELINALG;
+        }
+        const double cst = pow(2.0 * M_PI, -0.5 * n) / sqrt(det32);
+        const double w = f32(m->weights[d]);
+        out->logc[d] = (w > 0.0) ? log(w * cst) : -1.0e300;
+        for (int i = 0; i < n; ++i) out->mean[d][i] = f32(m->means[d * n + i]);
+        for (int i = 0; i < n * n; ++i) out->P[d][i] = P[i];
+    }
+    return GSE_OK;
+}
+
+int gse_build_density2(const gse_mixture* m, MixDensity2* out) {
+    int rc = check_mixture(m, GSE_NY);
+    if (rc) return rc;
+    MixDensityN g;
+    rc = gse_build_densityN(m, &g);
+    if (rc) return rc;
+    memset(out, 0, sizeof(*out));
+    out->nd = g.nd;
+    for (int d = 0; d < g.nd; ++d) {
+        out->logc[d] = g.logc[d];
+        out->mean[d][0] = g.mean[d][0];
+        out->mean[d][1] = g.mean[d][1];
+        out->p00[d] = g.P[d][0];
+        out->p01[d] = g.P[d][1] + g.P[d][2];
+        out->p11[d] = g.P[d][3];
+    }
+    return GSE_OK;
+}
+
+// ---- context ------------------------------------------------------------------------------------
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+extern "C" int gse_ctx_create(int device, int model_id, int64_t n_max, const gse_mixture* state,
+                              const gse_mixture* meas, gse_ctx** out) {
+    GSE_REQUIRE(out != NULL, "out is NULL");
+    GSE_REQUIRE(model_id == GSE_MODEL_BIOREACTOR, "unknown model_id (only GSE_MODEL_BIOREACTOR is compiled in)");
+    GSE_REQUIRE(n_max >= 1 && n_max <= ((int64_t)1 << 40), "n_max out of range");
+    int ndev = 0;
+    GSE_CHECK_CUDA(cudaGetDeviceCount(&ndev));
+    GSE_REQUIRE(device >= 0 && device < ndev, "device index out of range");
+    GSE_CHECK_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    GSE_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        gse_set_error("libgse_b200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+        return GSE_ECUDA;
+    }
+    gse_ctx* c = (gse_ctx*)calloc(1, sizeof(gse_ctx));
+    if (!c) { gse_set_error("out of host memory"); return GSE_ENOMEM; }
+    c->device = device;
+    c->model_id = model_id;
+    c->n_max = n_max;
+    c->num_sms = prop.multiProcessorCount;
+    int rc = gse_build_sampler5(state, &c->state_sampler);
+    if (rc == GSE_OK) rc = gse_build_density2(meas, &c->meas_density);
+    if (rc != GSE_OK) { free(c); return rc; }
+
+    // workspace: sized for the largest grid any kernel uses on n_max rows
+    c->max_blocks = gse_div_up(n_max, 256) + 8;        // >= blocks of any 4-rows-per-thread kernel
+    c->max_tiles = gse_div_up(n_max, 1024) + 8;        // scan tiles / merge partitions (>= 2n/4096)
+    size_t off = 0;
+    const size_t o_bmax = off; off = align_up(off + sizeof(float) * c->max_blocks, 256);
+    const size_t o_bsum = off; off = align_up(off + sizeof(float) * c->max_blocks, 256);
+    const size_t o_tick = off; off = align_up(off + sizeof(unsigned int) * 8, 256);
+    const size_t o_red = off; off = align_up(off + sizeof(double) * 48 * 2048, 256);
+    const size_t o_agg = off; off = align_up(off + sizeof(uint64_t) * c->max_tiles, 256);
+    const size_t o_inc = off; off = align_up(off + sizeof(uint64_t) * c->max_tiles, 256);
+    const size_t o_flag = off; off = align_up(off + sizeof(unsigned int) * c->max_tiles, 256);
+    const size_t o_part = off; off = align_up(off + sizeof(int64_t) * (c->max_tiles + 2), 256);
+    c->ws_bytes = off;
+    cudaError_t e = cudaMalloc(&c->ws, c->ws_bytes);
+    if (e != cudaSuccess) {
+        gse_set_error("cudaMalloc(%zu) for the workspace failed: %s", c->ws_bytes, cudaGetErrorString(e));
+        free(c);
+        return GSE_ENOMEM;
+    }
+    e = cudaMemset(c->ws, 0, c->ws_bytes);
+    if (e != cudaSuccess) {
+        gse_set_error("cudaMemset failed: %s", cudaGetErrorString(e));
+        cudaFree(c->ws);
+        free(c);
+        return GSE_ECUDA;
+    }
+    char* base = (char*)c->ws;
+    c->block_max = (float*)(base + o_bmax);
+    c->block_sum = (float*)(base + o_bsum);
+    c->ticket = (unsigned int*)(base + o_tick);
+    c->red_partials = (double*)(base + o_red);
+    c->tile_agg = (uint64_t*)(base + o_agg);
+    c->tile_inc = (uint64_t*)(base + o_inc);
+    c->tile_flag = (unsigned int*)(base + o_flag);
+    c->part = (int64_t*)(base + o_part);
+    c->scan_epoch = 0;
+    *out = c;
+    return GSE_OK;
+}
+
+extern "C" int gse_ctx_destroy(gse_ctx* ctx) {
+    if (!ctx) return GSE_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->ws) cudaFree(ctx->ws);
+    free(ctx);
+    return GSE_OK;
+}
+
+extern "C" int64_t gse_launch_count(const gse_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// Host evaluation of the device's output-count predicate (see gse_common.cuh): number of outputs
+// i in [0, n_total) with q*(u_i) <= bound, i.e. those sourced at or below cumulative weight `bound`.
+extern "C" int64_t gse_count_outputs_below(uint64_t bound, uint64_t total, double r, int64_t n_total) {
+    if (n_total <= 0 || total == 0) return 0;
+    const double Td = gse_u64_to_double(total);
+    const double nd = (double)n_total;
+    // q*(u_i) is non-decreasing in i: binary search for the first i with q*(u_i) > bound
+    int64_t lo = 0, hi = n_total;
+    while (lo < hi) {
+        const int64_t mid = lo + ((hi - lo) >> 1);
+        const uint64_t q = gse_threshold(gse_sample_position(mid, r, nd), Td);
+        if (q <= bound) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+extern "C" uint64_t gse_threshold_u64(double u, uint64_t total) {
+    return gse_threshold(u, gse_u64_to_double(total));
+}

@@ -1,0 +1,474 @@
+// Shared definitions for libgse_b200.so (sm_100a).  See include/gse.h for the ABI.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+
+#include "../../include/gse.h"
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+void gse_set_error(const char* fmt, ...);
+
+#define GSE_CHECK_CUDA(expr)                                                              \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            gse_set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,            \
+                          cudaGetErrorString(_e));                                        \
+            return GSE_ECUDA;                                                             \
+        }                                                                                 \
+    } while (0)
+
+#define GSE_CHECK_LAUNCH(ctx)                                                             \
+    do {                                                                                  \
+        (ctx)->launches++;                                                                \
+        cudaError_t _e = cudaGetLastError();                                              \
+        if (_e != cudaSuccess) {                                                          \
+            gse_set_error("kernel launch failed at %s:%d: %s", __FILE__, __LINE__,        \
+                          cudaGetErrorString(_e));                                        \
+            return GSE_ECUDA;                                                             \
+        }                                                                                 \
+    } while (0)
+
+#define GSE_REQUIRE(cond, msg)                                                            \
+    do {                                                                                  \
+        if (!(cond)) {                                                                    \
+            gse_set_error("invalid argument at %s:%d: %s", __FILE__, __LINE__, msg);      \
+            return GSE_EINVAL;                                                            \
+        }                                                                                 \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// kernel-parameter structs (passed by value: no __constant__ globals, so that several contexts
+// with different mixtures can live in one process)
+// ------------------------------------------------------------------------------------------------
+
+// Sampler for a 5-d Gaussian sum: component chosen by inverse cdf, then mean + L z.
+struct MixSampler5 {
+    int nd;
+    int diag;                          // every L is diagonal (the benchmark's noise, sim_base.py:141-160)
+    float cdf[GSE_MAX_ND];             // inclusive cumulative weights, cdf[nd-1] = 1
+    float mean[GSE_MAX_ND][GSE_NX];
+    float L[GSE_MAX_ND][GSE_NCOV];     // lower-triangular Cholesky factor, row-major packed
+};
+
+// log-density of a 2-d Gaussian sum (measurement noise), float64 quadratic forms.
+struct MixDensity2 {
+    int nd;
+    double logc[GSE_MAX_ND];           // log(w_d * const_d)          (MultivariateGaussianSum.py:36-37,60)
+    double mean[GSE_MAX_ND][2];
+    double p00[GSE_MAX_ND], p01[GSE_MAX_ND], p11[GSE_MAX_ND];   // inverse covariance; p01 = P01 + P10 (:33)
+};
+
+// Generic density (nx <= 5) used by gse_mixture_pdf.
+struct MixDensityN {
+    int nd, nx;
+    double logc[GSE_MAX_ND];
+    double mean[GSE_MAX_ND][GSE_NX];
+    double P[GSE_MAX_ND][GSE_NX * GSE_NX];
+};
+
+struct gse_ctx {
+    int device;
+    int model_id;
+    int64_t n_max;
+    int num_sms;
+    int64_t launches;
+    MixSampler5 state_sampler;
+    MixDensity2 meas_density;
+    // workspace
+    void* ws;                 // one allocation, carved below
+    size_t ws_bytes;
+    float* block_max;         // per-block partial maxima (update / loglik_max)
+    float* block_sum;         // per-block partial sums of exp(loglik - block max)
+    unsigned int* ticket;     // [0]: last-block counter for reductions, [1]: scan tile ticket
+    double* red_partials;     // per-block partial moments
+    uint64_t* tile_agg;       // scan: per-tile aggregate
+    uint64_t* tile_inc;       // scan: per-tile inclusive prefix
+    unsigned int* tile_flag;  // scan: (epoch << 2) | state
+    int64_t* part;            // merge-path split points
+    unsigned int scan_epoch;
+    int64_t max_blocks;
+    int64_t max_tiles;
+};
+
+int gse_build_sampler5(const gse_mixture* m, MixSampler5* out);
+int gse_build_density2(const gse_mixture* m, MixDensity2* out);
+int gse_build_densityN(const gse_mixture* m, MixDensityN* out);
+
+static inline int64_t gse_div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11).  Counter-based: the stream of row i at step t
+// is a pure function of (seed, i, t, subsequence) -- independent of launch geometry and of how
+// rows are sharded over GPUs.
+// ------------------------------------------------------------------------------------------------
+#define PHILOX_M0 0xD2511F53u
+#define PHILOX_M1 0xCD9E8D57u
+#define PHILOX_W0 0x9E3779B9u
+#define PHILOX_W1 0xBB67AE85u
+
+struct Philox4 {
+    uint32_t x, y, z, w;
+};
+
+__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                 uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)PHILOX_M0 * c0;
+        const uint64_t p1 = (uint64_t)PHILOX_M1 * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+        k0 += PHILOX_W0;
+        k1 += PHILOX_W1;
+    }
+    Philox4 o;
+    o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+    return o;
+}
+
+// uniform in (0, 1]: (x + 0.5) * 2^-32 evaluated in float32 (the curand convention)
+__device__ __forceinline__ float u32_to_unit(uint32_t x) {
+    return fmaf((float)x, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+}
+
+// Box-Muller with the MUFU approximations (lg2.approx, sin/cos.approx); the angle is folded to
+// (-pi, pi] where sin.approx / cos.approx are most accurate.
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
+    const float u1 = u32_to_unit(a);
+    const float u2 = u32_to_unit(b);
+    const float r = sqrtf(-2.0f * __logf(u1));
+    const float th = fmaf(u2, 6.2831853071795865f, -3.1415926535897932f);
+    float s, c;
+    __sincosf(th, &s, &c);
+    z0 = r * c;
+    z1 = r * s;
+}
+
+// Five state-noise values for row `index` at `step`, subsequence pair (sub, sub+1).
+// Draw layout (restated in oracle/philox.py):
+//   A = philox(index_lo, index_hi, step, 2*sub)    -> (z0, z1) = BM(A.x, A.y), (z2, z3) = BM(A.z, A.w)
+//   B = philox(index_lo, index_hi, step, 2*sub+1)  -> (z4, _ ) = BM(B.x, B.y), component from B.z
+template <bool DIAG>
+__device__ __forceinline__ void draw_mixture5(const MixSampler5& sp, uint64_t index, uint32_t step,
+                                              uint32_t sub, uint32_t k0, uint32_t k1, float out[5]) {
+    const Philox4 A = philox4x32_10((uint32_t)index, (uint32_t)(index >> 32), step, 2u * sub, k0, k1);
+    const Philox4 B = philox4x32_10((uint32_t)index, (uint32_t)(index >> 32), step, 2u * sub + 1u, k0, k1);
+    float z[5], spare;
+    box_muller(A.x, A.y, z[0], z[1]);
+    box_muller(A.z, A.w, z[2], z[3]);
+    box_muller(B.x, B.y, z[4], spare);
+    const float uc = u32_to_unit(B.z);
+    int comp = 0;
+#pragma unroll
+    for (int d = 0; d < GSE_MAX_ND - 1; ++d)
+        comp += (d < sp.nd - 1 && uc > sp.cdf[d]) ? 1 : 0;
+    if (DIAG) {
+        const int dg[5] = {0, 2, 5, 9, 14};
+#pragma unroll
+        for (int j = 0; j < 5; ++j) out[j] = fmaf(sp.L[comp][dg[j]], z[j], sp.mean[comp][j]);
+    } else {
+        int t = 0;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            float acc = sp.mean[comp][j];
+#pragma unroll
+            for (int m = 0; m <= j; ++m) acc = fmaf(sp.L[comp][t++], z[m], acc);
+            out[j] = acc;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Bioreactor model (model/BioreactorModel.py:170-253), float32, hard-coded.
+// ------------------------------------------------------------------------------------------------
+struct ModelInputs {
+    float feed;    // Fg_in * Cg_in           (:196,225)
+    float f_out;   // Fg_in + Fm_in           (:197)
+    float dt;
+};
+
+__device__ __forceinline__ void bioreactor_increment(const float x[5], const ModelInputs& in, float d[5]) {
+    // :192-193 -- the rate expressions see clamped Cg, Cx, Cfa, Ce; Ch is not clamped
+    const float Cg = fmaxf(x[0], 0.0f), Cx = fmaxf(x[1], 0.0f), Cfa = fmaxf(x[2], 0.0f),
+                Ce = fmaxf(x[3], 0.0f), Ch = x[4];
+    const float K_FA = (float)(0.25 / 116 * 24.6);            // :205
+    const float K_T1 = (float)((0.4 - 0.25) / 180 * 24.6);    // :209
+    const float K_E = (float)(0.025 / 46 * 24.6);             // :214
+    const float K_T2 = (float)((0.1 - 0.025) / 180 * 24.6);   // :219
+    const float K_H = (float)(1.0 / 2000 / (0.28 / 180));     // :210
+    const float rH = (float)(280.0 / 180) - Cg;               // :202
+    const float sat = __fdiv_rn(Cg, 1e-2f + Cg);              // Cg / (1e-2 + Cg)   :206,211
+    const float rFA = K_FA * Cx * sat;                        // :206
+    const float t1max = K_T1 * Cx;                            // :209
+    const float t1req = t1max - fmaf(t1max * K_H, rH, 0.01f * Ch);          // :210
+    const float t1 = fminf(t1max, fmaxf(0.0f, t1req)) * sat;                // :211
+    const float over = t1req - t1max;                                      // :215
+    const float rE = fminf(K_E * Cx, fmaxf(0.0f, over));                    // :216
+    const float t2 = fminf(K_T2 * Cx, fmaxf(0.0f, over - rE));              // :219-221
+    const float rG = -rFA * (float)(116.0 / 180) - t1 - rE * (float)(46.0 / 180) - t2;   // :223
+    d[0] = (in.feed - in.f_out * Cg + rG) * in.dt;            // :225
+    d[1] = 0.0f * Cx * in.dt;                                 // :226 (rX = 0 * Cx)
+    d[2] = (rFA - in.f_out * Cfa) * in.dt;                    // :227
+    d[3] = (rE - in.f_out * Ce) * in.dt;                      // :228
+    d[4] = rH * in.dt;                                        // :229
+}
+
+// static_outputs (:233-253): float32 products, as the reference produces them (see oracle/bioreactor.py)
+__device__ __forceinline__ float output_glucose(float Cg) { return __fmul_rn(Cg, 180.0f); }
+__device__ __forceinline__ float output_fa(float Cfa) { return __fmul_rn(Cfa, 116.0f); }
+
+// log pdf of the measurement mixture at e = z - y  (MultivariateGaussianSum.py:39-63), quadratic
+// forms in float64, the log-sum-exp tail in float32 (terms <= 1, so the absolute error of the
+// result is ~1e-7).
+__device__ __forceinline__ double meas_logpdf(const MixDensity2& md, double e0, double e1) {
+    double a[GSE_MAX_ND];
+    double m = -1.0e300;
+#pragma unroll
+    for (int d = 0; d < GSE_MAX_ND; ++d) {
+        if (d < md.nd) {
+            const double v0 = e0 - md.mean[d][0], v1 = e1 - md.mean[d][1];
+            const double q = v0 * (md.p00[d] * v0 + md.p01[d] * v1) + md.p11[d] * v1 * v1;
+            a[d] = md.logc[d] - 0.5 * q;
+            m = fmax(m, a[d]);
+        }
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int d = 0; d < GSE_MAX_ND; ++d)
+        if (d < md.nd) s += __expf((float)(a[d] - m));
+    return m + (double)__logf(s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// warp / block reductions
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// block-level (max, sum exp) reduction shared by K2 and gse_loglik_max.
+// Each block publishes (m_b, s_b = sum exp(v - m_b)); the last block to finish merges them in a
+// fixed order into stats[0] = M = max, stats[1] = S = sum exp(v - M).
+// ------------------------------------------------------------------------------------------------
+template <int THREADS, int NV>
+__device__ __forceinline__ void block_max_sumexp_finalize(const float vals[NV], const bool valid[NV],
+                                                          float* block_max, float* block_sum,
+                                                          unsigned int* ticket, double* stats) {
+    __shared__ float s_red[THREADS / 32];
+    __shared__ float s_bcast;
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float m = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < NV; ++r) if (valid[r]) m = fmaxf(m, vals[r]);
+    m = warp_max(m);
+    if (lane == 0) s_red[wid] = m;
+    __syncthreads();
+    if (wid == 0) {
+        float t = (lane < THREADS / 32) ? s_red[lane] : -INFINITY;
+        t = warp_max(t);
+        if (lane == 0) s_bcast = t;
+    }
+    __syncthreads();
+    const float bm = s_bcast;
+    float sum = 0.0f;
+#pragma unroll
+    for (int r = 0; r < NV; ++r) if (valid[r]) sum += __expf(vals[r] - bm);
+    sum = warp_sum(sum);
+    __syncthreads();
+    if (lane == 0) s_red[wid] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.0f;
+#pragma unroll
+        for (int w = 0; w < THREADS / 32; ++w) t += s_red[w];
+        block_max[blockIdx.x] = bm;
+        block_sum[blockIdx.x] = t;
+        __threadfence();
+        const unsigned int done = atomicAdd(ticket, 1u);
+        s_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // last block: merge all partials (fixed order per thread, then a fixed tree)
+    __shared__ double s_dred[THREADS / 32];
+    float gm = -INFINITY;
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += THREADS) gm = fmaxf(gm, __ldcg(block_max + b));
+    gm = warp_max(gm);
+    __syncthreads();
+    if (lane == 0) s_red[wid] = gm;
+    __syncthreads();
+    if (wid == 0) {
+        float t = (lane < THREADS / 32) ? s_red[lane] : -INFINITY;
+        t = warp_max(t);
+        if (lane == 0) s_bcast = t;
+    }
+    __syncthreads();
+    const float M = s_bcast;
+    double acc = 0.0;
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += THREADS) {
+        const float bmx = __ldcg(block_max + b);
+        if (bmx > -INFINITY) acc += (double)__ldcg(block_sum + b) * (double)__expf(bmx - M);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) s_dred[wid] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < THREADS / 32; ++w) t += s_dred[w];
+        stats[0] = (double)M;
+        stats[1] = t;
+        *ticket = 0u;
+    }
+}
+
+// streaming 128-bit accesses for touch-once columns
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+    float4 r;
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream4(float* p, const float4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+#endif  // __CUDACC__
+
+// ------------------------------------------------------------------------------------------------
+// Exact systematic-resampling thresholds (host + device).
+//
+// The reference compares  cumsum[k] / cumsum[-1] < (i + r) / N  in float64 (particle.py:89-98).
+// Here cumulative weights are exact integers C (uint64, <= 2^62); the comparison value is
+// g(C) = fl(fl(C) / fl(T)).  g is monotone, so  g(C) >= u  <=>  C >= q*(u)  with
+// q*(u) = min{C : g(C) >= u}, computed below in two steps:
+//   X*  = min{x double : fl(x / Td) >= u}      (estimate u*Td, then step by ulps with the real divide)
+//   q*  = min{C integer : fl(C) >= X*}          (round-to-nearest-even conversion inverted exactly)
+// tests/test_thresholds.py checks g(q*-1) < u <= g(q*) against Python integers / numpy float64.
+// ------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+#define GSE_HD __host__ __device__ __forceinline__
+#else
+#define GSE_HD static inline
+#endif
+
+GSE_HD double gse_bits_to_double(uint64_t b) {
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double((long long)b);
+#else
+    double d; memcpy(&d, &b, 8); return d;
+#endif
+}
+GSE_HD uint64_t gse_double_to_bits(double d) {
+#ifdef __CUDA_ARCH__
+    return (uint64_t)__double_as_longlong(d);
+#else
+    uint64_t b; memcpy(&b, &d, 8); return b;
+#endif
+}
+GSE_HD double gse_div(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __ddiv_rn(a, b);
+#else
+    return a / b;
+#endif
+}
+GSE_HD double gse_add(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+GSE_HD double gse_mul(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+GSE_HD double gse_u64_to_double(uint64_t c) {
+#ifdef __CUDA_ARCH__
+    return __ull2double_rn(c);
+#else
+    return (double)c;   // round-to-nearest-even on x86-64
+#endif
+}
+
+// u_i = (i + r) / N exactly as the reference evaluates it (particle.py:97)
+GSE_HD double gse_sample_position(int64_t i, double r, double n_total) {
+    return gse_div(gse_add((double)i, r), n_total);
+}
+
+// smallest double x >= 0 with fl(x / Td) >= u      (u in [0, 1], Td >= 1)
+GSE_HD double gse_threshold_double(double u, double Td) {
+    if (!(u > 0.0)) return 0.0;
+    double x = gse_mul(u, Td);
+    if (gse_div(x, Td) >= u) {
+        // walk down while the predecessor still qualifies
+        for (int it = 0; it < 8; ++it) {
+            if (!(x > 0.0)) break;
+            const double xp = gse_bits_to_double(gse_double_to_bits(x) - 1);
+            if (gse_div(xp, Td) >= u) x = xp; else break;
+        }
+    } else {
+        for (int it = 0; it < 8; ++it) {
+            x = gse_bits_to_double(gse_double_to_bits(x) + 1);
+            if (gse_div(x, Td) >= u) break;
+        }
+    }
+    return x;
+}
+
+// smallest integer C with fl(C) >= X  (X >= 0 a double, X <= 2^63)
+GSE_HD uint64_t gse_threshold_int(double X) {
+    if (!(X > 0.0)) return 0;
+    if (X < 9007199254740992.0) {                 // < 2^53: every integer is representable
+        const double c = ceil(X);
+        return (uint64_t)c;
+    }
+    const uint64_t bits = gse_double_to_bits(X);
+    const int e = (int)((bits >> 52) & 0x7ff) - 1075;     // X = m * 2^e, m in [2^52, 2^53)
+    const uint64_t mant = bits & 0xfffffffffffffull;
+    const uint64_t Xi = (uint64_t)X;                      // exact: X is an integer here
+    // gap between X and its predecessor
+    uint64_t gap = 1ull << e;
+    if (mant == 0 && e > 0) gap >>= 1;
+    if (mant == 0 && e == 0) gap = 1;                     // X = 2^53: predecessor 2^53 - 1
+    if (gap < 2) return Xi;                               // no integer strictly between
+    const uint64_t mid = Xi - (gap >> 1);                 // exact midpoint: ties to even
+    const bool x_even = (mant & 1ull) == 0;               // power of two has an even significand
+    return x_even ? mid : mid + 1;
+}
+
+// q*(u): smallest integer cumulative weight C (0 <= C <= T) with fl(fl(C)/fl(T)) >= u
+GSE_HD uint64_t gse_threshold(double u, double Td) {
+    return gse_threshold_int(gse_threshold_double(u, Td));
+}

@@ -1,0 +1,378 @@
+// Particle-filter kernels: initial draw (K0), predict (K1), update (K2), weighted moments (K6),
+// and the stand-alone mixture pdf / weight read-back helpers.  One thread owns 4 consecutive rows
+// so that every SoA column moves as 128-bit coalesced vectors.
+#include "gse_common.cuh"
+
+#define PF_THREADS 256
+#define ROWS_PER_THREAD 4
+
+static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
+
+#define CHECK_SOA(ptr, ld, n)                                                                   \
+    GSE_REQUIRE((ptr) != NULL && aligned16(ptr), "SoA base pointer must be non-NULL and 16-byte aligned"); \
+    GSE_REQUIRE((ld) % 4 == 0 && (ld) >= ((n) + 3) / 4 * 4, "ld must be a multiple of 4 and >= round_up(n, 4)")
+
+// ------------------------------------------------------------------------------------------------
+// K0: mixture draw into SoA columns
+// ------------------------------------------------------------------------------------------------
+template <bool DIAG>
+__global__ void __launch_bounds__(PF_THREADS)
+k_mixture_draw(float* __restrict__ x, int64_t ld, int64_t n, const __grid_constant__ MixSampler5 sp,
+               uint32_t k0, uint32_t k1, uint32_t step, int64_t index0) {
+    const int64_t g = (int64_t)blockIdx.x * PF_THREADS + threadIdx.x;
+    const int64_t row0 = g * ROWS_PER_THREAD;
+    if (row0 >= n) return;
+    float v[5][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        float o[5];
+        draw_mixture5<DIAG>(sp, (uint64_t)(index0 + row0 + r), step, 0u, k0, k1, o);
+#pragma unroll
+        for (int j = 0; j < 5; ++j) v[j][r] = o[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 5; ++j)
+        st_stream4(x + j * ld + row0, make_float4(v[j][0], v[j][1], v[j][2], v[j][3]));
+}
+
+extern "C" int gse_mixture_draw(gse_ctx* ctx, const gse_mixture* mix, float* x_dev, int64_t ld, int64_t n,
+                                uint64_t seed, uint64_t step, int64_t index0, void* stream) {
+    GSE_REQUIRE(ctx != NULL, "ctx is NULL");
+    GSE_REQUIRE(n >= 0, "n < 0");
+    if (n == 0) return GSE_OK;
+    CHECK_SOA(x_dev, ld, n);
+    MixSampler5 sp;
+    int rc = gse_build_sampler5(mix, &sp);
+    if (rc) return rc;
+    const int64_t groups = gse_div_up(n, ROWS_PER_THREAD);
+    const unsigned blocks = (unsigned)gse_div_up(groups, PF_THREADS);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (sp.diag)
+        k_mixture_draw<true><<<blocks, PF_THREADS, 0, s>>>(x_dev, ld, n, sp, (uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)step, index0);
+    else
+        k_mixture_draw<false><<<blocks, PF_THREADS, 0, s>>>(x_dev, ld, n, sp, (uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)step, index0);
+    GSE_CHECK_LAUNCH(ctx);
+    return GSE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: predict.  x += f(x, u, dt) (n_sub Euler sub-steps), then x += noise (particle.py:65-67).
+// ------------------------------------------------------------------------------------------------
+template <bool DIAG, bool HOST_NOISE>
+__global__ void __launch_bounds__(PF_THREADS)
+k_pf_predict(float* __restrict__ x, int64_t ld, int64_t n, ModelInputs in, int n_sub,
+             const __grid_constant__ MixSampler5 sp, uint32_t k0, uint32_t k1, uint32_t step,
+             int64_t index0, const float* __restrict__ noise, int64_t ldn) {
+    const int64_t g = (int64_t)blockIdx.x * PF_THREADS + threadIdx.x;
+    const int64_t row0 = g * ROWS_PER_THREAD;
+    if (row0 >= n) return;
+    float4 c[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) c[j] = ld_stream4(x + j * ld + row0);
+    float v[5][4];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) { v[j][0] = c[j].x; v[j][1] = c[j].y; v[j][2] = c[j].z; v[j][3] = c[j].w; }
+    float4 nz[5];
+    if (HOST_NOISE) {
+#pragma unroll
+        for (int j = 0; j < 5; ++j) nz[j] = ld_stream4(noise + j * ldn + row0);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        float xs[5] = {v[0][r], v[1][r], v[2][r], v[3][r], v[4][r]};
+        for (int s = 0; s < n_sub; ++s) {
+            float d[5];
+            bioreactor_increment(xs, in, d);
+#pragma unroll
+            for (int j = 0; j < 5; ++j) xs[j] = __fadd_rn(xs[j], d[j]);    // particles[i] += f(...)  (:66)
+        }
+        float e[5];
+        if (HOST_NOISE) {
+#pragma unroll
+            for (int j = 0; j < 5; ++j) e[j] = reinterpret_cast<const float*>(&nz[j])[r];
+        } else {
+            draw_mixture5<DIAG>(sp, (uint64_t)(index0 + row0 + r), step, 0u, k0, k1, e);
+        }
+#pragma unroll
+        for (int j = 0; j < 5; ++j) v[j][r] = __fadd_rn(xs[j], e[j]);      // particles += draw(N)   (:67)
+    }
+#pragma unroll
+    for (int j = 0; j < 5; ++j)
+        st_stream4(x + j * ld + row0, make_float4(v[j][0], v[j][1], v[j][2], v[j][3]));
+}
+
+extern "C" int gse_pf_predict(gse_ctx* ctx, float* x_dev, int64_t ld, int64_t n, const double u[GSE_NU],
+                              double dt, int n_sub, uint64_t seed, uint64_t step, int64_t index0,
+                              const float* noise_dev, int64_t ld_noise, void* stream) {
+    GSE_REQUIRE(ctx != NULL && u != NULL, "ctx / u is NULL");
+    GSE_REQUIRE(n >= 0 && n <= ctx->n_max, "n out of range for this context");
+    GSE_REQUIRE(n_sub >= 1, "n_sub must be >= 1");
+    if (n == 0) return GSE_OK;
+    CHECK_SOA(x_dev, ld, n);
+    if (noise_dev) { CHECK_SOA(noise_dev, ld_noise, n); }
+    ModelInputs in;
+    in.feed = (float)(u[0] * (5000.0 / 180.0));
+    in.f_out = (float)(u[0] + u[1]);
+    in.dt = (float)(dt / n_sub);
+    const int64_t groups = gse_div_up(n, ROWS_PER_THREAD);
+    const unsigned blocks = (unsigned)gse_div_up(groups, PF_THREADS);
+    cudaStream_t s = (cudaStream_t)stream;
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    if (noise_dev)
+        k_pf_predict<true, true><<<blocks, PF_THREADS, 0, s>>>(x_dev, ld, n, in, n_sub, ctx->state_sampler, k0, k1, (uint32_t)step, index0, noise_dev, ld_noise);
+    else if (ctx->state_sampler.diag)
+        k_pf_predict<true, false><<<blocks, PF_THREADS, 0, s>>>(x_dev, ld, n, in, n_sub, ctx->state_sampler, k0, k1, (uint32_t)step, index0, NULL, 0);
+    else
+        k_pf_predict<false, false><<<blocks, PF_THREADS, 0, s>>>(x_dev, ld, n, in, n_sub, ctx->state_sampler, k0, k1, (uint32_t)step, index0, NULL, 0);
+    GSE_CHECK_LAUNCH(ctx);
+    return GSE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: update.  loglik_i += log pdf_meas(z - g(x_i, u))   (particle.py:80-83), fused max / sum-exp.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PF_THREADS)
+k_pf_update(const float* __restrict__ xg, const float* __restrict__ xfa, float* __restrict__ loglik,
+            int64_t n, double z0, double z1, const __grid_constant__ MixDensity2 md,
+            float* block_max, float* block_sum, unsigned int* ticket, double* stats) {
+    const int64_t g = (int64_t)blockIdx.x * PF_THREADS + threadIdx.x;
+    const int64_t row0 = g * ROWS_PER_THREAD;
+    float vals[4] = {0.f, 0.f, 0.f, 0.f};
+    bool valid[4] = {false, false, false, false};
+    if (row0 < n) {
+        const float4 cg = ld_stream4(xg + row0);
+        const float4 cf = ld_stream4(xfa + row0);
+        const float4 lw = ld_stream4(loglik + row0);
+        const float a[4] = {cg.x, cg.y, cg.z, cg.w};
+        const float b[4] = {cf.x, cf.y, cf.z, cf.w};
+        const float l[4] = {lw.x, lw.y, lw.z, lw.w};
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const double e0 = z0 - (double)output_glucose(a[r]);       // e = z - y   (:82)
+            const double e1 = z1 - (double)output_fa(b[r]);
+            vals[r] = (float)((double)l[r] + meas_logpdf(md, e0, e1));  // weights[i] *= pdf(e)  (:83)
+            valid[r] = (row0 + r) < n;
+        }
+        st_stream4(loglik + row0, make_float4(vals[0], vals[1], vals[2], vals[3]));
+    }
+    block_max_sumexp_finalize<PF_THREADS, 4>(vals, valid, block_max, block_sum, ticket, stats);
+}
+
+extern "C" int gse_pf_update(gse_ctx* ctx, const float* x_dev, int64_t ld, int64_t n, float* loglik_dev,
+                             const double u[GSE_NU], const double z[GSE_NY], double* stats_dev, void* stream) {
+    GSE_REQUIRE(ctx != NULL && z != NULL && stats_dev != NULL, "ctx / z / stats is NULL");
+    GSE_REQUIRE(n >= 1 && n <= ctx->n_max, "n out of range for this context");
+    CHECK_SOA(x_dev, ld, n);
+    GSE_REQUIRE(loglik_dev != NULL && aligned16(loglik_dev), "loglik must be 16-byte aligned");
+    (void)u;   // static_outputs ignores u (BioreactorModel.py:250)
+    const int64_t groups = gse_div_up(n, ROWS_PER_THREAD);
+    const unsigned blocks = (unsigned)gse_div_up(groups, PF_THREADS);
+    GSE_REQUIRE((int64_t)blocks <= ctx->max_blocks, "workspace too small");
+    k_pf_update<<<blocks, PF_THREADS, 0, (cudaStream_t)stream>>>(
+        x_dev + 0 * ld, x_dev + 2 * ld, loglik_dev, n, z[0], z[1], ctx->meas_density,
+        ctx->block_max, ctx->block_sum, ctx->ticket, stats_dev);
+    GSE_CHECK_LAUNCH(ctx);
+    return GSE_OK;
+}
+
+__global__ void __launch_bounds__(PF_THREADS)
+k_loglik_max(const float* __restrict__ loglik, int64_t n, float* block_max, float* block_sum,
+             unsigned int* ticket, double* stats) {
+    const int64_t g = (int64_t)blockIdx.x * PF_THREADS + threadIdx.x;
+    const int64_t row0 = g * ROWS_PER_THREAD;
+    float vals[4] = {0.f, 0.f, 0.f, 0.f};
+    bool valid[4] = {false, false, false, false};
+    if (row0 < n) {
+        const float4 lw = ld_stream4(loglik + row0);
+        vals[0] = lw.x; vals[1] = lw.y; vals[2] = lw.z; vals[3] = lw.w;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) valid[r] = (row0 + r) < n;
+    }
+    block_max_sumexp_finalize<PF_THREADS, 4>(vals, valid, block_max, block_sum, ticket, stats);
+}
+
+extern "C" int gse_loglik_max(gse_ctx* ctx, const float* loglik_dev, int64_t n, double* stats_dev, void* stream) {
+    GSE_REQUIRE(ctx != NULL && stats_dev != NULL, "ctx / stats is NULL");
+    GSE_REQUIRE(n >= 1 && n <= ctx->n_max, "n out of range for this context");
+    GSE_REQUIRE(loglik_dev != NULL && aligned16(loglik_dev), "loglik must be 16-byte aligned");
+    const unsigned blocks = (unsigned)gse_div_up(gse_div_up(n, ROWS_PER_THREAD), PF_THREADS);
+    k_loglik_max<<<blocks, PF_THREADS, 0, (cudaStream_t)stream>>>(loglik_dev, n, ctx->block_max, ctx->block_sum,
+                                                                   ctx->ticket, stats_dev);
+    GSE_CHECK_LAUNCH(ctx);
+    return GSE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weights read-back: base * exp(loglik) * scale in float64 (the reference's `weights` attribute)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_weights_linear(const float* __restrict__ loglik, const double* __restrict__ base,
+                                 int64_t n, double scale, double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double w = scale;
+    if (loglik) w *= exp((double)loglik[i]);
+    if (base) w *= base[i];
+    out[i] = w;
+}
+
+extern "C" int gse_weights_linear(gse_ctx* ctx, const float* loglik_dev, const double* base_dev, int64_t n,
+                                  double scale, double* out_dev, void* stream) {
+    GSE_REQUIRE(ctx != NULL && out_dev != NULL, "ctx / out is NULL");
+    GSE_REQUIRE(n >= 0, "n < 0");
+    if (n == 0) return GSE_OK;
+    k_weights_linear<<<(unsigned)gse_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(loglik_dev, base_dev, n, scale, out_dev);
+    GSE_CHECK_LAUNCH(ctx);
+    return GSE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6: weighted moments about a pivot row, float64 accumulation, fixed-order two-level reduction.
+// out: [0] S0, [1..5] S1, [6..20] S2 lower triangle, [21..25] pivot; (GSF: [26..40] sum w P)
+// ------------------------------------------------------------------------------------------------
+#define MOM_THREADS 256
+template <int NEXTRA>
+__global__ void __launch_bounds__(MOM_THREADS)
+k_moments(const float* __restrict__ x, const float* __restrict__ extra, int64_t ld, int64_t n,
+          const float* __restrict__ loglik, const double* __restrict__ base,
+          const double* __restrict__ stats, double* partials, unsigned int* ticket, double* out) {
+    constexpr int NV = 21 + NEXTRA;
+    const float M = (float)stats[0];
+    float p[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) p[j] = __ldg(x + j * ld);
+    double acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+    const int64_t groups = (n + 3) / 4;
+    for (int64_t g = (int64_t)blockIdx.x * MOM_THREADS + threadIdx.x; g < groups; g += (int64_t)gridDim.x * MOM_THREADS) {
+        const int64_t row0 = g * 4;
+        float4 c[5];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) c[j] = ld_stream4(x + j * ld + row0);
+        float4 lw = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (loglik) lw = ld_stream4(loglik + row0);
+        const float l[4] = {lw.x, lw.y, lw.z, lw.w};
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            if (row0 + r < n) {
+                double w = loglik ? (double)__expf(l[r] - M) : 1.0;
+                if (base) w *= base[row0 + r];
+                double d[5];
+#pragma unroll
+                for (int j = 0; j < 5; ++j) d[j] = (double)(reinterpret_cast<const float*>(&c[j])[r] - p[j]);
+                acc[0] += w;
+                int t = 6;
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    const double wd = w * d[j];
+                    acc[1 + j] += wd;
+#pragma unroll
+                    for (int k = 0; k <= j; ++k) { acc[t] = fma(wd, d[k], acc[t]); ++t; }
+                }
+                if (NEXTRA > 0) {
+#pragma unroll
+                    for (int k = 0; k < NEXTRA; ++k) acc[21 + k] = fma(w, (double)extra[k * ld + row0 + r], acc[21 + k]);
+                }
+            }
+        }
+    }
+    __shared__ double s_part[MOM_THREADS / 32][NV];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const double v = warp_sum(acc[k]);
+        if (lane == 0) s_part[wid][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < MOM_THREADS / 32; ++w) t += s_part[w][threadIdx.x];
+        partials[(size_t)blockIdx.x * NV + threadIdx.x] = t;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x < NV) {
+        double t = 0.0;
+        for (unsigned int b = 0; b < gridDim.x; ++b) t += __ldcg(partials + (size_t)b * NV + threadIdx.x);
+        out[threadIdx.x < 21 ? threadIdx.x : threadIdx.x + 5] = t;
+    }
+    if (threadIdx.x < 5) out[21 + threadIdx.x] = (double)p[threadIdx.x];
+    if (threadIdx.x == 0) *ticket = 0u;
+}
+
+static int launch_moments(gse_ctx* ctx, const float* x, const float* extra, int64_t ld, int64_t n,
+                          const float* loglik, const double* base, const double* stats, double* out,
+                          void* stream) {
+    GSE_REQUIRE(ctx != NULL && stats != NULL && out != NULL, "ctx / stats / out is NULL");
+    GSE_REQUIRE(n >= 1 && n <= ctx->n_max, "n out of range for this context");
+    CHECK_SOA(x, ld, n);
+    const int64_t groups = gse_div_up(n, 4);
+    int64_t blocks = gse_div_up(groups, MOM_THREADS);
+    const int64_t cap = (int64_t)ctx->num_sms * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks > 2048) blocks = 2048;
+    if (extra)
+        k_moments<15><<<(unsigned)blocks, MOM_THREADS, 0, (cudaStream_t)stream>>>(x, extra, ld, n, loglik, base, stats, ctx->red_partials, ctx->ticket + 2, out);
+    else
+        k_moments<0><<<(unsigned)blocks, MOM_THREADS, 0, (cudaStream_t)stream>>>(x, NULL, ld, n, loglik, base, stats, ctx->red_partials, ctx->ticket + 2, out);
+    GSE_CHECK_LAUNCH(ctx);
+    return GSE_OK;
+}
+
+extern "C" int gse_pf_moments(gse_ctx* ctx, const float* x_dev, int64_t ld, int64_t n, const float* loglik_dev,
+                              const double* base_dev, const double* stats_dev, double* out_dev, void* stream) {
+    return launch_moments(ctx, x_dev, NULL, ld, n, loglik_dev, base_dev, stats_dev, out_dev, stream);
+}
+
+extern "C" int gse_gsf_moments(gse_ctx* ctx, const float* mean_dev, const float* cov_dev, int64_t ld, int64_t n,
+                               const float* loglik_dev, const double* base_dev, const double* stats_dev,
+                               double* out_dev, void* stream) {
+    GSE_REQUIRE(cov_dev != NULL, "cov is NULL");
+    return launch_moments(ctx, mean_dev, cov_dev, ld, n, loglik_dev, base_dev, stats_dev, out_dev, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// stand-alone mixture pdf (MultivariateGaussianSum.pdf, :39-63): float64 throughout, not a hot path
+// ------------------------------------------------------------------------------------------------
+__global__ void k_mixture_pdf(const float* __restrict__ x, int64_t ld, int64_t n,
+                              const __grid_constant__ MixDensityN md, double* __restrict__ out, int log_out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double xv[GSE_NX];
+    for (int j = 0; j < md.nx; ++j) xv[j] = (double)x[j * ld + i];
+    double a[GSE_MAX_ND];
+    double m = -1.0e300;
+    for (int d = 0; d < md.nd; ++d) {
+        double q = 0.0;
+        for (int r = 0; r < md.nx; ++r) {
+            double t = 0.0;
+            for (int c = 0; c < md.nx; ++c) t += md.P[d][r * md.nx + c] * (xv[c] - md.mean[d][c]);
+            q += (xv[r] - md.mean[d][r]) * t;
+        }
+        a[d] = md.logc[d] - 0.5 * q;
+        m = fmax(m, a[d]);
+    }
+    double s = 0.0;
+    for (int d = 0; d < md.nd; ++d) s += exp(a[d] - m);
+    const double lp = m + log(s);
+    out[i] = log_out ? lp : exp(lp);
+}
+
+extern "C" int gse_mixture_pdf(gse_ctx* ctx, const gse_mixture* mix, const float* x_dev, int64_t ld, int64_t n,
+                               double* out_dev, int log_out, void* stream) {
+    GSE_REQUIRE(ctx != NULL && x_dev != NULL && out_dev != NULL, "ctx / x / out is NULL");
+    GSE_REQUIRE(n >= 0 && ld >= n, "n / ld out of range");
+    if (n == 0) return GSE_OK;
+    MixDensityN md;
+    int rc = gse_build_densityN(mix, &md);
+    if (rc) return rc;
+    k_mixture_pdf<<<(unsigned)gse_div_up(n, 128), 128, 0, (cudaStream_t)stream>>>(x_dev, ld, n, md, out_dev, log_out);
+    GSE_CHECK_LAUNCH(ctx);
+    return GSE_OK;
+}

@@ -1,0 +1,253 @@
+"""Shared host-side plumbing of the two filters: the library context, the weight representation
+and the systematic resample (scan -> merge-path partition -> fused search + gather).
+
+Weights.  The reference keeps linear-domain weights (float32, float64 after the first resample,
+SURVEY.md quirk Q3) and multiplies pdf values into them, which underflows for informative
+measurements.  Here a weight is  ``base_scale * base_k * exp(loglik_k)``:
+
+* ``loglik`` -- float32 device array, the log pdf accumulated by ``update`` since the last reset;
+* ``base``   -- ``None`` (all ones) or a float64 device array holding weights a caller ASSIGNED
+  (``p.weights = w``, results/pf_openloop/pf_run_seq.py:124-125) exactly as given, so that a
+  resample of assigned weights works on the caller's float64 values bit for bit;
+* ``base_scale`` -- Python float, ``1/N`` after construction / resample (particle.py:50,103).
+
+The ``weights`` attribute materialises the reference's un-normalised linear weights on demand.
+"""
+import ctypes
+
+import numpy
+import torch
+
+from gpu_se_b200 import _device, _lib
+
+
+class Context:
+    """Owns a gse_ctx (include/gse.h: gse_ctx_create / gse_ctx_destroy)."""
+
+    def __init__(self, device, n_max, state_pdf, measurement_pdf):
+        self.device = _device.resolve_device(device)
+        state = (state_pdf.as_gse_mixture() if state_pdf is not None else
+                 _lib.make_mixture(numpy.zeros((1, 5)), numpy.eye(5)[None], numpy.ones(1)))
+        meas = (measurement_pdf.as_gse_mixture() if measurement_pdf is not None else
+                _lib.make_mixture(numpy.zeros((1, 2)), numpy.eye(2)[None], numpy.ones(1)))
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib.gse_ctx_create(self.device.index, _lib.GSE_MODEL_BIOREACTOR, int(n_max),
+                                               ctypes.byref(state), ctypes.byref(meas), ctypes.byref(handle)))
+        self.handle = handle
+        self.n_max = int(n_max)
+
+    @property
+    def launches(self):
+        return int(_lib.lib.gse_launch_count(self.handle))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            _lib.lib.gse_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def mixture_view(pdf):
+    """Accept the reference's own MultivariateGaussianSum objects (or anything with
+    means / covariances / weights) as well as this package's."""
+    if hasattr(pdf, "as_gse_mixture"):
+        return pdf
+    from gpu_se_b200.gaussian_sum_dist import MultivariateGaussianSum
+    cov = getattr(pdf, "_covariances64", None)
+    if cov is None:
+        inv = getattr(pdf, "_inverse_covariances", None)      # the reference keeps float64 only here (:33)
+        cov = numpy.linalg.inv(_device.to_numpy(inv)) if inv is not None else _device.to_numpy(pdf.covariances)
+    return MultivariateGaussianSum(_device.to_numpy(pdf.means), cov, _device.to_numpy(pdf.weights))
+
+
+class WeightedEnsemble:
+    """N weighted rows of an SoA float32 state of NCOLS columns, with systematic resampling."""
+
+    NCOLS = 5
+
+    def _init_ensemble(self, N, state_pdf, measurement_pdf, device, seed):
+        self.N_particles = int(N)
+        if self.N_particles < 1:
+            raise ValueError("N_particles must be >= 1")
+        self.state_pdf = state_pdf
+        self.measurement_pdf = measurement_pdf
+        self._state_mix = mixture_view(state_pdf)
+        self._meas_mix = mixture_view(measurement_pdf)
+        self._ctx = Context(device, self.N_particles, self._state_mix, self._meas_mix)
+        self.device = self._ctx.device
+        n = self.N_particles
+        self._ld = _device.round_up(n, 64)
+        dev = self.device
+        self._state = torch.zeros((self.NCOLS, self._ld), dtype=torch.float32, device=dev)
+        self._state_alt = torch.zeros((self.NCOLS, self._ld), dtype=torch.float32, device=dev)
+        self._loglik = torch.zeros(self._ld, dtype=torch.float32, device=dev)
+        self._base = None
+        self._base_max = None
+        self._base_scale = 1.0 / n
+        self._loglik_dirty = False
+        self._stats = torch.tensor([0.0, float(n), 0.0, 0.0], dtype=torch.float64, device=dev)
+        self._stats_uniform = self._stats.clone()
+        self._cumsum = torch.zeros(self._ld, dtype=torch.int64, device=dev)      # uint64 payload
+        self._offtot = torch.zeros(2, dtype=torch.int64, device=dev)             # [offset, total]
+        self._mom = torch.zeros(48, dtype=torch.float64, device=dev)
+        self._mom_host = torch.zeros(48, dtype=torch.float64).pin_memory()
+        self._mom_valid = False
+        self._seed = int(seed) if seed is not None else int(numpy.random.randint(0, 2 ** 31 - 1))
+        self._step = 0
+        self.last_sample_index = None
+
+    # -- helpers -------------------------------------------------------------------------
+    def _stream(self):
+        return _device.stream_ptr(self.device)
+
+    def _touch(self):
+        self._mom_valid = False
+
+    def _host_noise(self, pdf, shape):
+        """Noise rows for the host-noise mode when the state pdf is a deterministic test double."""
+        if hasattr(pdf, "draw_host"):
+            return numpy.asarray(pdf.draw_host(shape), dtype=numpy.float32)
+        return None
+
+    # -- weights -------------------------------------------------------------------------
+    @property
+    def weights(self):
+        n = self.N_particles
+        out = torch.empty(n, dtype=torch.float64, device=self.device)
+        _lib.check(_lib.lib.gse_weights_linear(
+            self._ctx.handle, self._loglik.data_ptr(), self._base.data_ptr() if self._base is not None else None,
+            n, float(self._base_scale), out.data_ptr(), self._stream()))
+        return _device.wrap(out)
+
+    @weights.setter
+    def weights(self, w):
+        n = self.N_particles
+        if isinstance(w, torch.Tensor):
+            w = w.detach().as_subclass(torch.Tensor).to(device=self.device, dtype=torch.float64).reshape(-1)
+        else:
+            w = torch.as_tensor(numpy.ascontiguousarray(_device.to_numpy(w), dtype=numpy.float64).reshape(-1),
+                                device=self.device)
+        if w.numel() != n:
+            raise ValueError("weights must have %d entries" % n)
+        self._base = w.contiguous().clone()
+        self._base_max = self._base.max()
+        self._base_scale = 1.0
+        self._loglik.zero_()
+        self._loglik_dirty = False
+        self._stats[0] = 0.0
+        self._stats[1] = self._base.sum()
+        self._touch()
+
+    def _reset_uniform(self):
+        self._base = None
+        self._base_max = None
+        self._base_scale = 1.0 / self.N_particles
+        self._loglik_dirty = False
+        self._stats.copy_(self._stats_uniform)
+
+    def _after_update(self):
+        self._loglik_dirty = True
+        self._touch()
+
+    # -- resample ------------------------------------------------------------------------
+    def _scan(self):
+        """cumsum of the fixed-point weights -> self._cumsum, total -> self._offtot[1]."""
+        n = self.N_particles
+        use_loglik = self._base is None or self._loglik_dirty
+        stats = self._stats
+        if self._base is not None and self._loglik_dirty:
+            # S bounds sum exp(loglik - M); the scale must bound sum base * exp(loglik - M)
+            stats = self._stats.clone()
+            stats[1] = stats[1] * self._base_max
+        _lib.check(_lib.lib.gse_scan_weights(
+            self._ctx.handle, self._loglik.data_ptr() if use_loglik else None,
+            self._base.data_ptr() if self._base is not None else None, stats.data_ptr(), n,
+            self._cumsum.data_ptr(), self._offtot.data_ptr() + 8, self._stream()))
+
+    def resample(self, r=None, return_index=False):
+        """Systematic resample (particle.py:85-103 / gs_ukf.py:151-171).  ``r`` defaults to
+        ``numpy.random.rand()`` exactly as the reference's CPU path draws it (:93), so seeding
+        numpy reproduces the reference's offset."""
+        n = self.N_particles
+        if r is None:
+            r = numpy.random.rand()
+        r = float(r)
+        self._scan()
+        idx = torch.empty(n, dtype=torch.int64, device=self.device) if return_index else None
+        _lib.check(_lib.lib.gse_resample_gather(
+            self._ctx.handle, self._cumsum.data_ptr(), n, self._offtot.data_ptr(), r, n, 0, n,
+            self._state.data_ptr(), self._ld, self._state_alt.data_ptr(), self._ld, self.NCOLS,
+            self._loglik.data_ptr(), idx.data_ptr() if idx is not None else None, self._stream()))
+        self._state, self._state_alt = self._state_alt, self._state
+        self._reset_uniform()
+        self._touch()
+        self.last_sample_index = idx
+        return idx
+
+    def cumulative_weights(self):
+        """(cumsum uint64 as numpy, total) of the current weights -- test / diagnostics hook."""
+        self._scan()
+        c = self._cumsum[:self.N_particles].cpu().numpy().view(numpy.uint64)
+        return c, int(c[-1])
+
+    # -- moments -------------------------------------------------------------------------
+    def _launch_moments(self):
+        raise NotImplementedError
+
+    def _moments(self):
+        if not self._mom_valid:
+            self._launch_moments()
+            self._mom[41:43].copy_(self._stats[0:2])        # M, S ride along in the same read-back
+            self._mom_host.copy_(self._mom, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            self._mom_np = self._mom_host.numpy().copy()
+            self._mom_valid = True
+        return self._mom_np
+
+    def _weight_prefactor(self, mom):
+        """A with  true weight_k = A * w_k,  w_k = base_k * exp(loglik_k - M)  the kernel's weights."""
+        return self._base_scale * float(numpy.exp(self._M_host(mom)))
+
+    def _M_host(self, mom):
+        return float(mom[41])
+
+    @staticmethod
+    def _unpack_sym(v):
+        m = numpy.zeros((5, 5))
+        t = 0
+        for i in range(5):
+            for j in range(i + 1):
+                m[i, j] = m[j, i] = v[t]
+                t += 1
+        return m
+
+    def _estimate_parts(self):
+        mom = self._moments()
+        S0, S1, S2 = mom[0], mom[1:6], self._unpack_sym(mom[6:21])
+        p = mom[21:26]
+        A = self._weight_prefactor(mom)
+        return mom, S0, S1, S2, p, A
+
+    def point_estimate(self, normalised=False):
+        """``weights @ particles`` with the reference's un-normalised weights (quirk Q4); pass
+        ``normalised=True`` for the weighted mean."""
+        mom, S0, S1, S2, p, A = self._estimate_parts()
+        if normalised:
+            return p + S1 / S0
+        return A * (S0 * p + S1)
+
+    def _scatter_about(self, normalised):
+        mom, S0, S1, S2, p, A = self._estimate_parts()
+        if normalised:
+            d = S1 / S0
+            return (S2 / S0 - numpy.outer(d, d)), mom, 1.0 / S0
+        mu = A * (S0 * p + S1)                 # the reference centres on the un-normalised estimate (:111)
+        d = mu - p
+        cov = A * (S2 - numpy.outer(S1, d) - numpy.outer(d, S1) + S0 * numpy.outer(d, d))
+        return cov, mom, A

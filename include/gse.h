@@ -1,0 +1,206 @@
+/*
+ * gse.h -- C ABI of libgse_b200.so: the B200 (sm_100a) state-estimation hot path of gpu_se.
+ *
+ * The reference (AlgorithmicAmoeba/gpu_se) is pure Python and has no FFI of its own; the
+ * interface this library sits behind is the reference's filter-class API
+ *     filter/particle.py:43-114,151-327   ParticleFilter / ParallelParticleFilter
+ *     filter/gs_ukf.py:45-183,223-449     (Parallel)GaussianSumUnscentedKalmanFilter
+ *     gaussian_sum_dist/MultivariateGaussianSum.py:27-97
+ * Each entry point below names the reference lines whose work it replaces.  The Python classes in
+ * gpu_se_b200/ mirror the reference's constructors and methods and call these functions through
+ * ctypes (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative gse_status otherwise; gse_last_error()
+ *    returns a thread-local message for the last failure.
+ *  - pointers named *_dev are raw DEVICE pointers owned by the caller (the Python side allocates
+ *    them as torch tensors); the library allocates nothing but the small per-context workspace.
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises.
+ *  - particle / component state is struct-of-arrays float32: column c of n rows starts at
+ *    base + c*ld  (ld = leading dimension in elements, a multiple of 4 so that every column is
+ *    16-byte aligned; base 16-byte aligned).
+ *  - weights are kept as a float32 log-likelihood array `loglik` (sum of log pdf values since the
+ *    last reset) times an optional float64 base weight array `base` (NULL = uniform):
+ *        weight_k  proportional to  base_k * exp(loglik_k)
+ *    `stats_dev` is 4 doubles: [0] = M = max_k loglik_k, [1] = S = sum_k exp(loglik_k - M)
+ *    (both written by the update kernels and gse_loglik_max, consumed by scan / moments; the
+ *    sharded driver all-reduces them between the two), [2..3] reserved.
+ *  - one context per GPU/filter; a context is not thread-safe; distinct contexts are independent.
+ */
+#ifndef GSE_H_
+#define GSE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSE_ABI_VERSION 1
+
+#define GSE_NX 5        /* states  (Cg, Cx, Cfa, Ce, Ch)   model/BioreactorModel.py:191 */
+#define GSE_NU 2        /* inputs  (Fg_in, Fm_in)          model/BioreactorModel.py:195 */
+#define GSE_NY 2        /* outputs (Cg*180, Cfa*116)       model/BioreactorModel.py:251-253 */
+#define GSE_NSIGMA 11   /* 2*Nx+1 sigma points             filter/gs_ukf.py:61 */
+#define GSE_NCOV 15     /* lower triangle of a 5x5 covariance, row-major (00,10,11,20,21,22,...) */
+#define GSE_MAX_ND 8    /* mixture components supported */
+
+#define GSE_MODEL_BIOREACTOR 1   /* Bioreactor.homeostatic_DEs / static_outputs */
+
+typedef enum gse_status {
+    GSE_OK = 0,
+    GSE_EINVAL = -1,      /* bad argument (null pointer, misaligned, n out of range ...) */
+    GSE_ECUDA = -2,       /* a CUDA runtime call or launch failed; see gse_last_error() */
+    GSE_ENOMEM = -3,
+    GSE_ELINALG = -4      /* mixture covariance not positive definite */
+} gse_status;
+
+/* Gaussian-sum parameters as the reference holds them
+ * (MultivariateGaussianSum.__init__, MultivariateGaussianSum.py:27-37): row-major
+ * means (nd, nx), covs (nd, nx, nx), weights (nd).  nx is 5 for state mixtures, 2 for the
+ * measurement mixture. */
+typedef struct gse_mixture {
+    int32_t nd;
+    int32_t nx;
+    double weights[GSE_MAX_ND];
+    double means[GSE_MAX_ND * GSE_NX];
+    double covs[GSE_MAX_ND * GSE_NX * GSE_NX];
+} gse_mixture;
+
+typedef struct gse_ctx gse_ctx;
+
+int gse_abi_version(void);
+const char* gse_last_error(void);
+
+/* Context: mixture constants (inverse covariances, normalising constants as
+ * MultivariateGaussianSum.py:33-37; Cholesky factors for sampling) + scan/reduction workspace
+ * for up to n_max rows.  `state` is the process-noise mixture (nx = 5), `meas` the measurement
+ * noise mixture (nx = 2).  Replaces the JIT of f/g in ParallelParticleFilter.__init__
+ * (particle.py:151-208): f and g are compiled in, selected by model_id. */
+int gse_ctx_create(int device, int model_id, int64_t n_max, const gse_mixture* state,
+                   const gse_mixture* meas, gse_ctx** out);
+int gse_ctx_destroy(gse_ctx* ctx);
+
+/* ---- sampling / density of a Gaussian sum (MultivariateGaussianSum.py:39-97) ---------------- */
+
+/* x[c*ld + i] = sample i of `mix` (nx = 5), i in [0, n): Philox4x32-10 stream keyed by
+ * (seed; counter = (index0 + i, step, subsequence)).  Replaces x0.draw(N) in
+ * ParticleFilter.__init__ (particle.py:49) and MultivariateGaussianSum.draw (:65-97); rows are
+ * NOT grouped by component (quirk Q5 of SURVEY.md is not reproduced). */
+int gse_mixture_draw(gse_ctx* ctx, const gse_mixture* mix, float* x_dev, int64_t ld, int64_t n,
+                     uint64_t seed, uint64_t step, int64_t index0, void* stream);
+
+/* out[i] = pdf of `mix` at row i of the SoA points x (nx columns), float64
+ * (MultivariateGaussianSum.pdf, :39-63).  log_out != 0 writes log pdf instead. */
+int gse_mixture_pdf(gse_ctx* ctx, const gse_mixture* mix, const float* x_dev, int64_t ld,
+                    int64_t n, double* out_dev, int log_out, void* stream);
+
+/* ---- particle filter ------------------------------------------------------------------------ */
+
+/* predict (particle.py:54-67 / :265-277): x_i += f(x_i, u, dt) [n_sub explicit-Euler sub-steps of
+ * dt/n_sub; the reference has n_sub = 1], then x_i += state noise.
+ * noise_dev == NULL: noise drawn in-kernel (Philox, counter = (index0 + i, step)).
+ * noise_dev != NULL: SoA (5, ld_noise) float32 host-supplied draws are added instead (the
+ * DeterministicGaussianSum cross-check mode, DeterministicGaussianSum.py:32-65). */
+int gse_pf_predict(gse_ctx* ctx, float* x_dev, int64_t ld, int64_t n, const double u[GSE_NU],
+                   double dt, int n_sub, uint64_t seed, uint64_t step, int64_t index0,
+                   const float* noise_dev, int64_t ld_noise, void* stream);
+
+/* update (particle.py:69-83 / :279-294): loglik_i += log pdf_meas(z - g(x_i, u));
+ * stats_dev[0] = max_i loglik_i, stats_dev[1] = sum_i exp(loglik_i - max). */
+int gse_pf_update(gse_ctx* ctx, const float* x_dev, int64_t ld, int64_t n, float* loglik_dev,
+                  const double u[GSE_NU], const double z[GSE_NY], double* stats_dev, void* stream);
+
+/* point_estimate + point_covariance in one pass (particle.py:105-114 / :318-327):
+ * out_dev[0] = S = sum_i w_i, out_dev[1..5] = sum_i w_i x_i, out_dev[6..20] = lower triangle of
+ * sum_i w_i (x_i - p)(x_i - p)' with pivot p = out_dev[21..25] (written by the kernel: row 0),
+ * where w_i = base_i * exp(loglik_i - stats_dev[0]).  26 doubles. */
+int gse_pf_moments(gse_ctx* ctx, const float* x_dev, int64_t ld, int64_t n,
+                   const float* loglik_dev, const double* base_dev, const double* stats_dev,
+                   double* out_dev, void* stream);
+
+/* ---- weights and systematic resampling (shared by PF and GS-UKF) ------------------------------ */
+
+/* stats_dev[0] = max_i loglik_i, stats_dev[1] = sum_i exp(loglik_i - max) (for callers that set
+ * loglik themselves). */
+int gse_loglik_max(gse_ctx* ctx, const float* loglik_dev, int64_t n, double* stats_dev,
+                   void* stream);
+
+/* out[i] = base_i * exp(loglik_i) * scale in float64: the reference's (un-normalised) `weights`
+ * attribute (particle.py:50,83).  base_dev NULL = 1. */
+int gse_weights_linear(gse_ctx* ctx, const float* loglik_dev, const double* base_dev, int64_t n,
+                       double scale, double* out_dev, void* stream);
+
+/* cumsum (particle.py:89 / :301-303, numpy.cumsum / torch.cumsum): inclusive scan of the
+ * fixed-point weights  q_i = rint(base_i * exp(loglik_i - stats_dev[0]) * 2^s)  into uint64
+ * cumsum_dev, with s = 61 - ceil(log2(stats_dev[1])) so that the total stays below 2^62
+ * (stats_dev[1] >= sum_i base_i * exp(loglik_i - stats_dev[0]); the update kernels write it).
+ * Integer addition is associative, so the result does not depend on the scan structure, the
+ * launch geometry or the number of GPUs.  loglik_dev may be NULL (weights = base; the caller
+ * then sets stats_dev[1] = sum base).  total_dev[0] receives cumsum[n-1] (NULL to skip). */
+int gse_scan_weights(gse_ctx* ctx, const float* loglik_dev, const double* base_dev,
+                     const double* stats_dev, int64_t n, uint64_t* cumsum_dev,
+                     uint64_t* total_dev, void* stream);
+
+/* Systematic resample of outputs [out0, out0 + n_out) of n_total from the local cumulative
+ * weights (particle.py:92-100; the reference GPU kernel _parallel_resample, :223-263, differs
+ * only on exact ties -- the CPU comparison `cumsum[k] < u` is the one followed):
+ *     u_i   = (i + r) / n_total                                  (float64, as the reference)
+ *     idx_i = min{ k : (offset + cumsum[k]) / total >= u_i }     (float64 divide, as `cumsum /= cumsum[-1]`)
+ * evaluated exactly through integer thresholds.  For every output: dst[:, i - out0] =
+ * src[:, idx_i] for ncols SoA columns (particles[sample_index], :102 / :315), loglik_out = 0
+ * (weights reset, :103 / :316; pass NULL to skip), idx_out (int64, NULL to skip) = idx_i.
+ * offset/total are read from offtot_dev[0..1] (uint64; the sharded driver writes the exclusive
+ * prefix of the shard totals and the global total there). */
+int gse_resample_gather(gse_ctx* ctx, const uint64_t* cumsum_dev, int64_t n_src,
+                        const uint64_t* offtot_dev, double r, int64_t n_total, int64_t out0,
+                        int64_t n_out, const float* src_dev, int64_t ld_src, float* dst_dev,
+                        int64_t ld_dst, int ncols, float* loglik_out_dev, int64_t* idx_out_dev,
+                        void* stream);
+
+/* Number of outputs i in [0, n_total) whose u_i maps at or below integer cumulative weight
+ * `bound` of `total`, i.e. #{ i : fl(fl(bound)/fl(total)) >= u_i }: host helper used by the sharded
+ * driver to split the output range between shards with the device's exact predicate. */
+int64_t gse_count_outputs_below(uint64_t bound, uint64_t total, double r, int64_t n_total);
+
+/* Host evaluation of the device's threshold q*(u) = min{ C : fl(fl(C)/fl(total)) >= u } (the same
+ * inline function the kernels use); exported for the parity tests. */
+uint64_t gse_threshold_u64(double u, uint64_t total);
+
+/* ---- Gaussian-sum unscented Kalman filter ------------------------------------------------------ */
+
+/* State: means SoA (5, ld), covariances SoA (15, ld) lower triangles, loglik (n).
+ *
+ * predict (gs_ukf.py:82-103 / :348-367): Cholesky (retry +1e-10 I, :72-75), 11 sigma points
+ * mean +- L[:, j] (no scaling, quirk Q6), f on each, an independent state-noise draw per sigma
+ * point (:99), weighted mean (numpy.average) and weighted scatter.  noise_dev != NULL: host noise,
+ * SoA (55, ld_noise) with row s*5 + j = component j of sigma point s. */
+int gse_gsf_predict(gse_ctx* ctx, float* mean_dev, float* cov_dev, int64_t ld, int64_t n,
+                    const double u[GSE_NU], double dt, uint64_t seed, uint64_t step,
+                    int64_t index0, const float* noise_dev, int64_t ld_noise, void* stream);
+
+/* update (gs_ukf.py:105-149 / :369-407): sigma points, g, P_xy, P_yy, K, mean/cov update,
+ * loglik_i += log pdf_meas(z - g(mean_i)); stats_dev[0] = max loglik. */
+int gse_gsf_update(gse_ctx* ctx, float* mean_dev, float* cov_dev, int64_t ld, int64_t n,
+                   float* loglik_dev, const double u[GSE_NU], const double z[GSE_NY],
+                   double* stats_dev, void* stream);
+
+/* sigma points (gs_ukf.py:69-80 / :332-346): out SoA (55, ld_out), row s*5 + j. */
+int gse_gsf_sigma_points(gse_ctx* ctx, const float* mean_dev, const float* cov_dev, int64_t ld,
+                         int64_t n, float* out_dev, int64_t ld_out, void* stream);
+
+/* point_estimate / point_covariance (gs_ukf.py:173-183 / :438-449): as gse_pf_moments on the
+ * means, plus out_dev[26..40] = sum_i w_i P_i (lower triangle).  41 doubles. */
+int gse_gsf_moments(gse_ctx* ctx, const float* mean_dev, const float* cov_dev, int64_t ld,
+                    int64_t n, const float* loglik_dev, const double* base_dev,
+                    const double* stats_dev, double* out_dev, void* stream);
+
+/* ---- introspection ------------------------------------------------------------------------------ */
+
+/* kernels launched by this context since creation (bench.py's gpu_launches). */
+int64_t gse_launch_count(const gse_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSE_H_ */

@@ -1,0 +1,81 @@
+"""Specification (numpy restatement) of the device sampler.  TEST INFRASTRUCTURE ONLY.
+
+This is not a restatement of reference code -- the reference draws its noise with
+numpy/cupy ``random.choice`` + ``multivariate_normal`` (MultivariateGaussianSum.py:79-95), which a
+counter-based in-kernel generator cannot and need not reproduce.  It restates
+THIS repo's sampler (csrc/gse_common.cuh: philox4x32_10, box_muller, draw_mixture5) so that the
+kernels' draws can be checked value by value:
+
+* Philox4x32-10: Salmon, Moraes, Dror, Shaw, "Parallel random numbers: as easy as 1, 2, 3", SC'11;
+  pinned by the Random123 known-answer vectors in tests/test_philox.py.
+* uniform: (x + 0.5) * 2^-32 in float32; Box-Muller with the angle folded to (-pi, pi].
+* draw layout for row ``index`` at ``step``, subsequence ``sub``:
+    A = philox(ctr=(index_lo, index_hi, step, 2*sub),   key=(seed_lo, seed_hi))
+    B = philox(ctr=(index_lo, index_hi, step, 2*sub+1), key=(seed_lo, seed_hi))
+    (z0, z1) = BM(A0, A1), (z2, z3) = BM(A2, A3), (z4, _) = BM(B0, B1), component from B2.
+"""
+import numpy
+
+M0, M1 = numpy.uint64(0xD2511F53), numpy.uint64(0xCD9E8D57)
+W0, W1 = 0x9E3779B9, 0xBB67AE85
+MASK = numpy.uint64(0xFFFFFFFF)
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Vectorised Philox4x32-10; counters are uint32 arrays (broadcastable), key two Python ints."""
+    c0, c1, c2, c3 = (numpy.asarray(c, dtype=numpy.uint64) & MASK for c in (c0, c1, c2, c3))
+    c0, c1, c2, c3 = numpy.broadcast_arrays(c0, c1, c2, c3)
+    k0, k1 = int(k0) & 0xFFFFFFFF, int(k1) & 0xFFFFFFFF
+    for _ in range(10):
+        p0 = M0 * c0
+        p1 = M1 * c2
+        n0 = (p1 >> numpy.uint64(32)) ^ c1 ^ numpy.uint64(k0)
+        n2 = (p0 >> numpy.uint64(32)) ^ c3 ^ numpy.uint64(k1)
+        c1 = p1 & MASK
+        c3 = p0 & MASK
+        c0, c2 = n0 & MASK, n2 & MASK
+        k0 = (k0 + W0) & 0xFFFFFFFF
+        k1 = (k1 + W1) & 0xFFFFFFFF
+    return (c0.astype(numpy.uint32), c1.astype(numpy.uint32), c2.astype(numpy.uint32), c3.astype(numpy.uint32))
+
+
+def u32_to_unit(x):
+    x = numpy.asarray(x, dtype=numpy.uint32).astype(numpy.float32)     # round-to-nearest like I2F
+    return (x.astype(numpy.float64) * 2.0 ** -32 + 2.0 ** -33).astype(numpy.float32)   # one fma rounding
+
+
+def box_muller(a, b):
+    u1 = u32_to_unit(a).astype(numpy.float64)
+    u2 = u32_to_unit(b).astype(numpy.float64)
+    r = numpy.sqrt(-2.0 * numpy.log(u1))
+    th = (u2 * numpy.float64(numpy.float32(6.2831853071795865))
+          - numpy.float64(numpy.float32(3.1415926535897932))).astype(numpy.float32).astype(numpy.float64)
+    return r * numpy.cos(th), r * numpy.sin(th)
+
+
+def standard_normals5(index, step, sub, seed):
+    """(n, 5) float64 standard normals and (n,) float32 component uniforms for rows ``index``."""
+    index = numpy.asarray(index, dtype=numpy.uint64)
+    lo, hi = index & MASK, index >> numpy.uint64(32)
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    A = philox4x32_10(lo, hi, numpy.uint64(step & 0xFFFFFFFF), numpy.uint64(2 * sub), k0, k1)
+    B = philox4x32_10(lo, hi, numpy.uint64(step & 0xFFFFFFFF), numpy.uint64(2 * sub + 1), k0, k1)
+    z0, z1 = box_muller(A[0], A[1])
+    z2, z3 = box_muller(A[2], A[3])
+    z4, _ = box_muller(B[0], B[1])
+    return numpy.stack([z0, z1, z2, z3, z4], axis=-1), u32_to_unit(B[2])
+
+
+def draw_mixture5(means, covariances, weights, index, step, sub, seed):
+    """(n, 5) float64 samples the device sampler produces for these rows (up to MUFU rounding)."""
+    means = numpy.asarray(means, dtype=numpy.float32).astype(numpy.float64)
+    covs = numpy.asarray(covariances, dtype=numpy.float32).astype(numpy.float64)
+    w = numpy.asarray(weights, dtype=numpy.float32).astype(numpy.float64)
+    cdf = (numpy.cumsum(w / w.sum())).astype(numpy.float32)
+    cdf[-1] = 1.0
+    z, uc = standard_normals5(index, step, sub, seed)
+    comp = numpy.zeros(z.shape[0], dtype=numpy.int64)
+    for d in range(len(w) - 1):
+        comp += (uc > cdf[d]).astype(numpy.int64)
+    L = numpy.linalg.cholesky(covs).astype(numpy.float32).astype(numpy.float64)
+    return means[comp] + numpy.einsum('nij,nj->ni', L[comp], z), comp

@@ -1,0 +1,71 @@
+"""The C-ABI library loads and exports every symbol include/gse.h declares; argument validation of
+the entry points that can be exercised without a GPU.  CPU only (no compute calls)."""
+import ctypes
+import os
+import re
+
+import numpy
+import pytest
+
+from conftest import ROOT
+
+
+def declared_functions():
+    text = open(os.path.join(ROOT, "include", "gse.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gse_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from gpu_se_b200 import _lib
+    names = declared_functions()
+    assert len(names) >= 18
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in names:
+        assert hasattr(raw, name), "libgse_b200.so does not export %s" % name
+    # the ctypes signature table covers exactly the header
+    assert sorted(_lib.SIGNATURES) == names
+    assert _lib.lib.gse_abi_version() == _lib.GSE_ABI_VERSION
+
+
+def test_struct_layout_matches_header():
+    from gpu_se_b200 import _lib
+    assert ctypes.sizeof(_lib.gse_mixture) == 8 + 8 * (8 + 40 + 200)
+    m = _lib.make_mixture(numpy.zeros((2, 5)), numpy.stack([numpy.eye(5)] * 2), [0.75, 0.25])
+    assert (m.nd, m.nx) == (2, 5) and m.weights[1] == 0.25 and m.covs[25 + 6] == 1.0
+    with pytest.raises(ValueError):
+        _lib.make_mixture(numpy.zeros((9, 5)), numpy.stack([numpy.eye(5)] * 9), numpy.ones(9))
+
+
+def test_missing_library_fails_loudly(tmp_path, monkeypatch):
+    from gpu_se_b200 import _lib
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.GseError, match="no CPU fallback"):
+        _lib._load()
+
+
+def test_unknown_model_is_rejected_without_fallback():
+    from gpu_se_b200.model.BioreactorModel import Bioreactor, model_id_for
+    assert model_id_for(Bioreactor.homeostatic_DEs, Bioreactor.static_outputs) == 1
+    with pytest.raises(NotImplementedError, match="no CPU fallback"):
+        model_id_for(lambda x, u, dt: x, lambda x, u: x)
+
+
+def test_no_gpu_means_error_not_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import gpu_se_b200 as g
+    sp = g.MultivariateGaussianSum(numpy.zeros((1, 5)), numpy.eye(5)[None], numpy.ones(1))
+    mp = g.MultivariateGaussianSum(numpy.zeros((1, 2)), numpy.eye(2)[None], numpy.ones(1))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        g.ParticleFilter(g.Bioreactor.homeostatic_DEs, g.Bioreactor.static_outputs, 16, sp, sp, mp)
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "gpu_se_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
