@@ -181,6 +181,15 @@ extern "C" int gse_ctx_create(int device, int model_id, int64_t n_max, const gse
     int rc = gse_build_sampler5(state, &c->state_sampler);
     if (rc == GSE_OK) rc = gse_build_density2(meas, &c->meas_density);
     if (rc != GSE_OK) { free(c); return rc; }
+    c->meas_density32.nd = c->meas_density.nd;
+    for (int d = 0; d < c->meas_density.nd; ++d) {
+        c->meas_density32.logc[d] = (float)c->meas_density.logc[d];
+        c->meas_density32.mean[d][0] = (float)c->meas_density.mean[d][0];
+        c->meas_density32.mean[d][1] = (float)c->meas_density.mean[d][1];
+        c->meas_density32.p00[d] = (float)c->meas_density.p00[d];
+        c->meas_density32.p01[d] = (float)c->meas_density.p01[d];
+        c->meas_density32.p11[d] = (float)c->meas_density.p11[d];
+    }
 
     // workspace: sized for the largest grid any kernel uses on n_max rows
     c->max_blocks = gse_div_up(n_max, 128) + 8;        // >= blocks of any kernel (GS-UKF: 128 components per block)
@@ -236,18 +245,19 @@ extern "C" int64_t gse_launch_count(const gse_ctx* ctx) { return ctx ? ctx->laun
 // i in [0, n_total) with q*(u_i) <= bound, i.e. those sourced at or below cumulative weight `bound`.
 extern "C" int64_t gse_count_outputs_below(uint64_t bound, uint64_t total, double r, int64_t n_total) {
     if (n_total <= 0 || total == 0) return 0;
-    const double Td = gse_u64_to_double(total);
     const double nd = (double)n_total;
+    const bool pow2 = (n_total & (n_total - 1)) == 0;
+    const double inv = 1.0 / nd;
     // q*(u_i) is non-decreasing in i: binary search for the first i with q*(u_i) > bound
     int64_t lo = 0, hi = n_total;
     while (lo < hi) {
         const int64_t mid = lo + ((hi - lo) >> 1);
-        const uint64_t q = gse_threshold(gse_sample_position(mid, r, nd), Td);
+        const uint64_t q = gse_threshold(gse_sample_position((double)mid, r, nd, inv, pow2), total);
         if (q <= bound) lo = mid + 1; else hi = mid;
     }
     return lo;
 }
 
 extern "C" uint64_t gse_threshold_u64(double u, uint64_t total) {
-    return gse_threshold(u, gse_u64_to_double(total));
+    return gse_threshold(u, total);
 }

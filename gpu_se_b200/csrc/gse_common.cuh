@@ -65,6 +65,14 @@ struct MixDensity2 {
     double p00[GSE_MAX_ND], p01[GSE_MAX_ND], p11[GSE_MAX_ND];   // inverse covariance; p01 = P01 + P10 (:33)
 };
 
+// float32 copy used by the particle-filter update kernel (see meas_logpdf32)
+struct MixDensity2f {
+    int nd;
+    float logc[GSE_MAX_ND];
+    float mean[GSE_MAX_ND][2];
+    float p00[GSE_MAX_ND], p01[GSE_MAX_ND], p11[GSE_MAX_ND];
+};
+
 // Generic density (nx <= 5) used by gse_mixture_pdf.
 struct MixDensityN {
     int nd, nx;
@@ -81,6 +89,7 @@ struct gse_ctx {
     int64_t launches;
     MixSampler5 state_sampler;
     MixDensity2 meas_density;
+    MixDensity2f meas_density32;
     // workspace
     void* ws;                 // one allocation, carved below
     size_t ws_bytes;
@@ -145,37 +154,80 @@ __device__ __forceinline__ float u32_to_unit(uint32_t x) {
 
 // Box-Muller with the MUFU approximations (lg2.approx, sin/cos.approx); the angle is folded to
 // (-pi, pi] where sin.approx / cos.approx are most accurate.
+__device__ __forceinline__ float mufu_sqrt(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float mufu_lg2(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float mufu_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float box_muller_radius(uint32_t a) {
+    // sqrt(-2 ln u1) = sqrt(lg2(u1) * (-2 ln 2))
+    return mufu_sqrt(mufu_lg2(u32_to_unit(a)) * -1.3862943611198906f);
+}
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
-    const float u1 = u32_to_unit(a);
-    const float u2 = u32_to_unit(b);
-    const float r = sqrtf(-2.0f * __logf(u1));
-    const float th = fmaf(u2, 6.2831853071795865f, -3.1415926535897932f);
-    float s, c;
-    __sincosf(th, &s, &c);
-    z0 = r * c;
-    z1 = r * s;
+    const float r = box_muller_radius(a);
+    const float th = fmaf(u32_to_unit(b), 6.2831853071795865f, -3.1415926535897932f);
+    z0 = r * __cosf(th);
+    z1 = r * __sinf(th);
+}
+__device__ __forceinline__ float box_muller_cos(uint32_t a, uint32_t b) {
+    const float th = fmaf(u32_to_unit(b), 6.2831853071795865f, -3.1415926535897932f);
+    return box_muller_radius(a) * __cosf(th);
 }
 
 // Five state-noise values for row `index` at `step`, subsequence pair (sub, sub+1).
 // Draw layout (restated in oracle/philox.py):
 //   A = philox(index_lo, index_hi, step, 2*sub)    -> (z0, z1) = BM(A.x, A.y), (z2, z3) = BM(A.z, A.w)
 //   B = philox(index_lo, index_hi, step, 2*sub+1)  -> (z4, _ ) = BM(B.x, B.y), component from B.z
-template <bool DIAG>
+template <bool DIAG, int ND>      // ND = 0: component count read from the sampler at run time
 __device__ __forceinline__ void draw_mixture5(const MixSampler5& sp, uint64_t index, uint32_t step,
                                               uint32_t sub, uint32_t k0, uint32_t k1, float out[5]) {
     const Philox4 A = philox4x32_10((uint32_t)index, (uint32_t)(index >> 32), step, 2u * sub, k0, k1);
     const Philox4 B = philox4x32_10((uint32_t)index, (uint32_t)(index >> 32), step, 2u * sub + 1u, k0, k1);
-    float z[5], spare;
+    float z[5];
     box_muller(A.x, A.y, z[0], z[1]);
     box_muller(A.z, A.w, z[2], z[3]);
-    box_muller(B.x, B.y, z[4], spare);
+    z[4] = box_muller_cos(B.x, B.y);
+    const int dg[5] = {0, 2, 5, 9, 14};
+    if (ND == 1) {
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            if (DIAG) out[j] = fmaf(sp.L[0][dg[j]], z[j], sp.mean[0][j]);
+        }
+        if (!DIAG) {
+            int t = 0;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                float acc = sp.mean[0][j];
+#pragma unroll
+                for (int m = 0; m <= j; ++m) acc = fmaf(sp.L[0][t++], z[m], acc);
+                out[j] = acc;
+            }
+        }
+        return;
+    }
     const float uc = u32_to_unit(B.z);
+    if (ND == 2 && DIAG) {
+        const bool second = uc > sp.cdf[0];
+#pragma unroll
+        for (int j = 0; j < 5; ++j)
+            out[j] = fmaf(second ? sp.L[1][dg[j]] : sp.L[0][dg[j]], z[j], second ? sp.mean[1][j] : sp.mean[0][j]);
+        return;
+    }
     int comp = 0;
 #pragma unroll
     for (int d = 0; d < GSE_MAX_ND - 1; ++d)
         comp += (d < sp.nd - 1 && uc > sp.cdf[d]) ? 1 : 0;
     if (DIAG) {
-        const int dg[5] = {0, 2, 5, 9, 14};
 #pragma unroll
         for (int j = 0; j < 5; ++j) out[j] = fmaf(sp.L[comp][dg[j]], z[j], sp.mean[comp][j]);
     } else {
@@ -209,7 +261,10 @@ __device__ __forceinline__ void bioreactor_increment(const float x[5], const Mod
     const float K_T2 = (float)((0.1 - 0.025) / 180 * 24.6);   // :219
     const float K_H = (float)(1.0 / 2000 / (0.28 / 180));     // :210
     const float rH = (float)(280.0 / 180) - Cg;               // :202
-    const float sat = __fdiv_rn(Cg, 1e-2f + Cg);              // Cg / (1e-2 + Cg)   :206,211
+    const float den = 1e-2f + Cg;
+    float rc = mufu_rcp(den);
+    rc = fmaf(rc, fmaf(-den, rc, 1.0f), rc);                  // one Newton step: <= 1 ulp
+    const float sat = Cg * rc;                                // Cg / (1e-2 + Cg)   :206,211
     const float rFA = K_FA * Cx * sat;                        // :206
     const float t1max = K_T1 * Cx;                            // :209
     const float t1req = t1max - fmaf(t1max * K_H, rH, 0.01f * Ch);          // :210
@@ -219,7 +274,7 @@ __device__ __forceinline__ void bioreactor_increment(const float x[5], const Mod
     const float t2 = fminf(K_T2 * Cx, fmaxf(0.0f, over - rE));              // :219-221
     const float rG = -rFA * (float)(116.0 / 180) - t1 - rE * (float)(46.0 / 180) - t2;   // :223
     d[0] = (in.feed - in.f_out * Cg + rG) * in.dt;            // :225
-    d[1] = 0.0f * Cx * in.dt;                                 // :226 (rX = 0 * Cx)
+    d[1] = 0.0f;                                              // :226 (rX = 0 * Cx)
     d[2] = (rFA - in.f_out * Cfa) * in.dt;                    // :227
     d[3] = (rE - in.f_out * Ce) * in.dt;                      // :228
     d[4] = rH * in.dt;                                        // :229
@@ -249,6 +304,47 @@ __device__ __forceinline__ double meas_logpdf(const MixDensity2& md, double e0, 
     for (int d = 0; d < GSE_MAX_ND; ++d)
         if (d < md.nd) s += __expf((float)(a[d] - m));
     return m + (double)__logf(s);
+}
+
+// float32 variant for the particle-filter update (K2).  e = z - y is formed from a float32 hi/lo
+// split of z: (z_hi - y) is exact (Sterbenz) whenever the innovation is small against the output,
+// so e carries a relative error of ~6e-8 and the log-density an error of ~3e-7 * max(1, |log pdf|)
+// -- inside the stated 1e-6 * max(1, |log w|) tolerance -- at a third of the issue slots of the
+// float64 form (K2 is instruction-issue bound, not HBM bound, in float64).
+template <int ND>                 // ND = 0: component count read from the density at run time
+__device__ __forceinline__ float meas_logpdf32(const MixDensity2f& md, float e0, float e1) {
+    if (ND > 0) {
+        float a[ND > 0 ? ND : 1];
+        float m = -3.0e38f;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            const float v0 = e0 - md.mean[d][0], v1 = e1 - md.mean[d][1];
+            const float q = fmaf(v0, fmaf(md.p00[d], v0, md.p01[d] * v1), md.p11[d] * v1 * v1);
+            a[d] = fmaf(-0.5f, q, md.logc[d]);
+            m = fmaxf(m, a[d]);
+        }
+        if (ND == 1) return a[0];
+        float s = 0.0f;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) s += __expf(a[d] - m);
+        return fmaf(mufu_lg2(s), 0.69314718055994531f, m);
+    }
+    float a[GSE_MAX_ND];
+    float m = -3.0e38f;
+#pragma unroll
+    for (int d = 0; d < GSE_MAX_ND; ++d) {
+        if (d < md.nd) {
+            const float v0 = e0 - md.mean[d][0], v1 = e1 - md.mean[d][1];
+            const float q = fmaf(v0, fmaf(md.p00[d], v0, md.p01[d] * v1), md.p11[d] * v1 * v1);
+            a[d] = fmaf(-0.5f, q, md.logc[d]);
+            m = fmaxf(m, a[d]);
+        }
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int d = 0; d < GSE_MAX_ND; ++d)
+        if (d < md.nd) s += __expf(a[d] - m);
+    return fmaf(mufu_lg2(s), 0.69314718055994531f, m);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -366,11 +462,14 @@ __device__ __forceinline__ void st_stream4(float* p, const float4& v) {
 // Exact systematic-resampling thresholds (host + device).
 //
 // The reference compares  cumsum[k] / cumsum[-1] < (i + r) / N  in float64 (particle.py:89-98).
-// Here cumulative weights are exact integers C (uint64, <= 2^62); the comparison value is
-// g(C) = fl(fl(C) / fl(T)).  g is monotone, so  g(C) >= u  <=>  C >= q*(u)  with
-// q*(u) = min{C : g(C) >= u}, computed below in two steps:
-//   X*  = min{x double : fl(x / Td) >= u}      (estimate u*Td, then step by ulps with the real divide)
-//   q*  = min{C integer : fl(C) >= X*}          (round-to-nearest-even conversion inverted exactly)
+// Here cumulative weights are exact integers C <= T < 2^53 (so fl(C), fl(T) are exact) and the
+// comparison value is g(C) = fl(C / T), a monotone function of C.  Hence
+//     g(C) >= u   <=>   C >= q*(u),     q*(u) = min{ C : fl(C / T) >= u }.
+// fl(x) >= u  <=>  x >= m, m = (pred(u) + u) / 2 the rounding boundary below u (ties to even: a
+// quotient exactly on the boundary rounds to u iff u's significand is even).  With u = Mu * 2^eu:
+// m = A * 2^ea, A = 2 Mu - 1 (4 Mu - 1 when u is a power of two), so
+//     q* = ceil(A * T * 2^ea)     (+1 on an exact tie with Mu odd)
+// evaluated with one 64 x 64 -> 128-bit product and a shift: no floating-point division at all.
 // tests/test_thresholds.py checks g(q*-1) < u <= g(q*) against Python integers / numpy float64.
 // ------------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
@@ -379,39 +478,13 @@ __device__ __forceinline__ void st_stream4(float* p, const float4& v) {
 #define GSE_HD static inline
 #endif
 
-GSE_HD double gse_bits_to_double(uint64_t b) {
-#ifdef __CUDA_ARCH__
-    return __longlong_as_double((long long)b);
-#else
-    double d; memcpy(&d, &b, 8); return d;
-#endif
-}
+#define GSE_TOTAL_BITS 52      /* the quantised weights sum to T <= 2^52 + n/2 < 2^53 */
+
 GSE_HD uint64_t gse_double_to_bits(double d) {
 #ifdef __CUDA_ARCH__
     return (uint64_t)__double_as_longlong(d);
 #else
     uint64_t b; memcpy(&b, &d, 8); return b;
-#endif
-}
-GSE_HD double gse_div(double a, double b) {
-#ifdef __CUDA_ARCH__
-    return __ddiv_rn(a, b);
-#else
-    return a / b;
-#endif
-}
-GSE_HD double gse_add(double a, double b) {
-#ifdef __CUDA_ARCH__
-    return __dadd_rn(a, b);
-#else
-    return a + b;
-#endif
-}
-GSE_HD double gse_mul(double a, double b) {
-#ifdef __CUDA_ARCH__
-    return __dmul_rn(a, b);
-#else
-    return a * b;
 #endif
 }
 GSE_HD double gse_u64_to_double(uint64_t c) {
@@ -421,54 +494,53 @@ GSE_HD double gse_u64_to_double(uint64_t c) {
     return (double)c;   // round-to-nearest-even on x86-64
 #endif
 }
-
-// u_i = (i + r) / N exactly as the reference evaluates it (particle.py:97)
-GSE_HD double gse_sample_position(int64_t i, double r, double n_total) {
-    return gse_div(gse_add((double)i, r), n_total);
+GSE_HD void gse_mul128(uint64_t a, uint64_t b, uint64_t& hi, uint64_t& lo) {
+#ifdef __CUDA_ARCH__
+    lo = a * b;
+    hi = __umul64hi(a, b);
+#else
+    const unsigned __int128 p = (unsigned __int128)a * b;
+    lo = (uint64_t)p;
+    hi = (uint64_t)(p >> 64);
+#endif
 }
 
-// smallest double x >= 0 with fl(x / Td) >= u      (u in [0, 1], Td >= 1)
-GSE_HD double gse_threshold_double(double u, double Td) {
-    if (!(u > 0.0)) return 0.0;
-    double x = gse_mul(u, Td);
-    if (gse_div(x, Td) >= u) {
-        // walk down while the predecessor still qualifies
-        for (int it = 0; it < 8; ++it) {
-            if (!(x > 0.0)) break;
-            const double xp = gse_bits_to_double(gse_double_to_bits(x) - 1);
-            if (gse_div(xp, Td) >= u) x = xp; else break;
-        }
-    } else {
-        for (int it = 0; it < 8; ++it) {
-            x = gse_bits_to_double(gse_double_to_bits(x) + 1);
-            if (gse_div(x, Td) >= u) break;
-        }
+// u_i = (i + r) / N exactly as the reference evaluates it (particle.py:97); di = (double)i
+GSE_HD double gse_sample_position(double di, double r, double n_total, double inv_n, bool n_pow2) {
+#ifdef __CUDA_ARCH__
+    const double s = __dadd_rn(di, r);
+    return n_pow2 ? __dmul_rn(s, inv_n) : __ddiv_rn(s, n_total);
+#else
+    const double s = di + r;
+    return n_pow2 ? s * inv_n : s / n_total;
+#endif
+}
+
+// q*(u): smallest integer C with fl(C / T) >= u, for 0 <= u <= 1 and 1 <= T < 2^53.
+GSE_HD uint64_t gse_threshold(double u, uint64_t T) {
+    if (!(u > 0.0)) return 0;
+    const uint64_t bits = gse_double_to_bits(u);
+    const uint64_t frac = bits & 0xfffffffffffffull;
+    const int ebits = (int)(bits >> 52);                 // u > 0: sign bit clear
+    if (ebits == 0) return 1;                            // subnormal u: any C >= 1 qualifies (1/T >> u)
+    const uint64_t Mu = frac | (1ull << 52);
+    const bool pow2 = (frac == 0);
+    const uint64_t A = pow2 ? (Mu << 2) - 1 : (Mu << 1) - 1;      // m = A * 2^ea
+    const int s = (pow2 ? 1077 : 1076) - ebits;                    // s = -ea = -(eu - 1 [-1]), eu = ebits - 1075
+    uint64_t hi, lo;
+    gse_mul128(A, T, hi, lo);
+    uint64_t c0;
+    bool rem;
+    if (s >= 128) {
+        c0 = 0;
+        rem = true;                                      // A * T > 0
+    } else if (s >= 64) {
+        const int t = s - 64;
+        c0 = hi >> t;
+        rem = (lo != 0) || ((t > 0) && ((hi & ((1ull << t) - 1)) != 0));
+    } else {                                             // 53 <= s < 64 (u in (1/2, 1]... down to 2^-10)
+        c0 = (hi << (64 - s)) | (lo >> s);
+        rem = (lo & ((1ull << s) - 1)) != 0;
     }
-    return x;
-}
-
-// smallest integer C with fl(C) >= X  (X >= 0 a double, X <= 2^63)
-GSE_HD uint64_t gse_threshold_int(double X) {
-    if (!(X > 0.0)) return 0;
-    if (X < 9007199254740992.0) {                 // < 2^53: every integer is representable
-        const double c = ceil(X);
-        return (uint64_t)c;
-    }
-    const uint64_t bits = gse_double_to_bits(X);
-    const int e = (int)((bits >> 52) & 0x7ff) - 1075;     // X = m * 2^e, m in [2^52, 2^53)
-    const uint64_t mant = bits & 0xfffffffffffffull;
-    const uint64_t Xi = (uint64_t)X;                      // exact: X is an integer here
-    // gap between X and its predecessor
-    uint64_t gap = 1ull << e;
-    if (mant == 0 && e > 0) gap >>= 1;
-    if (mant == 0 && e == 0) gap = 1;                     // X = 2^53: predecessor 2^53 - 1
-    if (gap < 2) return Xi;                               // no integer strictly between
-    const uint64_t mid = Xi - (gap >> 1);                 // exact midpoint: ties to even
-    const bool x_even = (mant & 1ull) == 0;               // power of two has an even significand
-    return x_even ? mid : mid + 1;
-}
-
-// q*(u): smallest integer cumulative weight C (0 <= C <= T) with fl(fl(C)/fl(T)) >= u
-GSE_HD uint64_t gse_threshold(double u, double Td) {
-    return gse_threshold_int(gse_threshold_double(u, Td));
+    return c0 + ((rem || (Mu & 1ull)) ? 1 : 0);
 }

@@ -7,7 +7,6 @@
 
 #define GSF_THREADS 128
 
-static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
 
 // sigma weights (gs_ukf.py:66-67), float32 as the reference stores them
 #define W_SIGMA_0 ((float)(1.0 / (1.0 + 5.0 / 4.0 * 5.0)))
@@ -117,7 +116,7 @@ k_gsf_predict(float* __restrict__ mean, float* __restrict__ cov, int64_t ld, int
 #pragma unroll
             for (int j = 0; j < 5; ++j) e[j] = noise[(s * 5 + j) * ldn + i];
         } else {
-            draw_mixture5<DIAG>(sp, (uint64_t)(index0 + i), step, (uint32_t)s, k0, k1, e);   // :99
+            draw_mixture5<DIAG, 0>(sp, (uint64_t)(index0 + i), step, (uint32_t)s, k0, k1, e);   // :99
         }
         const double w = (double)(s == 0 ? W_SIGMA_0 : W_SIGMA_I);
 #pragma unroll

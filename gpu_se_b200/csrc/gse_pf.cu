@@ -26,7 +26,7 @@ k_mixture_draw(float* __restrict__ x, int64_t ld, int64_t n, const __grid_consta
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         float o[5];
-        draw_mixture5<DIAG>(sp, (uint64_t)(index0 + row0 + r), step, 0u, k0, k1, o);
+        draw_mixture5<DIAG, 0>(sp, (uint64_t)(index0 + row0 + r), step, 0u, k0, k1, o);
 #pragma unroll
         for (int j = 0; j < 5; ++j) v[j][r] = o[j];
     }
@@ -58,7 +58,7 @@ extern "C" int gse_mixture_draw(gse_ctx* ctx, const gse_mixture* mix, float* x_d
 // ------------------------------------------------------------------------------------------------
 // K1: predict.  x += f(x, u, dt) (n_sub Euler sub-steps), then x += noise (particle.py:65-67).
 // ------------------------------------------------------------------------------------------------
-template <bool DIAG, bool HOST_NOISE>
+template <bool DIAG, bool HOST_NOISE, bool ONE_STEP, int ND>
 __global__ void __launch_bounds__(PF_THREADS)
 k_pf_predict(float* __restrict__ x, int64_t ld, int64_t n, ModelInputs in, int n_sub,
              const __grid_constant__ MixSampler5 sp, uint32_t k0, uint32_t k1, uint32_t step,
@@ -80,7 +80,8 @@ k_pf_predict(float* __restrict__ x, int64_t ld, int64_t n, ModelInputs in, int n
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         float xs[5] = {v[0][r], v[1][r], v[2][r], v[3][r], v[4][r]};
-        for (int s = 0; s < n_sub; ++s) {
+#pragma unroll 1
+        for (int s = 0; s < (ONE_STEP ? 1 : n_sub); ++s) {
             float d[5];
             bioreactor_increment(xs, in, d);
 #pragma unroll
@@ -91,7 +92,7 @@ k_pf_predict(float* __restrict__ x, int64_t ld, int64_t n, ModelInputs in, int n
 #pragma unroll
             for (int j = 0; j < 5; ++j) e[j] = reinterpret_cast<const float*>(&nz[j])[r];
         } else {
-            draw_mixture5<DIAG>(sp, (uint64_t)(index0 + row0 + r), step, 0u, k0, k1, e);
+            draw_mixture5<DIAG, ND>(sp, (uint64_t)(index0 + row0 + r), step, 0u, k0, k1, e);
         }
 #pragma unroll
         for (int j = 0; j < 5; ++j) v[j][r] = __fadd_rn(xs[j], e[j]);      // particles += draw(N)   (:67)
@@ -118,12 +119,17 @@ extern "C" int gse_pf_predict(gse_ctx* ctx, float* x_dev, int64_t ld, int64_t n,
     const unsigned blocks = (unsigned)gse_div_up(groups, PF_THREADS);
     cudaStream_t s = (cudaStream_t)stream;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-    if (noise_dev)
-        k_pf_predict<true, true><<<blocks, PF_THREADS, 0, s>>>(x_dev, ld, n, in, n_sub, ctx->state_sampler, k0, k1, (uint32_t)step, index0, noise_dev, ld_noise);
-    else if (ctx->state_sampler.diag)
-        k_pf_predict<true, false><<<blocks, PF_THREADS, 0, s>>>(x_dev, ld, n, in, n_sub, ctx->state_sampler, k0, k1, (uint32_t)step, index0, NULL, 0);
-    else
-        k_pf_predict<false, false><<<blocks, PF_THREADS, 0, s>>>(x_dev, ld, n, in, n_sub, ctx->state_sampler, k0, k1, (uint32_t)step, index0, NULL, 0);
+#define LAUNCH_PREDICT(DIAG, HOST, ONE, ND)                                                                      \
+    k_pf_predict<DIAG, HOST, ONE, ND><<<blocks, PF_THREADS, 0, s>>>(x_dev, ld, n, in, n_sub, ctx->state_sampler, k0, \
+                                                                     k1, (uint32_t)step, index0, noise_dev, ld_noise)
+    const bool one = (n_sub == 1);
+    const int nd = ctx->state_sampler.nd;
+    if (noise_dev) { if (one) LAUNCH_PREDICT(true, true, true, 0); else LAUNCH_PREDICT(true, true, false, 0); }
+    else if (ctx->state_sampler.diag && one && nd == 2) LAUNCH_PREDICT(true, false, true, 2);     // the benchmark's noise
+    else if (ctx->state_sampler.diag && one && nd == 1) LAUNCH_PREDICT(true, false, true, 1);
+    else if (ctx->state_sampler.diag) { if (one) LAUNCH_PREDICT(true, false, true, 0); else LAUNCH_PREDICT(true, false, false, 0); }
+    else { if (one) LAUNCH_PREDICT(false, false, true, 0); else LAUNCH_PREDICT(false, false, false, 0); }
+#undef LAUNCH_PREDICT
     GSE_CHECK_LAUNCH(ctx);
     return GSE_OK;
 }
@@ -131,9 +137,10 @@ extern "C" int gse_pf_predict(gse_ctx* ctx, float* x_dev, int64_t ld, int64_t n,
 // ------------------------------------------------------------------------------------------------
 // K2: update.  loglik_i += log pdf_meas(z - g(x_i, u))   (particle.py:80-83), fused max / sum-exp.
 // ------------------------------------------------------------------------------------------------
+template <int ND>
 __global__ void __launch_bounds__(PF_THREADS)
 k_pf_update(const float* __restrict__ xg, const float* __restrict__ xfa, float* __restrict__ loglik,
-            int64_t n, double z0, double z1, const __grid_constant__ MixDensity2 md,
+            int64_t n, float z0h, float z0l, float z1h, float z1l, const __grid_constant__ MixDensity2f md,
             float* block_max, float* block_sum, unsigned int* ticket, double* stats) {
     const int64_t g = (int64_t)blockIdx.x * PF_THREADS + threadIdx.x;
     const int64_t row0 = g * ROWS_PER_THREAD;
@@ -148,9 +155,9 @@ k_pf_update(const float* __restrict__ xg, const float* __restrict__ xfa, float* 
         const float l[4] = {lw.x, lw.y, lw.z, lw.w};
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            const double e0 = z0 - (double)output_glucose(a[r]);       // e = z - y   (:82)
-            const double e1 = z1 - (double)output_fa(b[r]);
-            vals[r] = (float)((double)l[r] + meas_logpdf(md, e0, e1));  // weights[i] *= pdf(e)  (:83)
+            const float e0 = __fadd_rn(__fsub_rn(z0h, output_glucose(a[r])), z0l);   // e = z - y   (:82)
+            const float e1 = __fadd_rn(__fsub_rn(z1h, output_fa(b[r])), z1l);
+            vals[r] = l[r] + meas_logpdf32<ND>(md, e0, e1);                 // weights[i] *= pdf(e)  (:83)
             valid[r] = (row0 + r) < n;
         }
         st_stream4(loglik + row0, make_float4(vals[0], vals[1], vals[2], vals[3]));
@@ -168,9 +175,20 @@ extern "C" int gse_pf_update(gse_ctx* ctx, const float* x_dev, int64_t ld, int64
     const int64_t groups = gse_div_up(n, ROWS_PER_THREAD);
     const unsigned blocks = (unsigned)gse_div_up(groups, PF_THREADS);
     GSE_REQUIRE((int64_t)blocks <= ctx->max_blocks, "workspace too small");
-    k_pf_update<<<blocks, PF_THREADS, 0, (cudaStream_t)stream>>>(
-        x_dev + 0 * ld, x_dev + 2 * ld, loglik_dev, n, z[0], z[1], ctx->meas_density,
-        ctx->block_max, ctx->block_sum, ctx->ticket, stats_dev);
+    const float z0h = (float)z[0], z1h = (float)z[1];
+    const float z0l = (float)(z[0] - (double)z0h), z1l = (float)(z[1] - (double)z1h);
+#define LAUNCH_UPDATE(ND)                                                                                   \
+    k_pf_update<ND><<<blocks, PF_THREADS, 0, (cudaStream_t)stream>>>(                                          \
+        x_dev + 0 * ld, x_dev + 2 * ld, loglik_dev, n, z0h, z0l, z1h, z1l, ctx->meas_density32, ctx->block_max, \
+        ctx->block_sum, ctx->ticket, stats_dev)
+    switch (ctx->meas_density32.nd) {
+        case 1: LAUNCH_UPDATE(1); break;
+        case 2: LAUNCH_UPDATE(2); break;
+        case 3: LAUNCH_UPDATE(3); break;
+        case 4: LAUNCH_UPDATE(4); break;
+        default: LAUNCH_UPDATE(0); break;
+    }
+#undef LAUNCH_UPDATE
     GSE_CHECK_LAUNCH(ctx);
     return GSE_OK;
 }

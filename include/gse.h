@@ -133,7 +133,7 @@ int gse_weights_linear(gse_ctx* ctx, const float* loglik_dev, const double* base
 
 /* cumsum (particle.py:89 / :301-303, numpy.cumsum / torch.cumsum): inclusive scan of the
  * fixed-point weights  q_i = rint(base_i * exp(loglik_i - stats_dev[0]) * 2^s)  into uint64
- * cumsum_dev, with s = 61 - ceil(log2(stats_dev[1])) so that the total stays below 2^62
+ * cumsum_dev, with s = 52 - ceil(log2(stats_dev[1])) so that the total stays below 2^53 (exact in float64)
  * (stats_dev[1] >= sum_i base_i * exp(loglik_i - stats_dev[0]); the update kernels write it).
  * Integer addition is associative, so the result does not depend on the scan structure, the
  * launch geometry or the number of GPUs.  loglik_dev may be NULL (weights = base; the caller

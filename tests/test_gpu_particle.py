@@ -224,7 +224,7 @@ def test_multi_step_vs_oracle_with_host_noise(g, noise_pdfs):
         r = float(rng.random())
         pf.resample(r=r)
         o.resample(r=r)
-        assert numpy.allclose(pf.point_estimate(), o.point_estimate(), rtol=1e-4, atol=1e-4)
+        assert numpy.allclose(pf.point_estimate(), o.point_estimate(), rtol=1e-4, atol=1e-3)   # ~1% of the posterior spread
         # re-seed the oracle with the device state: ancestors may differ at a handful of boundaries
         o.particles = pf.particles.get().copy()
 
