@@ -34,8 +34,11 @@ METRIC = "particle-steps/sec (predict+update+resample)"
 UNIT = "particle-steps/s"
 DT = 1.0                      # pf_run_seq.py:48  p.predict(u, 1.)
 U_NOMINAL = numpy.array([0.06, 0.2])
-# algorithmic bytes per particle and stage (SURVEY.md §8(d) with this layout)
-STAGE_BYTES = {"predict": 40, "update": 16, "scan": 12, "gather": 52}
+# algorithmic bytes per particle and stage (SURVEY.md §8(d) re-cut for the lazy resample --
+# predict reads its rows through the int32 ancestor index, so K5's gather rides inside K1):
+#   predict 4 R idx + 20 R + 20 W, update 8 R + 4 W, scan 4 R + 8 W, search 8 R + 4 W
+STAGE_BYTES = {"predict": 44, "update": 12, "scan": 12, "search": 12}
+STEP_BYTES = sum(STAGE_BYTES.values())          # 80 B per particle-step (SURVEY §8(d) counted 128 B with a materialised gather)
 
 
 def parse_args():
@@ -271,7 +274,7 @@ def run_ours(args):
         pf.resample(r=float(rs[k]))
         pf._stage_hook = None
         if record:
-            hook("gather")
+            hook("search")
 
     for k in range(W):
         step(k, False)
@@ -286,6 +289,7 @@ def run_ours(args):
     ev0.record(stream)
     for k in range(W, W + K):
         step(k, True)
+    getattr(pf, "local", pf)._materialise()     # the last resample's pending gather belongs to the timed region
     ev1.record(stream)
     barrier()
     t_wall1 = time.perf_counter()
@@ -329,7 +333,7 @@ def run_ours(args):
     value = n_total * K / (dev_ms * 1e-3)
     dom = max(stage_avg, key=stage_avg.get) if stage_avg else "predict"
     dom_ms = stage_avg.get(dom, dev_ms / K)
-    achieved = STAGE_BYTES.get(dom, 128) * n_local / (dom_ms * 1e-3) / 1e9
+    achieved = STAGE_BYTES.get(dom, STEP_BYTES) * n_local / (dom_ms * 1e-3) / 1e9
     stages = {k: {"ms": round(v, 4), "bytes_per_particle": STAGE_BYTES.get(k),
                   "gbs": round(STAGE_BYTES.get(k, 0) * n_local / (v * 1e-3) / 1e9, 1),
                   "frac": round(STAGE_BYTES.get(k, 0) * n_local / (v * 1e-3) / 1e9 / peak, 4)}
@@ -346,7 +350,9 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_particle": STAGE_BYTES.get(dom),
-                     "whole_step_frac": 120 * n_local / (dev_ms / K * 1e-3) / 1e9 / peak},
+                     "whole_step_frac": STEP_BYTES * n_local / (dev_ms / K * 1e-3) / 1e9 / peak,
+                     "whole_step_bytes_per_particle": STEP_BYTES,
+                     "survey_step_frac": 128 * n_local / (dev_ms / K * 1e-3) / 1e9 / peak},
         "stages": stages,
         "e2e": {"value": n_total * K / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / K,
                 "h2d_bytes_per_step": 48, "d2h_bytes_per_step": 48 * 8,

@@ -2,14 +2,14 @@
 
 There is no fallback: if the shared library is missing or cannot be loaded this module raises,
 and every filter operation raises with the library's own error message on a non-zero status.
-Build the library with ``python -m gpu_se_b200.build`` (``__graft_entry__.build()`` does that).
+Build the library with ``python gpu_se_b200/build.py`` (``__graft_entry__.build()`` does that).
 """
 import ctypes
 import os
 
 GSE_NX, GSE_NU, GSE_NY, GSE_NSIGMA, GSE_NCOV, GSE_MAX_ND = 5, 2, 2, 11, 15, 8
 GSE_MODEL_BIOREACTOR = 1
-GSE_ABI_VERSION = 1
+GSE_ABI_VERSION = 2
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgse_b200.so")
 
@@ -40,29 +40,29 @@ SIGNATURES = {
     "gse_ctx_destroy": (c_int, [c_vp]),
     "gse_mixture_draw": (c_int, [c_vp, c_mix_p, c_vp, c_i64, c_i64, c_u64, c_u64, c_i64, c_vp]),
     "gse_mixture_pdf": (c_int, [c_vp, c_mix_p, c_vp, c_i64, c_i64, c_vp, c_int, c_vp]),
-    "gse_pf_predict": (c_int, [c_vp, c_vp, c_i64, c_i64, c_dbl_p, c_dbl, c_int, c_u64, c_u64, c_i64, c_vp, c_i64,
-                               c_vp]),
-    "gse_pf_update": (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_dbl_p, c_dbl_p, c_vp, c_vp]),
-    "gse_pf_moments": (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "gse_pf_predict": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_dbl_p, c_dbl, c_int, c_u64, c_u64, c_i64,
+                               c_vp, c_i64, c_vp]),
+    "gse_pf_update": (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_dbl_p, c_dbl_p, c_vp, c_vp]),
+    "gse_pf_moments": (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "gse_loglik_max": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
     "gse_weights_linear": (c_int, [c_vp, c_vp, c_vp, c_i64, c_dbl, c_vp, c_vp]),
     "gse_scan_weights": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
-    "gse_resample_gather": (c_int, [c_vp, c_vp, c_i64, c_vp, c_dbl, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64,
-                                    c_int, c_vp, c_vp, c_vp]),
+    "gse_resample_search": (c_int, [c_vp, c_vp, c_i64, c_vp, c_dbl, c_i64, c_i64, c_i64, c_vp, c_vp]),
+    "gse_gather_rows": (c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_vp]),
     "gse_count_outputs_below": (c_i64, [c_u64, c_u64, c_dbl, c_i64]),
     "gse_threshold_u64": (c_u64, [c_dbl, c_u64]),
-    "gse_gsf_predict": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_dbl_p, c_dbl, c_u64, c_u64, c_i64, c_vp, c_i64,
-                                c_vp]),
-    "gse_gsf_update": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_dbl_p, c_dbl_p, c_vp, c_vp]),
+    "gse_gsf_predict": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_dbl_p, c_dbl, c_u64, c_u64,
+                                c_i64, c_vp, c_i64, c_vp]),
+    "gse_gsf_update": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_dbl_p, c_dbl_p, c_vp, c_vp]),
     "gse_gsf_sigma_points": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp]),
-    "gse_gsf_moments": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "gse_gsf_moments": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "gse_launch_count": (c_i64, [c_vp]),
 }
 
 
 def _load():
     if not os.path.exists(LIB_PATH):
-        raise GseError("libgse_b200.so not found at %s -- build it first (python -m gpu_se_b200.build); "
+        raise GseError("libgse_b200.so not found at %s -- build it first (python gpu_se_b200/build.py); "
                        "there is no CPU fallback" % LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():

@@ -1,6 +1,6 @@
 """Build libgse_b200.so in-tree with nvcc for sm_100a (no torch / pybind dependency).
 
-    python -m gpu_se_b200.build [--force] [-v]
+    python gpu_se_b200/build.py [--force] [-v]      (run as a script: the package itself needs the library)
 """
 import os
 import shutil

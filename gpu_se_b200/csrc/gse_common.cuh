@@ -102,6 +102,7 @@ struct gse_ctx {
     unsigned int* tile_flag;  // scan: (epoch << 2) | state
     int64_t* part;            // merge-path split points
     unsigned int scan_epoch;
+    int search_smem_opt_in;   // cudaFuncSetAttribute(k_resample_search, MaxDynamicSharedMemorySize) done on this device
     int64_t max_blocks;
     int64_t max_tiles;
 };
@@ -371,18 +372,35 @@ __device__ __forceinline__ double warp_sum(double v) {
 // Each block publishes (m_b, s_b = sum exp(v - m_b)); the last block to finish merges them in a
 // fixed order into stats[0] = M = max, stats[1] = S = sum exp(v - M).
 // ------------------------------------------------------------------------------------------------
-template <int THREADS, int NV>
-__device__ __forceinline__ void block_max_sumexp_finalize(const float vals[NV], const bool valid[NV],
-                                                          float* block_max, float* block_sum,
-                                                          unsigned int* ticket, double* stats) {
+// Online (max, sum exp) accumulator: after add(v...) the pair (m, s) satisfies
+// s = sum_k exp(v_k - m), m = max_k v_k.  One rescale per group of values, not per value.
+struct MaxSumExp {
+    float m, s;
+    __device__ __forceinline__ MaxSumExp() : m(-INFINITY), s(0.0f) {}
+    template <int NV>
+    __device__ __forceinline__ void add(const float vals[NV], const bool valid[NV]) {
+        float g = -INFINITY;
+#pragma unroll
+        for (int r = 0; r < NV; ++r) if (valid[r]) g = fmaxf(g, vals[r]);
+        const float mn = fmaxf(m, g);
+        if (mn > -INFINITY) {
+            float t = s * __expf(m - mn);          // m = -inf: exp(-inf) = 0, s = 0
+#pragma unroll
+            for (int r = 0; r < NV; ++r) if (valid[r]) t += __expf(vals[r] - mn);
+            s = t;
+            m = mn;
+        }
+    }
+};
+
+template <int THREADS>
+__device__ __forceinline__ void block_merge_max_sumexp(float m_t, float s_t, float* block_max, float* block_sum,
+                                                       unsigned int* ticket, double* stats) {
     __shared__ float s_red[THREADS / 32];
     __shared__ float s_bcast;
     __shared__ bool s_last;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    float m = -INFINITY;
-#pragma unroll
-    for (int r = 0; r < NV; ++r) if (valid[r]) m = fmaxf(m, vals[r]);
-    m = warp_max(m);
+    float m = warp_max(m_t);
     if (lane == 0) s_red[wid] = m;
     __syncthreads();
     if (wid == 0) {
@@ -392,9 +410,7 @@ __device__ __forceinline__ void block_max_sumexp_finalize(const float vals[NV], 
     }
     __syncthreads();
     const float bm = s_bcast;
-    float sum = 0.0f;
-#pragma unroll
-    for (int r = 0; r < NV; ++r) if (valid[r]) sum += __expf(vals[r] - bm);
+    float sum = (m_t > -INFINITY) ? s_t * __expf(m_t - bm) : 0.0f;
     sum = warp_sum(sum);
     __syncthreads();
     if (lane == 0) s_red[wid] = sum;
@@ -443,6 +459,15 @@ __device__ __forceinline__ void block_max_sumexp_finalize(const float vals[NV], 
         stats[1] = t;
         *ticket = 0u;
     }
+}
+
+template <int THREADS, int NV>
+__device__ __forceinline__ void block_max_sumexp_finalize(const float vals[NV], const bool valid[NV],
+                                                          float* block_max, float* block_sum,
+                                                          unsigned int* ticket, double* stats) {
+    MaxSumExp acc;
+    acc.add<NV>(vals, valid);
+    block_merge_max_sumexp<THREADS>(acc.m, acc.s, block_max, block_sum, ticket, stats);
 }
 
 // streaming 128-bit accesses for touch-once columns

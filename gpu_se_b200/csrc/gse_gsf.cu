@@ -93,16 +93,18 @@ extern "C" int gse_gsf_sigma_points(gse_ctx* ctx, const float* mean_dev, const f
 // ------------------------------------------------------------------------------------------------
 template <bool DIAG, bool HOST_NOISE>
 __global__ void __launch_bounds__(GSF_THREADS)
-k_gsf_predict(float* __restrict__ mean, float* __restrict__ cov, int64_t ld, int64_t n, ModelInputs in,
+k_gsf_predict(const float* mean_src, const float* cov_src, int64_t lds, const int32_t* __restrict__ idx,
+              float* mean, float* cov, int64_t ld, int64_t n, ModelInputs in,
               const __grid_constant__ MixSampler5 sp, uint32_t k0, uint32_t k1, uint32_t step, int64_t index0,
               const float* __restrict__ noise, int64_t ldn) {
     const int64_t i = (int64_t)blockIdx.x * GSF_THREADS + threadIdx.x;
     if (i >= n) return;
+    const int64_t is = idx ? (int64_t)idx[i] : i;          // pending resample: read through the ancestor index
     float m[5], P[15], L[15];
 #pragma unroll
-    for (int j = 0; j < 5; ++j) m[j] = mean[j * ld + i];
+    for (int j = 0; j < 5; ++j) m[j] = mean_src[j * lds + is];
 #pragma unroll
-    for (int j = 0; j < 15; ++j) P[j] = cov[j * ld + i];
+    for (int j = 0; j < 15; ++j) P[j] = cov_src[j * lds + is];
     cholesky5_retry(P, L);
 
     float sg[GSE_NSIGMA][5];
@@ -152,11 +154,15 @@ k_gsf_predict(float* __restrict__ mean, float* __restrict__ cov, int64_t ld, int
     for (int j = 0; j < 15; ++j) cov[j * ld + i] = C[j];
 }
 
-extern "C" int gse_gsf_predict(gse_ctx* ctx, float* mean_dev, float* cov_dev, int64_t ld, int64_t n,
+extern "C" int gse_gsf_predict(gse_ctx* ctx, const float* mean_src_dev, const float* cov_src_dev, int64_t ld_src,
+                               const int32_t* idx_dev, float* mean_dev, float* cov_dev, int64_t ld, int64_t n,
                                const double u[GSE_NU], double dt, uint64_t seed, uint64_t step, int64_t index0,
                                const float* noise_dev, int64_t ld_noise, void* stream) {
-    GSE_REQUIRE(ctx != NULL && u != NULL && mean_dev != NULL && cov_dev != NULL, "NULL argument");
+    GSE_REQUIRE(ctx != NULL && u != NULL && mean_dev != NULL && cov_dev != NULL && mean_src_dev != NULL &&
+                cov_src_dev != NULL, "NULL argument");
     GSE_REQUIRE(n >= 1 && n <= ctx->n_max && ld >= n, "n / ld out of range");
+    GSE_REQUIRE(idx_dev == NULL || mean_src_dev != mean_dev, "a gathering predict cannot run in place");
+    GSE_REQUIRE(idx_dev != NULL || ld_src >= n, "ld_src too small");
     GSE_REQUIRE(noise_dev == NULL || ld_noise >= n, "ld_noise too small");
     ModelInputs in;
     in.feed = (float)(u[0] * (5000.0 / 180.0));
@@ -166,11 +172,11 @@ extern "C" int gse_gsf_predict(gse_ctx* ctx, float* mean_dev, float* cov_dev, in
     cudaStream_t s = (cudaStream_t)stream;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     if (noise_dev)
-        k_gsf_predict<true, true><<<blocks, GSF_THREADS, 0, s>>>(mean_dev, cov_dev, ld, n, in, ctx->state_sampler, k0, k1, (uint32_t)step, index0, noise_dev, ld_noise);
+        k_gsf_predict<true, true><<<blocks, GSF_THREADS, 0, s>>>(mean_src_dev, cov_src_dev, ld_src, idx_dev, mean_dev, cov_dev, ld, n, in, ctx->state_sampler, k0, k1, (uint32_t)step, index0, noise_dev, ld_noise);
     else if (ctx->state_sampler.diag)
-        k_gsf_predict<true, false><<<blocks, GSF_THREADS, 0, s>>>(mean_dev, cov_dev, ld, n, in, ctx->state_sampler, k0, k1, (uint32_t)step, index0, NULL, 0);
+        k_gsf_predict<true, false><<<blocks, GSF_THREADS, 0, s>>>(mean_src_dev, cov_src_dev, ld_src, idx_dev, mean_dev, cov_dev, ld, n, in, ctx->state_sampler, k0, k1, (uint32_t)step, index0, NULL, 0);
     else
-        k_gsf_predict<false, false><<<blocks, GSF_THREADS, 0, s>>>(mean_dev, cov_dev, ld, n, in, ctx->state_sampler, k0, k1, (uint32_t)step, index0, NULL, 0);
+        k_gsf_predict<false, false><<<blocks, GSF_THREADS, 0, s>>>(mean_src_dev, cov_src_dev, ld_src, idx_dev, mean_dev, cov_dev, ld, n, in, ctx->state_sampler, k0, k1, (uint32_t)step, index0, NULL, 0);
     GSE_CHECK_LAUNCH(ctx);
     return GSE_OK;
 }
@@ -180,8 +186,8 @@ extern "C" int gse_gsf_predict(gse_ctx* ctx, float* mean_dev, float* cov_dev, in
 // float64 array, :118), so the Kalman algebra here is float64 too; storage stays float32.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GSF_THREADS)
-k_gsf_update(float* __restrict__ mean, float* __restrict__ cov, int64_t ld, int64_t n, float* __restrict__ loglik,
-             double z0, double z1, const __grid_constant__ MixDensity2 md, float* block_max, float* block_sum,
+k_gsf_update(float* __restrict__ mean, float* __restrict__ cov, int64_t ld, int64_t n, const float* loglik_in,
+             float* loglik, double z0, double z1, const __grid_constant__ MixDensity2 md, float* block_max, float* block_sum,
              unsigned int* ticket, double* stats) {
     const int64_t i = (int64_t)blockIdx.x * GSF_THREADS + threadIdx.x;
     float vals[1] = {0.0f};
@@ -258,7 +264,7 @@ k_gsf_update(float* __restrict__ mean, float* __restrict__ cov, int64_t ld, int6
         // global update: weights *= pdf(z - g(mean))  (:141-149)
         const double g0 = z0 - (double)output_glucose(mn[0]);
         const double g1 = z1 - (double)output_fa(mn[2]);
-        vals[0] = (float)((double)loglik[i] + meas_logpdf(md, g0, g1));
+        vals[0] = (float)((loglik_in ? (double)loglik_in[i] : 0.0) + meas_logpdf(md, g0, g1));
         valid[0] = true;
         loglik[i] = vals[0];
     }
@@ -266,14 +272,14 @@ k_gsf_update(float* __restrict__ mean, float* __restrict__ cov, int64_t ld, int6
 }
 
 extern "C" int gse_gsf_update(gse_ctx* ctx, float* mean_dev, float* cov_dev, int64_t ld, int64_t n,
-                              float* loglik_dev, const double u[GSE_NU], const double z[GSE_NY],
+                              const float* loglik_in_dev, float* loglik_dev, const double u[GSE_NU], const double z[GSE_NY],
                               double* stats_dev, void* stream) {
     GSE_REQUIRE(ctx != NULL && z != NULL && mean_dev != NULL && cov_dev != NULL && loglik_dev != NULL && stats_dev != NULL, "NULL argument");
     GSE_REQUIRE(n >= 1 && n <= ctx->n_max && ld >= n, "n / ld out of range");
     (void)u;
     const unsigned blocks = (unsigned)gse_div_up(n, GSF_THREADS);
     GSE_REQUIRE((int64_t)blocks <= ctx->max_blocks, "workspace too small");
-    k_gsf_update<<<blocks, GSF_THREADS, 0, (cudaStream_t)stream>>>(mean_dev, cov_dev, ld, n, loglik_dev, z[0], z[1],
+    k_gsf_update<<<blocks, GSF_THREADS, 0, (cudaStream_t)stream>>>(mean_dev, cov_dev, ld, n, loglik_in_dev, loglik_dev, z[0], z[1],
                                                                    ctx->meas_density, ctx->block_max, ctx->block_sum,
                                                                    ctx->ticket, stats_dev);
     GSE_CHECK_LAUNCH(ctx);

@@ -58,20 +58,34 @@ extern "C" int gse_mixture_draw(gse_ctx* ctx, const gse_mixture* mix, float* x_d
 // ------------------------------------------------------------------------------------------------
 // K1: predict.  x += f(x, u, dt) (n_sub Euler sub-steps), then x += noise (particle.py:65-67).
 // ------------------------------------------------------------------------------------------------
-template <bool DIAG, bool HOST_NOISE, bool ONE_STEP, int ND>
+template <bool DIAG, bool HOST_NOISE, bool ONE_STEP, int ND, bool GATHER>
 __global__ void __launch_bounds__(PF_THREADS)
-k_pf_predict(float* __restrict__ x, int64_t ld, int64_t n, ModelInputs in, int n_sub,
-             const __grid_constant__ MixSampler5 sp, uint32_t k0, uint32_t k1, uint32_t step,
-             int64_t index0, const float* __restrict__ noise, int64_t ldn) {
+k_pf_predict(const float* xs, int64_t lds, const int32_t* __restrict__ idx, float* xd, int64_t ldd, int64_t n,
+             ModelInputs in, int n_sub, const __grid_constant__ MixSampler5 sp, uint32_t k0, uint32_t k1,
+             uint32_t step, int64_t index0, const float* __restrict__ noise, int64_t ldn) {
     const int64_t g = (int64_t)blockIdx.x * PF_THREADS + threadIdx.x;
     const int64_t row0 = g * ROWS_PER_THREAD;
     if (row0 >= n) return;
-    float4 c[5];
-#pragma unroll
-    for (int j = 0; j < 5; ++j) c[j] = ld_stream4(x + j * ld + row0);
     float v[5][4];
+    if (GATHER) {
+        // rows of the resampled population are read through the ancestor index (the pending
+        // particles[sample_index] of the last resample, particle.py:102): idx is non-decreasing, so a
+        // warp's reads fall into one short window of each column
+        const int4 id4 = *reinterpret_cast<const int4*>(idx + row0);
+        const int id[4] = {id4.x, (row0 + 1 < n) ? id4.y : id4.x, (row0 + 2 < n) ? id4.z : id4.x,
+                           (row0 + 3 < n) ? id4.w : id4.x};
 #pragma unroll
-    for (int j = 0; j < 5; ++j) { v[j][0] = c[j].x; v[j][1] = c[j].y; v[j][2] = c[j].z; v[j][3] = c[j].w; }
+        for (int j = 0; j < 5; ++j) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) v[j][r] = __ldg(xs + j * lds + id[r]);
+        }
+    } else {
+        float4 c[5];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) c[j] = ld_stream4(xs + j * lds + row0);
+#pragma unroll
+        for (int j = 0; j < 5; ++j) { v[j][0] = c[j].x; v[j][1] = c[j].y; v[j][2] = c[j].z; v[j][3] = c[j].w; }
+    }
     float4 nz[5];
     if (HOST_NOISE) {
 #pragma unroll
@@ -79,13 +93,13 @@ k_pf_predict(float* __restrict__ x, int64_t ld, int64_t n, ModelInputs in, int n
     }
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-        float xs[5] = {v[0][r], v[1][r], v[2][r], v[3][r], v[4][r]};
+        float xv[5] = {v[0][r], v[1][r], v[2][r], v[3][r], v[4][r]};
 #pragma unroll 1
         for (int s = 0; s < (ONE_STEP ? 1 : n_sub); ++s) {
             float d[5];
-            bioreactor_increment(xs, in, d);
+            bioreactor_increment(xv, in, d);
 #pragma unroll
-            for (int j = 0; j < 5; ++j) xs[j] = __fadd_rn(xs[j], d[j]);    // particles[i] += f(...)  (:66)
+            for (int j = 0; j < 5; ++j) xv[j] = __fadd_rn(xv[j], d[j]);    // particles[i] += f(...)  (:66)
         }
         float e[5];
         if (HOST_NOISE) {
@@ -95,21 +109,28 @@ k_pf_predict(float* __restrict__ x, int64_t ld, int64_t n, ModelInputs in, int n
             draw_mixture5<DIAG, ND>(sp, (uint64_t)(index0 + row0 + r), step, 0u, k0, k1, e);
         }
 #pragma unroll
-        for (int j = 0; j < 5; ++j) v[j][r] = __fadd_rn(xs[j], e[j]);      // particles += draw(N)   (:67)
+        for (int j = 0; j < 5; ++j) v[j][r] = __fadd_rn(xv[j], e[j]);      // particles += draw(N)   (:67)
     }
 #pragma unroll
     for (int j = 0; j < 5; ++j)
-        st_stream4(x + j * ld + row0, make_float4(v[j][0], v[j][1], v[j][2], v[j][3]));
+        st_stream4(xd + j * ldd + row0, make_float4(v[j][0], v[j][1], v[j][2], v[j][3]));
 }
 
-extern "C" int gse_pf_predict(gse_ctx* ctx, float* x_dev, int64_t ld, int64_t n, const double u[GSE_NU],
-                              double dt, int n_sub, uint64_t seed, uint64_t step, int64_t index0,
-                              const float* noise_dev, int64_t ld_noise, void* stream) {
+extern "C" int gse_pf_predict(gse_ctx* ctx, const float* x_src_dev, int64_t ld_src, const int32_t* idx_dev,
+                              float* x_dst_dev, int64_t ld_dst, int64_t n, const double u[GSE_NU], double dt,
+                              int n_sub, uint64_t seed, uint64_t step, int64_t index0, const float* noise_dev,
+                              int64_t ld_noise, void* stream) {
     GSE_REQUIRE(ctx != NULL && u != NULL, "ctx / u is NULL");
     GSE_REQUIRE(n >= 0 && n <= ctx->n_max, "n out of range for this context");
     GSE_REQUIRE(n_sub >= 1, "n_sub must be >= 1");
     if (n == 0) return GSE_OK;
-    CHECK_SOA(x_dev, ld, n);
+    CHECK_SOA(x_dst_dev, ld_dst, n);
+    if (idx_dev) {
+        GSE_REQUIRE(x_src_dev != NULL && x_src_dev != x_dst_dev, "a gathering predict cannot run in place");
+        GSE_REQUIRE(aligned16(idx_dev), "idx must be 16-byte aligned");
+    } else {
+        CHECK_SOA(x_src_dev, ld_src, n);
+    }
     if (noise_dev) { CHECK_SOA(noise_dev, ld_noise, n); }
     ModelInputs in;
     in.feed = (float)(u[0] * (5000.0 / 180.0));
@@ -119,9 +140,12 @@ extern "C" int gse_pf_predict(gse_ctx* ctx, float* x_dev, int64_t ld, int64_t n,
     const unsigned blocks = (unsigned)gse_div_up(groups, PF_THREADS);
     cudaStream_t s = (cudaStream_t)stream;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#define LAUNCH_PREDICT_G(DIAG, HOST, ONE, ND, GATHER)                                                            \
+    k_pf_predict<DIAG, HOST, ONE, ND, GATHER><<<blocks, PF_THREADS, 0, s>>>(                                     \
+        x_src_dev, ld_src, idx_dev, x_dst_dev, ld_dst, n, in, n_sub, ctx->state_sampler, k0, k1, (uint32_t)step, \
+        index0, noise_dev, ld_noise)
 #define LAUNCH_PREDICT(DIAG, HOST, ONE, ND)                                                                      \
-    k_pf_predict<DIAG, HOST, ONE, ND><<<blocks, PF_THREADS, 0, s>>>(x_dev, ld, n, in, n_sub, ctx->state_sampler, k0, \
-                                                                     k1, (uint32_t)step, index0, noise_dev, ld_noise)
+    do { if (idx_dev) LAUNCH_PREDICT_G(DIAG, HOST, ONE, ND, true); else LAUNCH_PREDICT_G(DIAG, HOST, ONE, ND, false); } while (0)
     const bool one = (n_sub == 1);
     const int nd = ctx->state_sampler.nd;
     if (noise_dev) { if (one) LAUNCH_PREDICT(true, true, true, 0); else LAUNCH_PREDICT(true, true, false, 0); }
@@ -130,6 +154,7 @@ extern "C" int gse_pf_predict(gse_ctx* ctx, float* x_dev, int64_t ld, int64_t n,
     else if (ctx->state_sampler.diag) { if (one) LAUNCH_PREDICT(true, false, true, 0); else LAUNCH_PREDICT(true, false, false, 0); }
     else { if (one) LAUNCH_PREDICT(false, false, true, 0); else LAUNCH_PREDICT(false, false, false, 0); }
 #undef LAUNCH_PREDICT
+#undef LAUNCH_PREDICT_G
     GSE_CHECK_LAUNCH(ctx);
     return GSE_OK;
 }
@@ -137,22 +162,29 @@ extern "C" int gse_pf_predict(gse_ctx* ctx, float* x_dev, int64_t ld, int64_t n,
 // ------------------------------------------------------------------------------------------------
 // K2: update.  loglik_i += log pdf_meas(z - g(x_i, u))   (particle.py:80-83), fused max / sum-exp.
 // ------------------------------------------------------------------------------------------------
-template <int ND>
+// Persistent grid (a few CTAs per SM): every thread walks groups of 4 rows with a grid stride and
+// keeps a running (max, sum exp) pair, so the block-level reduction and its barriers run once per
+// CTA instead of once per 1024 rows.
+template <int ND, bool LL_ZERO>      // LL_ZERO: the accumulated log-likelihood is all zero (fresh resample)
 __global__ void __launch_bounds__(PF_THREADS)
-k_pf_update(const float* __restrict__ xg, const float* __restrict__ xfa, float* __restrict__ loglik,
-            int64_t n, float z0h, float z0l, float z1h, float z1l, const __grid_constant__ MixDensity2f md,
-            float* block_max, float* block_sum, unsigned int* ticket, double* stats) {
-    const int64_t g = (int64_t)blockIdx.x * PF_THREADS + threadIdx.x;
-    const int64_t row0 = g * ROWS_PER_THREAD;
-    float vals[4] = {0.f, 0.f, 0.f, 0.f};
-    bool valid[4] = {false, false, false, false};
-    if (row0 < n) {
+k_pf_update(const float* __restrict__ xg, const float* __restrict__ xfa, const float* loglik_in,
+            float* loglik, int64_t n, float z0h, float z0l, float z1h, float z1l,
+            const __grid_constant__ MixDensity2f md, float* block_max, float* block_sum, unsigned int* ticket,
+            double* stats) {
+    const int64_t groups = (n + 3) >> 2;
+    const int64_t stride = (int64_t)gridDim.x * PF_THREADS;
+    MaxSumExp acc;
+    for (int64_t g = (int64_t)blockIdx.x * PF_THREADS + threadIdx.x; g < groups; g += stride) {
+        const int64_t row0 = g * ROWS_PER_THREAD;
         const float4 cg = ld_stream4(xg + row0);
         const float4 cf = ld_stream4(xfa + row0);
-        const float4 lw = ld_stream4(loglik + row0);
+        float4 lw = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!LL_ZERO) lw = ld_stream4(loglik_in + row0);
         const float a[4] = {cg.x, cg.y, cg.z, cg.w};
         const float b[4] = {cf.x, cf.y, cf.z, cf.w};
         const float l[4] = {lw.x, lw.y, lw.z, lw.w};
+        float vals[4];
+        bool valid[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             const float e0 = __fadd_rn(__fsub_rn(z0h, output_glucose(a[r])), z0l);   // e = z - y   (:82)
@@ -161,26 +193,32 @@ k_pf_update(const float* __restrict__ xg, const float* __restrict__ xfa, float* 
             valid[r] = (row0 + r) < n;
         }
         st_stream4(loglik + row0, make_float4(vals[0], vals[1], vals[2], vals[3]));
+        acc.add<4>(vals, valid);
     }
-    block_max_sumexp_finalize<PF_THREADS, 4>(vals, valid, block_max, block_sum, ticket, stats);
+    block_merge_max_sumexp<PF_THREADS>(acc.m, acc.s, block_max, block_sum, ticket, stats);
 }
 
-extern "C" int gse_pf_update(gse_ctx* ctx, const float* x_dev, int64_t ld, int64_t n, float* loglik_dev,
-                             const double u[GSE_NU], const double z[GSE_NY], double* stats_dev, void* stream) {
+extern "C" int gse_pf_update(gse_ctx* ctx, const float* x_dev, int64_t ld, int64_t n, const float* loglik_in_dev,
+                             float* loglik_dev, const double u[GSE_NU], const double z[GSE_NY], double* stats_dev,
+                             void* stream) {
     GSE_REQUIRE(ctx != NULL && z != NULL && stats_dev != NULL, "ctx / z / stats is NULL");
     GSE_REQUIRE(n >= 1 && n <= ctx->n_max, "n out of range for this context");
     CHECK_SOA(x_dev, ld, n);
     GSE_REQUIRE(loglik_dev != NULL && aligned16(loglik_dev), "loglik must be 16-byte aligned");
+    GSE_REQUIRE(loglik_in_dev == NULL || aligned16(loglik_in_dev), "loglik_in must be 16-byte aligned");
     (void)u;   // static_outputs ignores u (BioreactorModel.py:250)
     const int64_t groups = gse_div_up(n, ROWS_PER_THREAD);
-    const unsigned blocks = (unsigned)gse_div_up(groups, PF_THREADS);
+    int64_t nblk = gse_div_up(groups, PF_THREADS);
+    if (nblk > (int64_t)ctx->num_sms * 8) nblk = (int64_t)ctx->num_sms * 8;      // persistent: 8 CTAs of 256 per SM
+    const unsigned blocks = (unsigned)nblk;
     GSE_REQUIRE((int64_t)blocks <= ctx->max_blocks, "workspace too small");
     const float z0h = (float)z[0], z1h = (float)z[1];
     const float z0l = (float)(z[0] - (double)z0h), z1l = (float)(z[1] - (double)z1h);
-#define LAUNCH_UPDATE(ND)                                                                                   \
-    k_pf_update<ND><<<blocks, PF_THREADS, 0, (cudaStream_t)stream>>>(                                          \
-        x_dev + 0 * ld, x_dev + 2 * ld, loglik_dev, n, z0h, z0l, z1h, z1l, ctx->meas_density32, ctx->block_max, \
-        ctx->block_sum, ctx->ticket, stats_dev)
+#define LAUNCH_UPDATE_Z(ND, ZERO)                                                                           \
+    k_pf_update<ND, ZERO><<<blocks, PF_THREADS, 0, (cudaStream_t)stream>>>(                                    \
+        x_dev + 0 * ld, x_dev + 2 * ld, loglik_in_dev, loglik_dev, n, z0h, z0l, z1h, z1l, ctx->meas_density32, \
+        ctx->block_max, ctx->block_sum, ctx->ticket, stats_dev)
+#define LAUNCH_UPDATE(ND) do { if (loglik_in_dev) LAUNCH_UPDATE_Z(ND, false); else LAUNCH_UPDATE_Z(ND, true); } while (0)
     switch (ctx->meas_density32.nd) {
         case 1: LAUNCH_UPDATE(1); break;
         case 2: LAUNCH_UPDATE(2); break;
@@ -189,6 +227,7 @@ extern "C" int gse_pf_update(gse_ctx* ctx, const float* x_dev, int64_t ld, int64
         default: LAUNCH_UPDATE(0); break;
     }
 #undef LAUNCH_UPDATE
+#undef LAUNCH_UPDATE_Z
     GSE_CHECK_LAUNCH(ctx);
     return GSE_OK;
 }
@@ -196,24 +235,28 @@ extern "C" int gse_pf_update(gse_ctx* ctx, const float* x_dev, int64_t ld, int64
 __global__ void __launch_bounds__(PF_THREADS)
 k_loglik_max(const float* __restrict__ loglik, int64_t n, float* block_max, float* block_sum,
              unsigned int* ticket, double* stats) {
-    const int64_t g = (int64_t)blockIdx.x * PF_THREADS + threadIdx.x;
-    const int64_t row0 = g * ROWS_PER_THREAD;
-    float vals[4] = {0.f, 0.f, 0.f, 0.f};
-    bool valid[4] = {false, false, false, false};
-    if (row0 < n) {
+    const int64_t groups = (n + 3) >> 2;
+    const int64_t stride = (int64_t)gridDim.x * PF_THREADS;
+    MaxSumExp acc;
+    for (int64_t g = (int64_t)blockIdx.x * PF_THREADS + threadIdx.x; g < groups; g += stride) {
+        const int64_t row0 = g * ROWS_PER_THREAD;
         const float4 lw = ld_stream4(loglik + row0);
-        vals[0] = lw.x; vals[1] = lw.y; vals[2] = lw.z; vals[3] = lw.w;
+        const float vals[4] = {lw.x, lw.y, lw.z, lw.w};
+        bool valid[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) valid[r] = (row0 + r) < n;
+        acc.add<4>(vals, valid);
     }
-    block_max_sumexp_finalize<PF_THREADS, 4>(vals, valid, block_max, block_sum, ticket, stats);
+    block_merge_max_sumexp<PF_THREADS>(acc.m, acc.s, block_max, block_sum, ticket, stats);
 }
 
 extern "C" int gse_loglik_max(gse_ctx* ctx, const float* loglik_dev, int64_t n, double* stats_dev, void* stream) {
     GSE_REQUIRE(ctx != NULL && stats_dev != NULL, "ctx / stats is NULL");
     GSE_REQUIRE(n >= 1 && n <= ctx->n_max, "n out of range for this context");
     GSE_REQUIRE(loglik_dev != NULL && aligned16(loglik_dev), "loglik must be 16-byte aligned");
-    const unsigned blocks = (unsigned)gse_div_up(gse_div_up(n, ROWS_PER_THREAD), PF_THREADS);
+    int64_t nblk = gse_div_up(gse_div_up(n, ROWS_PER_THREAD), PF_THREADS);
+    if (nblk > (int64_t)ctx->num_sms * 8) nblk = (int64_t)ctx->num_sms * 8;
+    const unsigned blocks = (unsigned)nblk;
     k_loglik_max<<<blocks, PF_THREADS, 0, (cudaStream_t)stream>>>(loglik_dev, n, ctx->block_max, ctx->block_sum,
                                                                    ctx->ticket, stats_dev);
     GSE_CHECK_LAUNCH(ctx);
@@ -248,16 +291,16 @@ extern "C" int gse_weights_linear(gse_ctx* ctx, const float* loglik_dev, const d
 // out: [0] S0, [1..5] S1, [6..20] S2 lower triangle, [21..25] pivot; (GSF: [26..40] sum w P)
 // ------------------------------------------------------------------------------------------------
 #define MOM_THREADS 256
-template <int NEXTRA>
+template <int NEXTRA, bool GATHER>
 __global__ void __launch_bounds__(MOM_THREADS)
 k_moments(const float* __restrict__ x, const float* __restrict__ extra, int64_t ld, int64_t n,
-          const float* __restrict__ loglik, const double* __restrict__ base,
+          const int32_t* __restrict__ idx, const float* __restrict__ loglik, const double* __restrict__ base,
           const double* __restrict__ stats, double* partials, unsigned int* ticket, double* out) {
     constexpr int NV = 21 + NEXTRA;
     const float M = (float)stats[0];
     float p[5];
 #pragma unroll
-    for (int j = 0; j < 5; ++j) p[j] = __ldg(x + j * ld);
+    for (int j = 0; j < 5; ++j) p[j] = __ldg(x + j * ld + (GATHER ? idx[0] : 0));
     double acc[NV];
 #pragma unroll
     for (int k = 0; k < NV; ++k) acc[k] = 0.0;
@@ -265,8 +308,19 @@ k_moments(const float* __restrict__ x, const float* __restrict__ extra, int64_t 
     for (int64_t g = (int64_t)blockIdx.x * MOM_THREADS + threadIdx.x; g < groups; g += (int64_t)gridDim.x * MOM_THREADS) {
         const int64_t row0 = g * 4;
         float4 c[5];
+        int id[4] = {0, 0, 0, 0};
+        if (GATHER) {
+            const int4 id4 = *reinterpret_cast<const int4*>(idx + row0);
+            id[0] = id4.x; id[1] = (row0 + 1 < n) ? id4.y : id4.x; id[2] = (row0 + 2 < n) ? id4.z : id4.x;
+            id[3] = (row0 + 3 < n) ? id4.w : id4.x;
 #pragma unroll
-        for (int j = 0; j < 5; ++j) c[j] = ld_stream4(x + j * ld + row0);
+            for (int j = 0; j < 5; ++j)
+                c[j] = make_float4(__ldg(x + j * ld + id[0]), __ldg(x + j * ld + id[1]), __ldg(x + j * ld + id[2]),
+                                   __ldg(x + j * ld + id[3]));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 5; ++j) c[j] = ld_stream4(x + j * ld + row0);
+        }
         float4 lw = make_float4(0.f, 0.f, 0.f, 0.f);
         if (loglik) lw = ld_stream4(loglik + row0);
         const float l[4] = {lw.x, lw.y, lw.z, lw.w};
@@ -277,7 +331,7 @@ k_moments(const float* __restrict__ x, const float* __restrict__ extra, int64_t 
                 if (base) w *= base[row0 + r];
                 double d[5];
 #pragma unroll
-                for (int j = 0; j < 5; ++j) d[j] = (double)(reinterpret_cast<const float*>(&c[j])[r] - p[j]);
+                for (int j = 0; j < 5; ++j) d[j] = (double)reinterpret_cast<const float*>(&c[j])[r] - (double)p[j];   // exact
                 acc[0] += w;
                 int t = 6;
 #pragma unroll
@@ -289,7 +343,8 @@ k_moments(const float* __restrict__ x, const float* __restrict__ extra, int64_t 
                 }
                 if (NEXTRA > 0) {
 #pragma unroll
-                    for (int k = 0; k < NEXTRA; ++k) acc[21 + k] = fma(w, (double)extra[k * ld + row0 + r], acc[21 + k]);
+                    for (int k = 0; k < NEXTRA; ++k)
+                        acc[21 + k] = fma(w, (double)extra[k * ld + (GATHER ? (int64_t)id[r] : row0 + r)], acc[21 + k]);
                 }
             }
         }
@@ -325,34 +380,39 @@ k_moments(const float* __restrict__ x, const float* __restrict__ extra, int64_t 
 }
 
 static int launch_moments(gse_ctx* ctx, const float* x, const float* extra, int64_t ld, int64_t n,
-                          const float* loglik, const double* base, const double* stats, double* out,
+                          const int32_t* idx, const float* loglik, const double* base, const double* stats, double* out,
                           void* stream) {
     GSE_REQUIRE(ctx != NULL && stats != NULL && out != NULL, "ctx / stats / out is NULL");
     GSE_REQUIRE(n >= 1 && n <= ctx->n_max, "n out of range for this context");
-    CHECK_SOA(x, ld, n);
+    if (idx == NULL) { CHECK_SOA(x, ld, n); }
     const int64_t groups = gse_div_up(n, 4);
     int64_t blocks = gse_div_up(groups, MOM_THREADS);
     const int64_t cap = (int64_t)ctx->num_sms * 8;
     if (blocks > cap) blocks = cap;
     if (blocks > 2048) blocks = 2048;
-    if (extra)
-        k_moments<15><<<(unsigned)blocks, MOM_THREADS, 0, (cudaStream_t)stream>>>(x, extra, ld, n, loglik, base, stats, ctx->red_partials, ctx->ticket + 2, out);
-    else
-        k_moments<0><<<(unsigned)blocks, MOM_THREADS, 0, (cudaStream_t)stream>>>(x, NULL, ld, n, loglik, base, stats, ctx->red_partials, ctx->ticket + 2, out);
+    GSE_REQUIRE(idx == NULL || aligned16(idx), "idx must be 16-byte aligned");
+#define LAUNCH_MOM(NE, G, EX)                                                                                \
+    k_moments<NE, G><<<(unsigned)blocks, MOM_THREADS, 0, (cudaStream_t)stream>>>(x, EX, ld, n, idx, loglik, base, \
+                                                                                 stats, ctx->red_partials,     \
+                                                                                 ctx->ticket + 2, out)
+    if (extra) { if (idx) LAUNCH_MOM(15, true, extra); else LAUNCH_MOM(15, false, extra); }
+    else { if (idx) LAUNCH_MOM(0, true, NULL); else LAUNCH_MOM(0, false, NULL); }
+#undef LAUNCH_MOM
     GSE_CHECK_LAUNCH(ctx);
     return GSE_OK;
 }
 
-extern "C" int gse_pf_moments(gse_ctx* ctx, const float* x_dev, int64_t ld, int64_t n, const float* loglik_dev,
-                              const double* base_dev, const double* stats_dev, double* out_dev, void* stream) {
-    return launch_moments(ctx, x_dev, NULL, ld, n, loglik_dev, base_dev, stats_dev, out_dev, stream);
+extern "C" int gse_pf_moments(gse_ctx* ctx, const float* x_dev, int64_t ld, int64_t n, const int32_t* idx_dev,
+                              const float* loglik_dev, const double* base_dev, const double* stats_dev,
+                              double* out_dev, void* stream) {
+    return launch_moments(ctx, x_dev, NULL, ld, n, idx_dev, loglik_dev, base_dev, stats_dev, out_dev, stream);
 }
 
 extern "C" int gse_gsf_moments(gse_ctx* ctx, const float* mean_dev, const float* cov_dev, int64_t ld, int64_t n,
-                               const float* loglik_dev, const double* base_dev, const double* stats_dev,
-                               double* out_dev, void* stream) {
+                               const int32_t* idx_dev, const float* loglik_dev, const double* base_dev,
+                               const double* stats_dev, double* out_dev, void* stream) {
     GSE_REQUIRE(cov_dev != NULL, "cov is NULL");
-    return launch_moments(ctx, mean_dev, cov_dev, ld, n, loglik_dev, base_dev, stats_dev, out_dev, stream);
+    return launch_moments(ctx, mean_dev, cov_dev, ld, n, idx_dev, loglik_dev, base_dev, stats_dev, out_dev, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

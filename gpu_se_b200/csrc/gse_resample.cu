@@ -1,12 +1,12 @@
 // Systematic resampling: fixed-point weight scan (K3a tile sums, K3b scan), merge-path partition
-// and the fused search + gather (K4+K5).  Shared by the particle filter and the GS-UKF.
+// the search (K4) and the materialising gather (K5).  Shared by the particle filter and the GS-UKF.
 //
 // Weights are quantised to integers q_i = rint(w_i * 2^s) and summed with integer adds.  Integer
 // addition is associative, so the cumulative weights are independent of the scan structure, the
 // launch geometry and the number of GPUs, and every comparison below is exact.
 //
-// The scan is reduce-then-scan (tile sums -> offsets -> in-tile scan) rather than a single pass
-// with look-back: both kernels are pure streaming kernels with no inter-block waiting.
+// The scan is reduce-then-scan (per-warp run sums -> offsets -> in-run scan) rather than a single
+// pass with look-back: both kernels are pure streaming kernels with no inter-block waiting.
 #include "gse_common.cuh"
 
 #define TILE_THREADS 256
@@ -97,49 +97,71 @@ __device__ __forceinline__ uint64_t warp_inclusive_scan_u64(uint64_t v, int lane
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3a: per-tile sums of the quantised weights; the last block to finish turns them into exclusive
-// tile offsets (fixed order) and writes the grand total.
+// K3a / K3b.  Persistent grid; every WARP owns a contiguous run of 512-row tiles and walks it with
+// a running carry in registers, so neither pass has a block-level barrier on its data path.
+//   K3a: sum of the warp's run -> warp_sum[w]; the last block to finish turns the (at most a few
+//        thousand) warp sums into exclusive offsets warp_off[w] in a fixed order and writes the total.
+//   K3b: re-quantise, scan inside the warp (shuffles), add the carry, store the cumulative weights.
 // ------------------------------------------------------------------------------------------------
+#define WTILE_ROWS (32 * TILE_ITEMS)               // 512 rows per warp tile
+#define SCAN_WARPS (TILE_THREADS / 32)
+
+struct ScanGeom {
+    int64_t ntiles;        // ceil(n / 512)
+    int64_t tiles_per_warp;
+    int nwarps;            // warps that own at least one tile
+};
+
+static ScanGeom scan_geometry(int64_t n, int num_sms, unsigned* blocks) {
+    ScanGeom g;
+    g.ntiles = gse_div_up(n, WTILE_ROWS);
+    const int64_t max_warps = (int64_t)num_sms * 4 * SCAN_WARPS;     // 4 resident CTAs per SM at 64 registers
+    g.tiles_per_warp = gse_div_up(g.ntiles, max_warps);
+    g.nwarps = (int)gse_div_up(g.ntiles, g.tiles_per_warp);
+    *blocks = (unsigned)gse_div_up(g.nwarps, SCAN_WARPS);
+    return g;
+}
+
 template <bool HAS_LL, bool HAS_BASE>
 __global__ void __launch_bounds__(TILE_THREADS)
 k_weight_tile_sums(const float* __restrict__ loglik, const double* __restrict__ base,
-                   const double* __restrict__ stats, int64_t n, uint64_t* tile_sum, uint64_t* tile_off,
-                   uint64_t* total_out, unsigned int* ticket) {
-    __shared__ uint64_t s_w[TILE_THREADS / 32];
+                   const double* __restrict__ stats, int64_t n, const ScanGeom geo, uint64_t* warp_sum,
+                   uint64_t* warp_off, uint64_t* total_out, unsigned int* ticket) {
     __shared__ uint64_t s_scan[TILE_THREADS];
     __shared__ bool s_last;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const float M = HAS_LL ? (float)stats[0] : 0.0f;
     const int sexp = quantisation_exponent(stats[1]);
-    const int64_t row0 = (int64_t)blockIdx.x * TILE_ROWS + (int64_t)tid * TILE_ITEMS;
-    uint64_t q[TILE_ITEMS];
-    uint64_t sum = 0;
-    if (row0 < n) {
-        quantise16<HAS_LL, HAS_BASE>(loglik, base, M, sexp, row0, n, q);
+    const int w = blockIdx.x * SCAN_WARPS + wid;
+    if (w < geo.nwarps) {
+        const int64_t t0 = (int64_t)w * geo.tiles_per_warp;
+        const int64_t t1 = min(t0 + geo.tiles_per_warp, geo.ntiles);
+        uint64_t sum = 0;
+        for (int64_t t = t0; t < t1; ++t) {
+            const int64_t row0 = t * WTILE_ROWS + (int64_t)lane * TILE_ITEMS;
+            if (row0 < n) {
+                uint64_t q[TILE_ITEMS];
+                quantise16<HAS_LL, HAS_BASE>(loglik, base, M, sexp, row0, n, q);
 #pragma unroll
-        for (int r = 0; r < TILE_ITEMS; ++r) sum += q[r];
+                for (int r = 0; r < TILE_ITEMS; ++r) sum += q[r];
+            }
+        }
+        sum = warp_sum_u64(sum);
+        if (lane == 0) warp_sum[w] = sum;
     }
-    sum = warp_sum_u64(sum);
-    if (lane == 0) s_w[wid] = sum;
+    __threadfence();
     __syncthreads();
-    if (tid == 0) {
-        uint64_t t = 0;
-#pragma unroll
-        for (int w = 0; w < TILE_THREADS / 32; ++w) t += s_w[w];
-        tile_sum[blockIdx.x] = t;
-        __threadfence();
-        s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
-    }
+    if (tid == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    // exclusive scan of gridDim.x tile sums by one block: contiguous chunk per thread
-    const unsigned int nt = gridDim.x;
-    const unsigned int chunk = (nt + TILE_THREADS - 1) / TILE_THREADS;
-    const unsigned int b0 = tid * chunk;
+    // exclusive scan of nwarps sums by one block: contiguous chunk per thread
+    const int nt = geo.nwarps;
+    const int chunk = (nt + TILE_THREADS - 1) / TILE_THREADS;
+    const int b0 = tid * chunk;
     uint64_t part = 0;
-    for (unsigned int k = 0; k < chunk; ++k)
-        if (b0 + k < nt) part += __ldcg(tile_sum + b0 + k);
+    for (int k = 0; k < chunk; ++k)
+        if (b0 + k < nt) part += __ldcg(warp_sum + b0 + k);
     s_scan[tid] = part;
     __syncthreads();
     if (wid == 0) {                                     // 256 partials: 8 per lane
@@ -155,48 +177,48 @@ k_weight_tile_sums(const float* __restrict__ loglik, const double* __restrict__ 
     }
     __syncthreads();
     uint64_t run = s_scan[tid];
-    for (unsigned int k = 0; k < chunk; ++k) {
+    for (int k = 0; k < chunk; ++k) {
         if (b0 + k < nt) {
-            tile_off[b0 + k] = run;
-            run += __ldcg(tile_sum + b0 + k);
+            warp_off[b0 + k] = run;
+            run += __ldcg(warp_sum + b0 + k);
         }
     }
     if (tid == 0) *ticket = 0u;
 }
 
-// ------------------------------------------------------------------------------------------------
-// K3b: in-tile inclusive scan + tile offset -> cumulative weights.
-// ------------------------------------------------------------------------------------------------
 template <bool HAS_LL, bool HAS_BASE>
 __global__ void __launch_bounds__(TILE_THREADS)
 k_weight_scan(const float* __restrict__ loglik, const double* __restrict__ base,
-              const double* __restrict__ stats, int64_t n, const uint64_t* __restrict__ tile_off,
-              uint64_t* __restrict__ cumsum) {
-    __shared__ uint64_t s_w[TILE_THREADS / 32];
+              const double* __restrict__ stats, int64_t n, const ScanGeom geo,
+              const uint64_t* __restrict__ warp_off, uint64_t* __restrict__ cumsum) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int w = blockIdx.x * SCAN_WARPS + wid;
+    if (w >= geo.nwarps) return;
     const float M = HAS_LL ? (float)stats[0] : 0.0f;
     const int sexp = quantisation_exponent(stats[1]);
-    const int64_t row0 = (int64_t)blockIdx.x * TILE_ROWS + (int64_t)tid * TILE_ITEMS;
-    uint64_t q[TILE_ITEMS];
+    const int64_t t0 = (int64_t)w * geo.tiles_per_warp;
+    const int64_t t1 = min(t0 + geo.tiles_per_warp, geo.ntiles);
+    uint64_t carry = warp_off[w];
+    for (int64_t t = t0; t < t1; ++t) {
+        const int64_t row0 = t * WTILE_ROWS + (int64_t)lane * TILE_ITEMS;
+        uint64_t q[TILE_ITEMS];
 #pragma unroll
-    for (int r = 0; r < TILE_ITEMS; ++r) q[r] = 0;
-    if (row0 < n) quantise16<HAS_LL, HAS_BASE>(loglik, base, M, sexp, row0, n, q);
+        for (int r = 0; r < TILE_ITEMS; ++r) q[r] = 0;
+        if (row0 < n) quantise16<HAS_LL, HAS_BASE>(loglik, base, M, sexp, row0, n, q);
 #pragma unroll
-    for (int r = 1; r < TILE_ITEMS; ++r) q[r] += q[r - 1];
-    const uint64_t incl = warp_inclusive_scan_u64(q[TILE_ITEMS - 1], lane);
-    if (lane == 31) s_w[wid] = incl;
-    __syncthreads();
-    uint64_t off = tile_off[blockIdx.x] + (incl - q[TILE_ITEMS - 1]);
+        for (int r = 1; r < TILE_ITEMS; ++r) q[r] += q[r - 1];
+        const uint64_t incl = warp_inclusive_scan_u64(q[TILE_ITEMS - 1], lane);
+        const uint64_t off = carry + (incl - q[TILE_ITEMS - 1]);
+        if (row0 + TILE_ITEMS <= n) {
 #pragma unroll
-    for (int w = 0; w < TILE_THREADS / 32; ++w) off += (w < wid) ? s_w[w] : 0;
-    if (row0 + TILE_ITEMS <= n) {
+            for (int v = 0; v < TILE_ITEMS / 4; ++v)
+                st_u64x4(cumsum + row0 + 4 * v, off + q[4 * v], off + q[4 * v + 1], off + q[4 * v + 2], off + q[4 * v + 3]);
+        } else {
 #pragma unroll
-        for (int v = 0; v < TILE_ITEMS / 4; ++v)
-            st_u64x4(cumsum + row0 + 4 * v, off + q[4 * v], off + q[4 * v + 1], off + q[4 * v + 2], off + q[4 * v + 3]);
-    } else {
-#pragma unroll
-        for (int r = 0; r < TILE_ITEMS; ++r)
-            if (row0 + r < n) cumsum[row0 + r] = off + q[r];
+            for (int r = 0; r < TILE_ITEMS; ++r)
+                if (row0 + r < n) cumsum[row0 + r] = off + q[r];
+        }
+        carry += __shfl_sync(0xffffffffu, incl, 31);
     }
 }
 
@@ -209,17 +231,18 @@ extern "C" int gse_scan_weights(gse_ctx* ctx, const float* loglik_dev, const dou
     GSE_REQUIRE(loglik_dev == NULL || aligned32(loglik_dev), "loglik must be 32-byte aligned");
     GSE_REQUIRE(base_dev == NULL || aligned32(base_dev), "base must be 32-byte aligned");
     GSE_REQUIRE(aligned32(cumsum_dev), "cumsum must be 32-byte aligned");
-    const int64_t tiles = gse_div_up(n, TILE_ROWS);
-    GSE_REQUIRE(tiles <= ctx->max_tiles, "workspace too small");
+    unsigned g = 0;
+    const ScanGeom geo = scan_geometry(n, ctx->num_sms, &g);
+    GSE_REQUIRE(geo.nwarps <= ctx->max_tiles, "workspace too small");
     cudaStream_t s = (cudaStream_t)stream;
-    const unsigned g = (unsigned)tiles;
 #define LAUNCH_SCAN(LL, BASE)                                                                                   \
     do {                                                                                                        \
-        k_weight_tile_sums<LL, BASE><<<g, TILE_THREADS, 0, s>>>(loglik_dev, base_dev, stats_dev, n, ctx->tile_agg, \
-                                                                ctx->tile_inc, total_dev, ctx->ticket + 1);     \
+        k_weight_tile_sums<LL, BASE><<<g, TILE_THREADS, 0, s>>>(loglik_dev, base_dev, stats_dev, n, geo,        \
+                                                                ctx->tile_agg, ctx->tile_inc, total_dev,        \
+                                                                ctx->ticket + 1);                               \
         GSE_CHECK_LAUNCH(ctx);                                                                                  \
-        k_weight_scan<LL, BASE><<<g, TILE_THREADS, 0, s>>>(loglik_dev, base_dev, stats_dev, n, ctx->tile_inc,   \
-                                                           cumsum_dev);                                         \
+        k_weight_scan<LL, BASE><<<g, TILE_THREADS, 0, s>>>(loglik_dev, base_dev, stats_dev, n, geo,             \
+                                                           ctx->tile_inc, cumsum_dev);                          \
         GSE_CHECK_LAUNCH(ctx);                                                                                  \
     } while (0)
     if (loglik_dev && base_dev) LAUNCH_SCAN(true, true);
@@ -233,11 +256,12 @@ extern "C" int gse_scan_weights(gse_ctx* ctx, const float* loglik_dev, const dou
 // Merge-path partition.  Sources k (cumulative weights C_k) and outputs i (thresholds q*_i) are two
 // sorted sequences; source k precedes output i in the merged order iff C_k < q*_i, so that
 // idx_i = #{k : C_k < q*_i} = number of sources merged before output i.  Block b owns merged
-// elements [b*W, (b+1)*W): at most W sources staged in shared memory and at most W outputs.
+// elements [b*W, (b+1)*W): at most W sources and at most W outputs, both staged in shared memory.
 // One warp finds each split point with a 32-ary search (5 rounds of dependent loads at 2^24).
 // ------------------------------------------------------------------------------------------------
-#define RG_THREADS 512
-#define RG_WORK 4096
+#define RS_THREADS 256
+#define RS_VT 16
+#define RS_WORK (RS_THREADS * RS_VT)      // 4096 merged elements per block
 
 struct ResampleArgs {
     const uint64_t* cumsum;
@@ -255,31 +279,23 @@ struct ResampleArgs {
 // i iff fl(C_k / T) < u_i.  Its integer threshold q*(u) lies in [qa - 2, qa + 2] with
 // qa = floor(fl(u * T)) (T < 2^53: the product is within 1/2 of the real value and the rounding
 // boundary below u is less than 2 away from u * T), so the comparison is decided by two integer
-// compares except inside that 5-wide window, where the float64 division is evaluated for real.
-// The spacing of consecutive cumulative weights is ~T / n, so the window is hit with probability
-// ~5 n / 2^52 per probe.
-struct OutputKey {
-    double u;          // sample position (i + r) / N
-    uint64_t q_lo;     // local lower bound  (qa - 2) - offset, saturating at 0
-    uint64_t q_hi;     // local upper bound  (qa + 2) - offset, saturating at 0
-};
-
-__device__ __forceinline__ OutputKey output_key(const ResampleArgs& a, double di, uint64_t off, double Td) {
-    OutputKey k;
-    k.u = gse_sample_position(di, a.r, a.n_total, a.inv_n, a.n_pow2 != 0);
-    const uint64_t qa = __double2ull_rd(__dmul_rn(k.u, Td));
-    const uint64_t lo = qa > 2 ? qa - 2 : 0;
-    const uint64_t hi = qa + 2;
-    k.q_lo = lo > off ? lo - off : 0ull;
-    k.q_hi = hi > off ? hi - off : 0ull;
-    return k;
+// compares against q_lo = qa - 2 (local: minus the shard offset, saturating at 0) and q_lo + 4,
+// except inside that window, where the float64 division is evaluated for real.  The spacing of
+// consecutive cumulative weights is ~T / n, so the window is hit with probability ~5 n / 2^52.
+__device__ __forceinline__ double sample_u(const ResampleArgs& a, double di) {
+    return gse_sample_position(di, a.r, a.n_total, a.inv_n, a.n_pow2 != 0);
 }
-
-// does the source with LOCAL cumulative weight c precede the output?  (exact)
-__device__ __forceinline__ bool precedes(uint64_t c, const OutputKey& k, uint64_t off, double Td) {
-    if (c < k.q_lo) return true;
-    if (c >= k.q_hi) return false;
-    return __ddiv_rn(__ull2double_rn(c + off), Td) < k.u;
+__device__ __forceinline__ uint64_t output_qlo(const ResampleArgs& a, double di, uint64_t off, double Td) {
+    const uint64_t qa = __double2ull_rd(__dmul_rn(sample_u(a, di), Td));
+    const uint64_t lo = qa > 2 ? qa - 2 : 0;
+    return lo > off ? lo - off : 0ull;
+}
+// does the source with LOCAL cumulative weight c precede the output with global index di?  (exact)
+__device__ __forceinline__ bool precedes(const ResampleArgs& a, uint64_t c, uint64_t q_lo, double di,
+                                         uint64_t off, double Td) {
+    if (c < q_lo) return true;
+    if (c >= q_lo + 4) return false;
+    return __ddiv_rn(__ull2double_rn(c + off), Td) < sample_u(a, di);
 }
 
 __global__ void __launch_bounds__(128)
@@ -289,7 +305,7 @@ k_resample_partition(const ResampleArgs a, int64_t* __restrict__ part, int64_t n
     if (b > nparts) return;
     const uint64_t off = a.offtot[0];
     const double Td = __ull2double_rn(a.offtot[1]);
-    int64_t diag = b * RG_WORK;
+    int64_t diag = b * RS_WORK;
     const int64_t total = a.n_src + a.n_out;
     if (diag > total) diag = total;
     int64_t lo = diag > a.n_out ? diag - a.n_out : 0;
@@ -310,8 +326,8 @@ k_resample_partition(const ResampleArgs a, int64_t* __restrict__ part, int64_t n
         bool pred = false;
         if (active) {
             const uint64_t c = a.cumsum[mid];
-            const OutputKey k = output_key(a, (double)(a.out0 + (diag - 1 - mid)), off, Td);
-            pred = precedes(c, k, off, Td);
+            const double di = (double)(a.out0 + (diag - 1 - mid));
+            pred = precedes(a, c, output_qlo(a, di, off, Td), di, off, Td);
         }
         const unsigned int bal = __ballot_sync(0xffffffffu, pred);
         const int ntrue = __popc(bal);                              // trues form a prefix of the lanes
@@ -327,86 +343,90 @@ k_resample_partition(const ResampleArgs a, int64_t* __restrict__ part, int64_t n
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4+K5: per block, stage the source window of cumulative weights in shared memory.  Each warp
-// owns a run of 256 consecutive outputs and walks it 32 at a time: lane l holds output base + l, so
-// the 32 thresholds of a round are adjacent and non-decreasing -- the search range starts at the
-// previous round's last position and is capped 64 sources ahead when that bound holds (it does
-// unless the round crosses a stretch of sources without offspring), and the gathered rows are
-// written by consecutive lanes to consecutive addresses.
+// K4: search.  Per block: stage the source window of cumulative weights in shared memory together
+// with the EXACT integer threshold q*(u_i) of every output of the window (gse_threshold: one
+// 64 x 64 -> 128-bit product per output, no division), so that "source k precedes output i" is the
+// single integer compare C_k < q*_i from here on.  The <= 4096 merged elements are split between
+// the threads (merge path, binary search in shared memory) and every thread merges its 16 elements
+// serially.  idx_i = number of sources merged before output i; written back coalesced as int32.
 // ------------------------------------------------------------------------------------------------
-#define RG_WARPS (RG_THREADS / 32)
-#define RG_CHUNK (RG_WORK / RG_WARPS)      // 256 outputs per warp
-
-__global__ void __launch_bounds__(RG_THREADS)
-k_resample_gather(const ResampleArgs a, const int64_t* __restrict__ part, const float* __restrict__ src,
-                  int64_t ld_src, float* __restrict__ dst, int64_t ld_dst, int ncols,
-                  float* __restrict__ loglik_out, int64_t* __restrict__ idx_out) {
-    __shared__ uint64_t s_c[RG_WORK];
+__global__ void __launch_bounds__(RS_THREADS)
+k_resample_search(const ResampleArgs a, const int64_t* __restrict__ part, int32_t* __restrict__ idx_out) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    uint64_t* s_c = reinterpret_cast<uint64_t*>(s_raw);                 // [RS_WORK] local cumulative weights
+    uint64_t* s_q = s_c + RS_WORK;                                      // [RS_WORK] local thresholds, then idx
+    int* s_split = reinterpret_cast<int*>(s_q + RS_WORK);               // [RS_THREADS + 1]
+    const int tid = threadIdx.x;
     const int64_t b = blockIdx.x;
     const int64_t total = a.n_src + a.n_out;
-    int64_t d0 = b * RG_WORK, d1 = d0 + RG_WORK;
+    int64_t d0 = b * RS_WORK, d1 = d0 + RS_WORK;
     if (d1 > total) d1 = total;
     const int64_t a0 = part[b], a1 = part[b + 1];
     const int64_t o0 = d0 - a0, o1 = d1 - a1;
     if (o1 <= o0) return;                                  // a stretch of sources with no offspring
     const int ns = (int)(a1 - a0);
     const int no = (int)(o1 - o0);
-    for (int k = threadIdx.x; k < ns; k += RG_THREADS) s_c[k] = a.cumsum[a0 + k];
-    __syncthreads();
+    const int nm = ns + no;
     const uint64_t off = a.offtot[0];
-    const double Td = __ull2double_rn(a.offtot[1]);
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int jbeg = wid * RG_CHUNK;
-    const int jend = min(jbeg + RG_CHUNK, no);
-    if (jbeg >= jend) return;
-    double di = (double)(a.out0 + o0 + jbeg + lane);
-    int lo = 0;                                            // warp-uniform: every earlier source precedes
-    for (int base = jbeg; base < jend; base += 32, di += 32.0) {
-        const int j = base + lane;
-        const bool valid = j < jend;
-        const int last = min(31, jend - 1 - base);         // last valid lane of this round
-        const OutputKey key = output_key(a, di, off, Td);
-        // upper end of the search range, warp-uniform
-        const uint64_t qmax = __shfl_sync(0xffffffffu, key.q_lo, last);
-        int hi = min(lo + 64, ns);
-        if (hi < ns && s_c[hi - 1] < qmax) hi = ns;
-        int l = lo, h = hi;                                // first k in [lo, hi) with C_k >= q_lo, else hi
-        while (l < h) {
-            const int mid = (l + h) >> 1;
-            if (s_c[mid] < key.q_lo) l = mid + 1; else h = mid;
+    const uint64_t T = a.offtot[1];
+    const double dbase = (double)(a.out0 + o0);            // global index of the block's first output
+    for (int k = tid; k < ns; k += RS_THREADS) s_c[k] = a.cumsum[a0 + k];
+    for (int j = tid; j < no; j += RS_THREADS) {
+        const uint64_t q = gse_threshold(sample_u(a, dbase + (double)j), T);
+        s_q[j] = q > off ? q - off : 0ull;                 // C_k + off < q*  <=>  C_k < q* - off
+    }
+    __syncthreads();
+    // split point of diagonal d: smallest s with NOT (C[s] < q[d - 1 - s])
+    {
+        const int d = min(tid * RS_VT, nm);
+        int lo = max(0, d - no), hi = min(d, ns);
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (s_c[mid] < s_q[d - 1 - mid]) lo = mid + 1; else hi = mid;
         }
-        lo = __shfl_sync(0xffffffffu, l, last);
-        // resolve the (rare) sources inside the rounding window with the reference's own division
-        while (l < ns && s_c[l] < key.q_hi && precedes(s_c[l], key, off, Td)) ++l;
-        if (valid) {
-            int64_t idx = a0 + l;
-            if (idx >= a.n_src) idx = a.n_src - 1;         // only reachable through a degenerate total
-            const int64_t jo = o0 + j;
-            if (dst) {
-                for (int c = 0; c < ncols; ++c) dst[c * ld_dst + jo] = __ldg(src + c * ld_src + idx);
+        s_split[tid] = lo;
+        if (tid == 0) s_split[RS_THREADS] = ns;
+    }
+    __syncthreads();
+    {
+        const int d = min(tid * RS_VT, nm), d_end = min((tid + 1) * RS_VT, nm);
+        int sa = s_split[tid];
+        const int sa_end = s_split[tid + 1];
+        int sb = d - sa;
+        const int sb_end = d_end - sa_end;
+        int32_t* s_idx = reinterpret_cast<int32_t*>(s_q);          // low word of s_q[j]: written by its owner only
+        const int base = (int)a0;
+        uint64_t c = sa < sa_end ? s_c[sa] : ~0ull;                // exhausted side never wins the compare
+        uint64_t q = sb < sb_end ? s_q[sb] : ~0ull;
+        for (int step = d; step < d_end; ++step) {
+            if (c < q) {
+                ++sa;
+                c = sa < sa_end ? s_c[sa] : ~0ull;
+            } else {
+                s_idx[2 * sb] = base + sa;
+                ++sb;
+                q = sb < sb_end ? s_q[sb] : ~0ull;
             }
-            if (loglik_out) loglik_out[jo] = 0.0f;
-            if (idx_out) idx_out[jo] = idx;
         }
     }
+    __syncthreads();
+    const int32_t* s_idx = reinterpret_cast<const int32_t*>(s_q);
+    const int last = (int)(a.n_src - 1);                           // > last only through a degenerate total
+    for (int j = tid; j < no; j += RS_THREADS) idx_out[o0 + j] = min(s_idx[2 * j], last);
 }
 
-extern "C" int gse_resample_gather(gse_ctx* ctx, const uint64_t* cumsum_dev, int64_t n_src,
+#define RS_SMEM (2 * RS_WORK * sizeof(uint64_t) + (RS_THREADS + 1) * sizeof(int))
+
+extern "C" int gse_resample_search(gse_ctx* ctx, const uint64_t* cumsum_dev, int64_t n_src,
                                    const uint64_t* offtot_dev, double r, int64_t n_total, int64_t out0,
-                                   int64_t n_out, const float* src_dev, int64_t ld_src, float* dst_dev,
-                                   int64_t ld_dst, int ncols, float* loglik_out_dev, int64_t* idx_out_dev,
-                                   void* stream) {
-    GSE_REQUIRE(ctx != NULL && cumsum_dev != NULL && offtot_dev != NULL, "ctx / cumsum / offtot is NULL");
-    GSE_REQUIRE(n_src >= 1 && n_src <= ctx->n_max, "n_src out of range for this context");
+                                   int64_t n_out, int32_t* idx_out_dev, void* stream) {
+    GSE_REQUIRE(ctx != NULL && cumsum_dev != NULL && offtot_dev != NULL && idx_out_dev != NULL,
+                "ctx / cumsum / offtot / idx is NULL");
+    GSE_REQUIRE(n_src >= 1 && n_src <= ctx->n_max && n_src <= 0x7fffffff, "n_src out of range for this context");
     GSE_REQUIRE(n_out >= 0 && n_out <= ctx->n_max, "n_out out of range for this context");
     GSE_REQUIRE(n_total >= 1 && out0 >= 0 && out0 + n_out <= n_total, "output range outside [0, n_total)");
     GSE_REQUIRE(r >= 0.0 && r < 1.0, "r must be in [0, 1)");
     if (n_out == 0) return GSE_OK;
-    if (dst_dev) {
-        GSE_REQUIRE(src_dev != NULL && ncols >= 1, "src is NULL / ncols < 1");
-        GSE_REQUIRE(ld_src >= n_src && ld_dst >= n_out, "ld too small");
-        GSE_REQUIRE(src_dev != dst_dev, "gather cannot be done in place");
-    }
     ResampleArgs a;
     a.cumsum = cumsum_dev;
     a.offtot = offtot_dev;
@@ -417,13 +437,76 @@ extern "C" int gse_resample_gather(gse_ctx* ctx, const uint64_t* cumsum_dev, int
     a.n_total = (double)n_total;
     a.inv_n = 1.0 / (double)n_total;
     a.n_pow2 = ((n_total & (n_total - 1)) == 0) ? 1 : 0;
-    const int64_t nparts = gse_div_up(n_src + n_out, RG_WORK);
+    const int64_t nparts = gse_div_up(n_src + n_out, RS_WORK);
     GSE_REQUIRE(nparts + 1 <= ctx->max_tiles + 2, "workspace too small");
     cudaStream_t s = (cudaStream_t)stream;
     k_resample_partition<<<(unsigned)gse_div_up((nparts + 1) * 32, 128), 128, 0, s>>>(a, ctx->part, nparts);
     GSE_CHECK_LAUNCH(ctx);
-    k_resample_gather<<<(unsigned)nparts, RG_THREADS, 0, s>>>(a, ctx->part, src_dev, ld_src, dst_dev, ld_dst, ncols,
-                                                              loglik_out_dev, idx_out_dev);
+    if (!ctx->search_smem_opt_in) {        // > 48 KB of dynamic shared memory needs the opt-in (per device)
+        GSE_CHECK_CUDA(cudaFuncSetAttribute(k_resample_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM));
+        ctx->search_smem_opt_in = 1;
+    }
+    k_resample_search<<<(unsigned)nparts, RS_THREADS, RS_SMEM, s>>>(a, ctx->part, idx_out_dev);
+    GSE_CHECK_LAUNCH(ctx);
+    return GSE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: materialising gather  dst[:, i] = src[:, idx_i]  (particles[sample_index], particle.py:102 /
+// :315).  Only used when the resampled rows themselves are needed (the `particles` attribute, the
+// sharded slab exchange): the filters normally hand idx to the next predict / moments kernel, which
+// reads its rows through it.  idx is non-decreasing, so the reads of a warp fall in one short
+// window of each column (or on one address when a heavy source has many offspring).
+// ------------------------------------------------------------------------------------------------
+#define GR_THREADS 256
+template <bool VEC>
+__global__ void __launch_bounds__(GR_THREADS)
+k_gather_rows(const int32_t* __restrict__ idx, int64_t n_out, const float* __restrict__ src, int64_t ld_src,
+              float* __restrict__ dst, int64_t ld_dst, int ncols, float* __restrict__ loglik_out) {
+    if (VEC) {
+        const int64_t row0 = ((int64_t)blockIdx.x * GR_THREADS + threadIdx.x) * 4;
+        if (row0 >= n_out) return;
+        if (row0 + 4 <= n_out) {
+            const int4 id = *reinterpret_cast<const int4*>(idx + row0);
+            for (int c = 0; c < ncols; ++c) {
+                const float* col = src + c * ld_src;
+                st_stream4(dst + c * ld_dst + row0,
+                           make_float4(__ldg(col + id.x), __ldg(col + id.y), __ldg(col + id.z), __ldg(col + id.w)));
+            }
+            if (loglik_out) st_stream4(loglik_out + row0, make_float4(0.f, 0.f, 0.f, 0.f));
+        } else {                                           // ragged tail: never touch rows >= n_out
+            for (int64_t i = row0; i < n_out; ++i) {
+                const int k = idx[i];
+                for (int c = 0; c < ncols; ++c) dst[c * ld_dst + i] = __ldg(src + c * ld_src + k);
+                if (loglik_out) loglik_out[i] = 0.0f;
+            }
+        }
+    } else {
+        const int64_t i = (int64_t)blockIdx.x * GR_THREADS + threadIdx.x;
+        if (i >= n_out) return;
+        const int k = idx[i];
+        for (int c = 0; c < ncols; ++c) dst[c * ld_dst + i] = __ldg(src + c * ld_src + k);
+        if (loglik_out) loglik_out[i] = 0.0f;
+    }
+}
+
+extern "C" int gse_gather_rows(gse_ctx* ctx, const int32_t* idx_dev, int64_t n_out, const float* src_dev,
+                               int64_t ld_src, float* dst_dev, int64_t ld_dst, int ncols,
+                               float* loglik_out_dev, void* stream) {
+    GSE_REQUIRE(ctx != NULL && idx_dev != NULL && src_dev != NULL && dst_dev != NULL, "NULL argument");
+    GSE_REQUIRE(n_out >= 0 && ncols >= 1 && ld_dst >= n_out, "n_out / ncols / ld out of range");
+    GSE_REQUIRE(src_dev != dst_dev, "gather cannot be done in place");
+    if (n_out == 0) return GSE_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    // vector path: idx, dst columns and loglik 16-byte aligned
+    const bool vec = (((uintptr_t)idx_dev | (uintptr_t)dst_dev | (uintptr_t)loglik_out_dev) & 15u) == 0 &&
+                     ld_dst % 4 == 0;
+    if (vec)
+        k_gather_rows<true><<<(unsigned)gse_div_up(gse_div_up(n_out, 4), GR_THREADS), GR_THREADS, 0, s>>>(
+            idx_dev, n_out, src_dev, ld_src, dst_dev, ld_dst, ncols, loglik_out_dev);
+    else
+        k_gather_rows<false><<<(unsigned)gse_div_up(n_out, GR_THREADS), GR_THREADS, 0, s>>>(
+            idx_dev, n_out, src_dev, ld_src, dst_dev, ld_dst, ncols, loglik_out_dev);
     GSE_CHECK_LAUNCH(ctx);
     return GSE_OK;
 }

@@ -12,6 +12,14 @@ measurements.  Here a weight is  ``base_scale * base_k * exp(loglik_k)``:
 * ``base_scale`` -- Python float, ``1/N`` after construction / resample (particle.py:50,103).
 
 The ``weights`` attribute materialises the reference's un-normalised linear weights on demand.
+
+Lazy resampling.  ``resample()`` only produces the int32 ancestor index (the reference's
+``sample_index``, particle.py:100): ``_pending`` is set and the next ``predict`` / moments kernel
+reads row ``idx[i]`` of the pre-resample state for row ``i``, so ``particles[sample_index]``
+(particle.py:102) costs no pass of its own through HBM.  Anything that needs the rows in place
+(``particles`` / ``means`` attributes, ``update`` right after ``resample``) calls ``_materialise()``.
+``_loglik_zero`` marks the accumulated log-likelihood as all zero (weights just reset, :103) so that
+``update`` does not read it and nothing has to zero-fill it.
 """
 import ctypes
 
@@ -71,7 +79,7 @@ class WeightedEnsemble:
 
     NCOLS = 5
 
-    def _init_ensemble(self, N, state_pdf, measurement_pdf, device, seed):
+    def _init_ensemble(self, N, state_pdf, measurement_pdf, device, seed, workspace_rows=None):
         self.N_particles = int(N)
         if self.N_particles < 1:
             raise ValueError("N_particles must be >= 1")
@@ -79,7 +87,7 @@ class WeightedEnsemble:
         self.measurement_pdf = measurement_pdf
         self._state_mix = mixture_view(state_pdf)
         self._meas_mix = mixture_view(measurement_pdf)
-        self._ctx = Context(device, self.N_particles, self._state_mix, self._meas_mix)
+        self._ctx = Context(device, max(self.N_particles, int(workspace_rows or 0)), self._state_mix, self._meas_mix)
         self.device = self._ctx.device
         n = self.N_particles
         self._ld = _device.round_up(n, 64)
@@ -87,6 +95,9 @@ class WeightedEnsemble:
         self._state = torch.zeros((self.NCOLS, self._ld), dtype=torch.float32, device=dev)
         self._state_alt = torch.zeros((self.NCOLS, self._ld), dtype=torch.float32, device=dev)
         self._loglik = torch.zeros(self._ld, dtype=torch.float32, device=dev)
+        self._loglik_zero = True       # logically all zero; the buffer need not be
+        self._idx = torch.zeros(self._ld, dtype=torch.int32, device=dev)      # ancestor index of the last resample
+        self._pending = False          # rows must be read through self._idx
         self._base = None
         self._base_max = None
         self._base_scale = 1.0 / n
@@ -110,6 +121,29 @@ class WeightedEnsemble:
     def _touch(self):
         self._mom_valid = False
 
+    def _idx_ptr(self):
+        return self._idx.data_ptr() if self._pending else None
+
+    def _loglik_ptr(self):
+        """Device pointer of the accumulated log-likelihood, None while it is all zero."""
+        return None if self._loglik_zero else self._loglik.data_ptr()
+
+    def _ensure_loglik_buffer(self):
+        if self._loglik_zero:
+            self._loglik.zero_()
+            self._loglik_zero = False
+        return self._loglik.data_ptr()
+
+    def _materialise(self):
+        """Apply a pending resample: state <- state[:, idx]  (particles[sample_index], particle.py:102)."""
+        if self._pending:
+            n = self.N_particles
+            _lib.check(_lib.lib.gse_gather_rows(self._ctx.handle, self._idx.data_ptr(), n, self._state.data_ptr(),
+                                                self._ld, self._state_alt.data_ptr(), self._ld, self.NCOLS, None,
+                                                self._stream()))
+            self._state, self._state_alt = self._state_alt, self._state
+            self._pending = False
+
     def _host_noise(self, pdf, shape):
         """Noise rows for the host-noise mode when the state pdf is a deterministic test double."""
         if hasattr(pdf, "draw_host"):
@@ -122,7 +156,7 @@ class WeightedEnsemble:
         n = self.N_particles
         out = torch.empty(n, dtype=torch.float64, device=self.device)
         _lib.check(_lib.lib.gse_weights_linear(
-            self._ctx.handle, self._loglik.data_ptr(), self._base.data_ptr() if self._base is not None else None,
+            self._ctx.handle, self._loglik_ptr(), self._base.data_ptr() if self._base is not None else None,
             n, float(self._base_scale), out.data_ptr(), self._stream()))
         return _device.wrap(out)
 
@@ -139,7 +173,7 @@ class WeightedEnsemble:
         self._base = w.contiguous().clone()
         self._base_max = self._base.max()
         self._base_scale = 1.0
-        self._loglik.zero_()
+        self._loglik_zero = True
         self._loglik_dirty = False
         self._stats[0] = 0.0
         self._stats[1] = self._base.sum()
@@ -154,6 +188,7 @@ class WeightedEnsemble:
 
     def _after_update(self):
         self._loglik_dirty = True
+        self._loglik_zero = False
         self._touch()
 
     # -- resample ------------------------------------------------------------------------
@@ -167,29 +202,31 @@ class WeightedEnsemble:
             stats = self._stats.clone()
             stats[1] = stats[1] * self._base_max
         _lib.check(_lib.lib.gse_scan_weights(
-            self._ctx.handle, self._loglik.data_ptr() if use_loglik else None,
+            self._ctx.handle, self._ensure_loglik_buffer() if use_loglik else None,
             self._base.data_ptr() if self._base is not None else None, stats.data_ptr(), n,
             self._cumsum.data_ptr(), self._offtot.data_ptr() + 8, self._stream()))
 
     def resample(self, r=None, return_index=False):
         """Systematic resample (particle.py:85-103 / gs_ukf.py:151-171).  ``r`` defaults to
         ``numpy.random.rand()`` exactly as the reference's CPU path draws it (:93), so seeding
-        numpy reproduces the reference's offset."""
+        numpy reproduces the reference's offset.  Produces the ancestor index only; the rows move
+        when the next kernel reads them (see the module docstring)."""
         n = self.N_particles
         if r is None:
             r = numpy.random.rand()
         r = float(r)
+        self._materialise()                       # a second resample without a predict in between
         self._scan()
         if self._stage_hook is not None:
             self._stage_hook("scan")
-        idx = torch.empty(n, dtype=torch.int64, device=self.device) if return_index else None
-        _lib.check(_lib.lib.gse_resample_gather(
+        _lib.check(_lib.lib.gse_resample_search(
             self._ctx.handle, self._cumsum.data_ptr(), n, self._offtot.data_ptr(), r, n, 0, n,
-            self._state.data_ptr(), self._ld, self._state_alt.data_ptr(), self._ld, self.NCOLS,
-            self._loglik.data_ptr(), idx.data_ptr() if idx is not None else None, self._stream()))
-        self._state, self._state_alt = self._state_alt, self._state
+            self._idx.data_ptr(), self._stream()))
+        self._pending = True
+        self._loglik_zero = True                  # weights = 1/N  (:103 / :316)
         self._reset_uniform()
         self._touch()
+        idx = self._idx[:n].to(torch.int64) if return_index else None
         self.last_sample_index = idx
         return idx
 

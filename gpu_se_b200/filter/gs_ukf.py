@@ -22,11 +22,13 @@ class ParallelGaussianSumUnscentedKalmanFilter(WeightedEnsemble):
 
     NCOLS = 20
 
-    def __init__(self, f, g, N_particles, x0, state_pdf, measurement_pdf, *, device=None, seed=None, means=None):
+    def __init__(self, f, g, N_particles, x0, state_pdf, measurement_pdf, *, device=None, seed=None, means=None,
+                 index0=0, workspace_rows=None):
         self.f = f
         self.g = g
         self._model_id = model_id_for(f, g)
-        self._init_ensemble(N_particles, state_pdf, measurement_pdf, device, seed)
+        self._init_ensemble(N_particles, state_pdf, measurement_pdf, device, seed, workspace_rows)
+        self._index0 = int(index0)
         n = self.N_particles
         self._Nx, self._Ny, self._N_sigmas = 5, 2, 11
         self._w_sigma = numpy.full(11, 1 / (2 * 5 + 8 / 5), dtype=numpy.float32)   # gs_ukf.py:66
@@ -38,7 +40,7 @@ class ParallelGaussianSumUnscentedKalmanFilter(WeightedEnsemble):
         else:
             mix = mixture_view(x0).as_gse_mixture()
             _lib.check(_lib.lib.gse_mixture_draw(self._ctx.handle, mix, self._state.data_ptr(), self._ld, n,
-                                                 self._seed, 0xFFFFFFFF, 0, self._stream()))
+                                                 self._seed, 0xFFFFFFFF, self._index0, self._stream()))
         # covariances = repeat(state_pdf.covariances[0])  (gs_ukf.py:52), float32
         cov0 = numpy.asarray(_device.to_numpy(self._state_mix.covariances)[0], dtype=numpy.float32)
         self.covariances = numpy.repeat(cov0[None], n, axis=0)
@@ -52,6 +54,7 @@ class ParallelGaussianSumUnscentedKalmanFilter(WeightedEnsemble):
 
     @property
     def means(self):
+        self._materialise()
         return _device.wrap(self._state[:5, :self.N_particles].t())
 
     @means.setter
@@ -60,12 +63,14 @@ class ParallelGaussianSumUnscentedKalmanFilter(WeightedEnsemble):
         v = torch.as_tensor(numpy.ascontiguousarray(_device.to_numpy(value), dtype=numpy.float32), device=self.device)
         if tuple(v.shape) != (n, 5):
             raise ValueError("means must have shape (%d, 5)" % n)
+        self._materialise()
         self._state[:5, :n].copy_(v.t())
         self._touch()
 
     @property
     def covariances(self):
         n = self.N_particles
+        self._materialise()
         full = torch.empty((n, 5, 5), dtype=torch.float32, device=self.device)
         for t, (i, j) in enumerate(_TRI):
             full[:, i, j] = self._state[5 + t, :n]
@@ -78,6 +83,7 @@ class ParallelGaussianSumUnscentedKalmanFilter(WeightedEnsemble):
         v = torch.as_tensor(numpy.ascontiguousarray(_device.to_numpy(value), dtype=numpy.float32), device=self.device)
         if tuple(v.shape) != (n, 5, 5):
             raise ValueError("covariances must have shape (%d, 5, 5)" % n)
+        self._materialise()
         for t, (i, j) in enumerate(_TRI):
             self._state[5 + t, :n].copy_(v[:, i, j])
         self._touch()
@@ -86,6 +92,7 @@ class ParallelGaussianSumUnscentedKalmanFilter(WeightedEnsemble):
     def _get_sigma_points(self):
         """(N, 11, 5) sigma points (gs_ukf.py:332-346)."""
         n = self.N_particles
+        self._materialise()
         out = torch.empty((55, self._ld), dtype=torch.float32, device=self.device)
         _lib.check(_lib.lib.gse_gsf_sigma_points(self._ctx.handle, self._mean_ptr(), self._cov_ptr(), self._ld, n,
                                                  out.data_ptr(), self._ld, self._stream()))
@@ -102,17 +109,24 @@ class ParallelGaussianSumUnscentedKalmanFilter(WeightedEnsemble):
             host = numpy.ascontiguousarray(_device.to_numpy(noise), dtype=numpy.float32).reshape(n, 55)
             nz[:, :n].copy_(torch.as_tensor(host, device=self.device).t())
             nz_ptr, ld_nz = nz.data_ptr(), self._ld
-        _lib.check(_lib.lib.gse_gsf_predict(self._ctx.handle, self._mean_ptr(), self._cov_ptr(), self._ld, n,
-                                            _lib.as_double2(u), float(dt), self._seed, self._step, 0,
-                                            nz_ptr, ld_nz, self._stream()))
+        src_mean, src_cov = self._mean_ptr(), self._cov_ptr()
+        idx = self._idx_ptr()
+        if self._pending:                      # apply the pending resample on the way in
+            self._state, self._state_alt = self._state_alt, self._state
+            self._pending = False
+        _lib.check(_lib.lib.gse_gsf_predict(self._ctx.handle, src_mean, src_cov, self._ld, idx, self._mean_ptr(),
+                                            self._cov_ptr(), self._ld, n, _lib.as_double2(u), float(dt), self._seed,
+                                            self._step, self._index0, nz_ptr, ld_nz, self._stream()))
         self._step += 1
         self._touch()
 
     def update(self, u, z):
         """gs_ukf.py:369-407."""
+        self._materialise()
         _lib.check(_lib.lib.gse_gsf_update(self._ctx.handle, self._mean_ptr(), self._cov_ptr(), self._ld,
-                                           self.N_particles, self._loglik.data_ptr(), _lib.as_double2(u),
-                                           _lib.as_double2(z), self._stats.data_ptr(), self._stream()))
+                                           self.N_particles, self._loglik_ptr(), self._loglik.data_ptr(),
+                                           _lib.as_double2(u), _lib.as_double2(z), self._stats.data_ptr(),
+                                           self._stream()))
         self._after_update()
 
     # resample(): WeightedEnsemble.resample gathers all 20 rows (gs_ukf.py:409-436)
@@ -120,8 +134,8 @@ class ParallelGaussianSumUnscentedKalmanFilter(WeightedEnsemble):
     # -- estimates -----------------------------------------------------------------------
     def _launch_moments(self):
         _lib.check(_lib.lib.gse_gsf_moments(
-            self._ctx.handle, self._mean_ptr(), self._cov_ptr(), self._ld, self.N_particles,
-            self._loglik.data_ptr(), self._base.data_ptr() if self._base is not None else None,
+            self._ctx.handle, self._mean_ptr(), self._cov_ptr(), self._ld, self.N_particles, self._idx_ptr(),
+            self._loglik_ptr(), self._base.data_ptr() if self._base is not None else None,
             self._stats.data_ptr(), self._mom.data_ptr(), self._stream()))
 
     def covariance_matrix(self, normalised=False):

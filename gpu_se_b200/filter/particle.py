@@ -24,16 +24,19 @@ class ParallelParticleFilter(WeightedEnsemble):
     seed : int, Philox key for the in-kernel process noise and the initial draw
     n_sub : int, explicit-Euler sub-steps per ``predict`` (the reference takes one, quirk Q1)
     particles : (N, 5) array, initial particles instead of ``x0.draw(N)``
+    index0 : int, global index of row 0 when this filter is one shard of a larger population
+    workspace_rows : int, size the library workspace for this many rows (>= N_particles)
     """
 
     NCOLS = 5
 
     def __init__(self, f, g, N_particles, x0, state_pdf, measurement_pdf, *, device=None, seed=None,
-                 n_sub=1, particles=None):
+                 n_sub=1, particles=None, index0=0, workspace_rows=None):
         self.f = f
         self.g = g
         self._model_id = model_id_for(f, g)
-        self._init_ensemble(N_particles, state_pdf, measurement_pdf, device, seed)
+        self._init_ensemble(N_particles, state_pdf, measurement_pdf, device, seed, workspace_rows)
+        self._index0 = int(index0)     # global index of local row 0 (sharded runs): keys the Philox stream
         self._n_sub = int(n_sub)
         n = self.N_particles
         if particles is not None:
@@ -44,11 +47,12 @@ class ParallelParticleFilter(WeightedEnsemble):
             # particles = x0.draw(N)  (particle.py:49) -- drawn on the device, straight into SoA
             mix = mixture_view(x0).as_gse_mixture()
             _lib.check(_lib.lib.gse_mixture_draw(self._ctx.handle, mix, self._state.data_ptr(), self._ld, n,
-                                                 self._seed, 0xFFFFFFFF, 0, self._stream()))
+                                                 self._seed, 0xFFFFFFFF, self._index0, self._stream()))
 
     # -- state attribute ---------------------------------------------------------------
     @property
     def particles(self):
+        self._materialise()
         return _device.wrap(self._state[:, :self.N_particles].t())
 
     @particles.setter
@@ -61,6 +65,7 @@ class ParallelParticleFilter(WeightedEnsemble):
                                 device=self.device)
         if tuple(v.shape) != (n, 5):
             raise ValueError("particles must have shape (%d, 5)" % n)
+        self._pending = False
         self._state[:, :n].copy_(v.t())
         self._touch()
 
@@ -78,17 +83,23 @@ class ParallelParticleFilter(WeightedEnsemble):
             nz[:, :n].copy_(torch.as_tensor(numpy.ascontiguousarray(_device.to_numpy(noise), dtype=numpy.float32)
                                             .reshape(n, 5), device=self.device).t())
             nz_ptr, ld_nz = nz.data_ptr(), self._ld
-        _lib.check(_lib.lib.gse_pf_predict(self._ctx.handle, self._state.data_ptr(), self._ld, n,
-                                           _lib.as_double2(u), float(dt), self._n_sub, self._seed, self._step, 0,
-                                           nz_ptr, ld_nz, self._stream()))
+        # a pending resample is applied on the way in: read state[:, idx], write the other buffer
+        dst = self._state_alt if self._pending else self._state
+        _lib.check(_lib.lib.gse_pf_predict(self._ctx.handle, self._state.data_ptr(), self._ld, self._idx_ptr(),
+                                           dst.data_ptr(), self._ld, n, _lib.as_double2(u), float(dt), self._n_sub,
+                                           self._seed, self._step, self._index0, nz_ptr, ld_nz, self._stream()))
+        if self._pending:
+            self._state, self._state_alt = self._state_alt, self._state
+            self._pending = False
         self._step += 1
         self._touch()
 
     def update(self, u, z):
         """particle.py:279-294."""
+        self._materialise()
         _lib.check(_lib.lib.gse_pf_update(self._ctx.handle, self._state.data_ptr(), self._ld, self.N_particles,
-                                          self._loglik.data_ptr(), _lib.as_double2(u), _lib.as_double2(z),
-                                          self._stats.data_ptr(), self._stream()))
+                                          self._loglik_ptr(), self._loglik.data_ptr(), _lib.as_double2(u),
+                                          _lib.as_double2(z), self._stats.data_ptr(), self._stream()))
         self._after_update()
 
     # resample(): WeightedEnsemble.resample  (particle.py:296-316)
@@ -96,7 +107,7 @@ class ParallelParticleFilter(WeightedEnsemble):
     # -- estimates -----------------------------------------------------------------------
     def _launch_moments(self):
         _lib.check(_lib.lib.gse_pf_moments(
-            self._ctx.handle, self._state.data_ptr(), self._ld, self.N_particles, self._loglik.data_ptr(),
+            self._ctx.handle, self._state.data_ptr(), self._ld, self.N_particles, self._idx_ptr(), self._loglik_ptr(),
             self._base.data_ptr() if self._base is not None else None, self._stats.data_ptr(),
             self._mom.data_ptr(), self._stream()))
 

@@ -1,0 +1,280 @@
+"""Particle filter sharded over the GPUs of one node: one process per GPU (``torch.distributed``,
+NCCL over NVLink 5 / NVSwitch), contiguous shards of the global row index space, and a globally
+consistent systematic resample.
+
+The reference has no multi-GPU path; this is the north-star design:
+
+* ``predict`` / ``update`` / moments touch local rows only.  The Philox stream is keyed by the GLOBAL
+  row index, so a sharded run draws exactly the noise a single-GPU run of the same seed draws.
+* after ``update`` the local ``(M_s, S_s)`` = (max log-likelihood, sum exp(loglik - M_s)) are combined
+  with two tiny all-reduces (max, then sum of S_s * exp(M_s - M)), so that every shard quantises its
+  weights with the same fixed-point scale (csrc/gse_resample.cu) -- the cumulative weights are
+  integers, hence independent of how the rows are split over GPUs.
+* ``resample``: local scan -> all-gather of the G shard totals T_s (uint64) -> exclusive offsets
+  O_s and total T.  Shard s is the *source* of the global outputs ``[a_s, b_s)`` whose sample
+  position falls in ``(O_s, O_s + T_s] / T`` (closed form through the device's exact predicate,
+  ``gse_count_outputs_below``); it runs the search + gather for that range, writes the part it
+  owns itself straight into its own state and ships the rest as contiguous column slabs to the
+  owning shards (grouped NCCL send/recv, received in place -- no packing copies).
+
+``plan_resample`` and ``exchange_columns`` are pure host / ``torch.distributed`` code and run on
+CPU tensors over ``gloo`` as well (tests/test_sharded_cpu.py).
+"""
+import numpy
+import torch
+import torch.distributed as dist
+
+from gpu_se_b200 import _device, _lib
+from gpu_se_b200.filter.particle import ParallelParticleFilter
+
+
+def shard_bounds(n_total, world):
+    """Contiguous split of [0, n_total): the first n_total % world shards hold one extra row."""
+    base, rem = divmod(int(n_total), int(world))
+    bounds, lo = [], 0
+    for s in range(world):
+        hi = lo + base + (1 if s < rem else 0)
+        bounds.append((lo, hi))
+        lo = hi
+    return bounds
+
+
+class ResamplePlan:
+    """Who sources which global outputs, and which slabs move between shards.
+
+    offsets[s], total : exclusive prefix of the shard totals and their sum (Python ints)
+    src_ranges[s]     : (a_s, b_s) -- outputs sourced by shard s
+    transfers         : list of (src, dst, start, stop) global output ranges, src-major, ascending
+    """
+
+    def __init__(self, totals, r, n_total, bounds):
+        totals = [int(t) for t in totals]
+        world = len(totals)
+        self.offsets, acc = [], 0
+        for t in totals:
+            self.offsets.append(acc)
+            acc += t
+        self.total = acc
+        if self.total <= 0:
+            raise FloatingPointError("all weights are zero: cannot resample")
+        cnt = _lib.lib.gse_count_outputs_below
+        self.src_ranges = []
+        for s in range(world):
+            a = 0 if s == 0 else int(cnt(self.offsets[s], self.total, float(r), int(n_total)))
+            b = int(n_total) if s == world - 1 else int(cnt(self.offsets[s] + totals[s], self.total, float(r),
+                                                            int(n_total)))
+            self.src_ranges.append((a, max(a, b)))
+        self.transfers = []
+        for s, (a, b) in enumerate(self.src_ranges):
+            for t, (lo, hi) in enumerate(bounds):
+                start, stop = max(a, lo), min(b, hi)
+                if stop > start:
+                    self.transfers.append((s, t, start, stop))
+
+    def exchanged_rows(self):
+        return sum(stop - start for s, t, start, stop in self.transfers if s != t)
+
+
+def plan_resample(totals, r, n_total, bounds):
+    return ResamplePlan(totals, r, n_total, bounds)
+
+
+def exchange_columns(plan, rank, bounds, staging, staging_start, dst, ncols, group=None):
+    """Ship the slabs of ``plan`` that cross shards.  ``staging`` (ncols, >= rows sourced here for
+    other shards) holds the gathered rows of the remote-bound outputs in ascending output order,
+    starting with output ``staging_start[t]`` at column offset ``staging_off[t]`` per destination
+    (see ``staging_layout``); ``dst`` (ncols, ld) is the local destination state whose column j
+    holds global output ``bounds[rank][0] + j``.  Receives land in place."""
+    ops = []
+    lo = bounds[rank][0]
+    for s, t, start, stop in plan.transfers:
+        if s == t:
+            continue
+        cnt = stop - start
+        if s == rank:
+            off = staging_start[t]
+            for c in range(ncols):
+                ops.append(dist.P2POp(dist.isend, staging[c, off:off + cnt], t, group))
+        elif t == rank:
+            for c in range(ncols):
+                ops.append(dist.P2POp(dist.irecv, dst[c, start - lo:stop - lo], s, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+
+def staging_layout(plan, rank, align=64):
+    """Column offset in the staging buffer of each remote destination's slab, and the total width."""
+    offs, width = {}, 0
+    for s, t, start, stop in plan.transfers:
+        if s == rank and t != rank:
+            offs[t] = width
+            width += _device.round_up(stop - start, align)
+    return offs, width
+
+
+class ShardedParticleFilter:
+    """``ParallelParticleFilter`` over all ranks of ``group``: same constructor and
+    ``predict / update / resample / point_estimate / point_covariance`` calls, every rank calling
+    each method collectively with identical arguments.  ``N_particles`` is the GLOBAL count;
+    ``particles`` / ``weights`` are this rank's shard."""
+
+    def __init__(self, f, g, N_particles, x0, state_pdf, measurement_pdf, *, device=None, seed=0, n_sub=1,
+                 group=None, particles=None):
+        if not dist.is_initialized():
+            raise RuntimeError("ShardedParticleFilter needs an initialised torch.distributed process group")
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.N_particles = int(N_particles)
+        if self.N_particles < self.world:
+            raise ValueError("need at least one particle per shard")
+        self.bounds = shard_bounds(self.N_particles, self.world)
+        lo, hi = self.bounds[self.rank]
+        local_particles = None
+        if particles is not None:
+            local_particles = _device.to_numpy(particles)[lo:hi]
+        self.local = ParallelParticleFilter(f, g, hi - lo, x0, state_pdf, measurement_pdf, device=device, seed=seed,
+                                            n_sub=n_sub, particles=local_particles, index0=lo,
+                                            workspace_rows=max(b - a for a, b in self.bounds))
+        self.device = self.local.device
+        self._set_uniform()
+        self.last_plan = None
+        self.exchanged_rows = 0
+        self._stage_hook = None
+
+    # -- weights ---------------------------------------------------------------------------------
+    def _set_uniform(self):
+        loc = self.local
+        loc._base_scale = 1.0 / self.N_particles
+        loc._stats_uniform[1] = float(self.N_particles)
+        loc._stats.copy_(loc._stats_uniform)
+
+    @property
+    def particles(self):
+        return self.local.particles
+
+    @property
+    def weights(self):
+        return self.local.weights
+
+    def set_global_weights(self, w):
+        """Assign weights from the full (N,) global array (every rank passes the same array)."""
+        lo, hi = self.bounds[self.rank]
+        w = numpy.ascontiguousarray(_device.to_numpy(w), dtype=numpy.float64).reshape(-1)
+        if w.size != self.N_particles:
+            raise ValueError("weights must have %d entries" % self.N_particles)
+        full = torch.as_tensor(w, device=self.device)
+        self.local.weights = full[lo:hi]
+        self.local._stats[1] = full.sum()              # the same bound on every shard -> one scale
+        self.local._base_max = full.max()
+
+    def _allreduce_stats(self):
+        st = self.local._stats
+        m = st[0:1].clone()
+        dist.all_reduce(m, op=dist.ReduceOp.MAX, group=self.group)
+        s = st[1:2] * torch.exp(st[0:1] - m)
+        dist.all_reduce(s, op=dist.ReduceOp.SUM, group=self.group)
+        st[0:1] = m
+        st[1:2] = s
+
+    # -- the three stages ------------------------------------------------------------------------
+    def predict(self, u, dt, noise=None):
+        if noise is not None:
+            lo, hi = self.bounds[self.rank]
+            noise = _device.to_numpy(noise)[lo:hi]
+        self.local.predict(u, dt, noise=noise)
+
+    def update(self, u, z):
+        self.local.update(u, z)
+        self._allreduce_stats()
+
+    def resample(self, r=None, return_index=False):
+        loc = self.local
+        loc._materialise()
+        if r is None:
+            rt = torch.tensor([numpy.random.rand()], dtype=torch.float64, device=self.device)
+            dist.broadcast(rt, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0,
+                           group=self.group)
+            r = float(rt.item())
+        r = float(r)
+        n_loc = loc.N_particles
+        lo, hi = self.bounds[self.rank]
+        loc._scan()                                               # local cumsum, T_s -> _offtot[1]
+        if self._stage_hook is not None:
+            self._stage_hook("scan")
+        mine = loc._offtot[1:2].clone()
+        allt = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(allt, mine, group=self.group)
+        totals = [int(t) for t in torch.cat(allt).cpu().tolist()]
+        plan = plan_resample(totals, r, self.N_particles, self.bounds)
+        self.last_plan = plan
+        loc._offtot.copy_(torch.tensor([plan.offsets[self.rank], plan.total], dtype=torch.int64))
+        offs, width = staging_layout(plan, self.rank)
+        ncols = loc.NCOLS
+        staging = torch.empty((ncols, max(width, 1)), dtype=torch.float32, device=self.device)
+        idx = torch.full((n_loc,), -1, dtype=torch.int64, device=self.device) if return_index else None
+        widest = max([stop - start for s, t, start, stop in plan.transfers if s == self.rank] + [4])
+        scratch = torch.empty(_device.round_up(widest, 64), dtype=torch.int32, device=self.device)
+        for s, t, start, stop in plan.transfers:
+            if s != self.rank:
+                continue
+            cnt = stop - start
+            if t == self.rank:
+                dst_ptr, ld_dst = loc._state_alt.data_ptr() + 4 * (start - lo), loc._ld
+            else:
+                dst_ptr, ld_dst = staging.data_ptr() + 4 * offs[t], staging.shape[1]
+            _lib.check(_lib.lib.gse_resample_search(
+                loc._ctx.handle, loc._cumsum.data_ptr(), n_loc, loc._offtot.data_ptr(), r, self.N_particles, start,
+                cnt, scratch.data_ptr(), loc._stream()))
+            _lib.check(_lib.lib.gse_gather_rows(
+                loc._ctx.handle, scratch.data_ptr(), cnt, loc._state.data_ptr(), loc._ld, dst_ptr, ld_dst, ncols,
+                None, loc._stream()))
+            if idx is not None and t == self.rank:
+                idx[start - lo:stop - lo] = scratch[:cnt].to(torch.int64) + lo      # global ancestor index
+        exchange_columns(plan, self.rank, self.bounds, staging, offs, loc._state_alt, ncols, self.group)
+        self.exchanged_rows = plan.exchanged_rows()
+        loc._state, loc._state_alt = loc._state_alt, loc._state
+        loc._loglik_zero = True
+        loc._reset_uniform()
+        self._set_uniform()
+        loc._touch()
+        return idx
+
+    # -- estimates -------------------------------------------------------------------------------
+    def _global_moments(self):
+        loc = self.local
+        loc._launch_moments()
+        loc._mom[41:43].copy_(loc._stats[0:2])
+        allm = [torch.empty_like(loc._mom) for _ in range(self.world)]
+        dist.all_gather(allm, loc._mom, group=self.group)
+        mom = torch.stack(allm).cpu().numpy()
+        p = mom[0, 21:26].copy()                                  # common pivot: rank 0's row 0
+        S0, S1, S2 = 0.0, numpy.zeros(5), numpy.zeros((5, 5))
+        for m in mom:
+            s0, s1, s2 = m[0], m[1:6], loc._unpack_sym(m[6:21])
+            d = m[21:26] - p
+            S2 = S2 + s2 + numpy.outer(s1, d) + numpy.outer(d, s1) + s0 * numpy.outer(d, d)
+            S1 = S1 + s1 + s0 * d
+            S0 = S0 + s0
+        A = loc._base_scale * float(numpy.exp(mom[0, 41]))
+        return S0, S1, S2, p, A
+
+    def point_estimate(self, normalised=False):
+        S0, S1, S2, p, A = self._global_moments()
+        return p + S1 / S0 if normalised else A * (S0 * p + S1)
+
+    def covariance_matrix(self, normalised=False):
+        S0, S1, S2, p, A = self._global_moments()
+        if normalised:
+            d = S1 / S0
+            return S2 / S0 - numpy.outer(d, d)
+        d = A * (S0 * p + S1) - p
+        return A * (S2 - numpy.outer(S1, d) - numpy.outer(d, S1) + S0 * numpy.outer(d, d))
+
+    def point_covariance(self, normalised=False):
+        return float(numpy.linalg.svd(self.covariance_matrix(normalised), compute_uv=False)[0])
+
+    @property
+    def _ctx(self):
+        return self.local._ctx

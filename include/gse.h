@@ -22,9 +22,17 @@
  *  - weights are kept as a float32 log-likelihood array `loglik` (sum of log pdf values since the
  *    last reset) times an optional float64 base weight array `base` (NULL = uniform):
  *        weight_k  proportional to  base_k * exp(loglik_k)
+ *    A NULL `loglik` input means "all zero" (the state right after a resample: nothing is read).
  *    `stats_dev` is 4 doubles: [0] = M = max_k loglik_k, [1] = S = sum_k exp(loglik_k - M)
  *    (both written by the update kernels and gse_loglik_max, consumed by scan / moments; the
  *    sharded driver all-reduces them between the two), [2..3] reserved.
+ *  - resampling is LAZY: gse_resample_search produces the int32 ancestor index `idx` (the
+ *    reference's sample_index, particle.py:100 / :314); the kernels that consume the population
+ *    next (predict, moments) take `idx_dev` and read row idx[i] of the pre-resample state for
+ *    output row i, so `particles[sample_index]` (particle.py:102 / :315) never makes its own trip
+ *    through HBM.  idx_dev == NULL means "rows are in place".  gse_gather_rows materialises the
+ *    gather when the rows themselves are wanted.  idx buffers are 16-byte aligned and hold at
+ *    least round_up(n, 4) entries.
  *  - one context per GPU/filter; a context is not thread-safe; distinct contexts are independent.
  */
 #ifndef GSE_H_
@@ -36,7 +44,7 @@
 extern "C" {
 #endif
 
-#define GSE_ABI_VERSION 1
+#define GSE_ABI_VERSION 2
 
 #define GSE_NX 5        /* states  (Cg, Cx, Cfa, Ce, Ch)   model/BioreactorModel.py:191 */
 #define GSE_NU 2        /* inputs  (Fg_in, Fm_in)          model/BioreactorModel.py:195 */
@@ -98,24 +106,29 @@ int gse_mixture_pdf(gse_ctx* ctx, const gse_mixture* mix, const float* x_dev, in
 /* ---- particle filter ------------------------------------------------------------------------ */
 
 /* predict (particle.py:54-67 / :265-277): x_i += f(x_i, u, dt) [n_sub explicit-Euler sub-steps of
- * dt/n_sub; the reference has n_sub = 1], then x_i += state noise.
+ * dt/n_sub; the reference has n_sub = 1], then x_i += state noise.  Reads row idx[i] (or row i when
+ * idx_dev is NULL) of x_src, writes row i of x_dst; x_src == x_dst is allowed only without idx.
  * noise_dev == NULL: noise drawn in-kernel (Philox, counter = (index0 + i, step)).
  * noise_dev != NULL: SoA (5, ld_noise) float32 host-supplied draws are added instead (the
  * DeterministicGaussianSum cross-check mode, DeterministicGaussianSum.py:32-65). */
-int gse_pf_predict(gse_ctx* ctx, float* x_dev, int64_t ld, int64_t n, const double u[GSE_NU],
-                   double dt, int n_sub, uint64_t seed, uint64_t step, int64_t index0,
-                   const float* noise_dev, int64_t ld_noise, void* stream);
+int gse_pf_predict(gse_ctx* ctx, const float* x_src_dev, int64_t ld_src, const int32_t* idx_dev,
+                   float* x_dst_dev, int64_t ld_dst, int64_t n, const double u[GSE_NU], double dt,
+                   int n_sub, uint64_t seed, uint64_t step, int64_t index0, const float* noise_dev,
+                   int64_t ld_noise, void* stream);
 
-/* update (particle.py:69-83 / :279-294): loglik_i += log pdf_meas(z - g(x_i, u));
+/* update (particle.py:69-83 / :279-294): loglik_i = loglik_in_i + log pdf_meas(z - g(x_i, u))
+ * (loglik_in_dev NULL = zeros; may equal loglik_dev);
  * stats_dev[0] = max_i loglik_i, stats_dev[1] = sum_i exp(loglik_i - max). */
-int gse_pf_update(gse_ctx* ctx, const float* x_dev, int64_t ld, int64_t n, float* loglik_dev,
-                  const double u[GSE_NU], const double z[GSE_NY], double* stats_dev, void* stream);
+int gse_pf_update(gse_ctx* ctx, const float* x_dev, int64_t ld, int64_t n, const float* loglik_in_dev,
+                  float* loglik_dev, const double u[GSE_NU], const double z[GSE_NY], double* stats_dev,
+                  void* stream);
 
-/* point_estimate + point_covariance in one pass (particle.py:105-114 / :318-327):
- * out_dev[0] = S = sum_i w_i, out_dev[1..5] = sum_i w_i x_i, out_dev[6..20] = lower triangle of
+/* point_estimate + point_covariance in one pass (particle.py:105-114 / :318-327), over rows
+ * idx[i] (or i) of x:
+ * out_dev[0] = S = sum_i w_i, out_dev[1..5] = sum_i w_i (x_i - p), out_dev[6..20] = lower triangle of
  * sum_i w_i (x_i - p)(x_i - p)' with pivot p = out_dev[21..25] (written by the kernel: row 0),
  * where w_i = base_i * exp(loglik_i - stats_dev[0]).  26 doubles. */
-int gse_pf_moments(gse_ctx* ctx, const float* x_dev, int64_t ld, int64_t n,
+int gse_pf_moments(gse_ctx* ctx, const float* x_dev, int64_t ld, int64_t n, const int32_t* idx_dev,
                    const float* loglik_dev, const double* base_dev, const double* stats_dev,
                    double* out_dev, void* stream);
 
@@ -147,16 +160,18 @@ int gse_scan_weights(gse_ctx* ctx, const float* loglik_dev, const double* base_d
  * only on exact ties -- the CPU comparison `cumsum[k] < u` is the one followed):
  *     u_i   = (i + r) / n_total                                  (float64, as the reference)
  *     idx_i = min{ k : (offset + cumsum[k]) / total >= u_i }     (float64 divide, as `cumsum /= cumsum[-1]`)
- * evaluated exactly through integer thresholds.  For every output: dst[:, i - out0] =
- * src[:, idx_i] for ncols SoA columns (particles[sample_index], :102 / :315), loglik_out = 0
- * (weights reset, :103 / :316; pass NULL to skip), idx_out (int64, NULL to skip) = idx_i.
- * offset/total are read from offtot_dev[0..1] (uint64; the sharded driver writes the exclusive
- * prefix of the shard totals and the global total there). */
-int gse_resample_gather(gse_ctx* ctx, const uint64_t* cumsum_dev, int64_t n_src,
+ * evaluated exactly through integer thresholds; idx_out_dev[i - out0] = idx_i (int32, local source
+ * row).  offset/total are read from offtot_dev[0..1] (uint64; the sharded driver writes the
+ * exclusive prefix of the shard totals and the global total there). */
+int gse_resample_search(gse_ctx* ctx, const uint64_t* cumsum_dev, int64_t n_src,
                         const uint64_t* offtot_dev, double r, int64_t n_total, int64_t out0,
-                        int64_t n_out, const float* src_dev, int64_t ld_src, float* dst_dev,
-                        int64_t ld_dst, int ncols, float* loglik_out_dev, int64_t* idx_out_dev,
-                        void* stream);
+                        int64_t n_out, int32_t* idx_out_dev, void* stream);
+
+/* dst[:, i] = src[:, idx[i]] for ncols SoA columns, i in [0, n_out) (particles[sample_index],
+ * particle.py:102 / :315); loglik_out_dev (NULL to skip) is zeroed (weights reset, :103 / :316). */
+int gse_gather_rows(gse_ctx* ctx, const int32_t* idx_dev, int64_t n_out, const float* src_dev,
+                    int64_t ld_src, float* dst_dev, int64_t ld_dst, int ncols, float* loglik_out_dev,
+                    void* stream);
 
 /* Number of outputs i in [0, n_total) whose u_i maps at or below integer cumulative weight
  * `bound` of `total`, i.e. #{ i : fl(fl(bound)/fl(total)) >= u_i }: host helper used by the sharded
@@ -173,17 +188,20 @@ uint64_t gse_threshold_u64(double u, uint64_t total);
  *
  * predict (gs_ukf.py:82-103 / :348-367): Cholesky (retry +1e-10 I, :72-75), 11 sigma points
  * mean +- L[:, j] (no scaling, quirk Q6), f on each, an independent state-noise draw per sigma
- * point (:99), weighted mean (numpy.average) and weighted scatter.  noise_dev != NULL: host noise,
- * SoA (55, ld_noise) with row s*5 + j = component j of sigma point s. */
-int gse_gsf_predict(gse_ctx* ctx, float* mean_dev, float* cov_dev, int64_t ld, int64_t n,
+ * point (:99), weighted mean (numpy.average) and weighted scatter.  Reads component idx[i] (or i)
+ * of the *_src arrays, writes component i.  noise_dev != NULL: host noise, SoA (55, ld_noise) with
+ * row s*5 + j = component j of sigma point s. */
+int gse_gsf_predict(gse_ctx* ctx, const float* mean_src_dev, const float* cov_src_dev, int64_t ld_src,
+                    const int32_t* idx_dev, float* mean_dev, float* cov_dev, int64_t ld, int64_t n,
                     const double u[GSE_NU], double dt, uint64_t seed, uint64_t step,
                     int64_t index0, const float* noise_dev, int64_t ld_noise, void* stream);
 
 /* update (gs_ukf.py:105-149 / :369-407): sigma points, g, P_xy, P_yy, K, mean/cov update,
- * loglik_i += log pdf_meas(z - g(mean_i)); stats_dev[0] = max loglik. */
+ * loglik_i = loglik_in_i + log pdf_meas(z - g(mean_i)) (loglik_in_dev NULL = zeros);
+ * stats_dev[0] = max loglik, stats_dev[1] = sum exp(loglik - max). */
 int gse_gsf_update(gse_ctx* ctx, float* mean_dev, float* cov_dev, int64_t ld, int64_t n,
-                   float* loglik_dev, const double u[GSE_NU], const double z[GSE_NY],
-                   double* stats_dev, void* stream);
+                   const float* loglik_in_dev, float* loglik_dev, const double u[GSE_NU],
+                   const double z[GSE_NY], double* stats_dev, void* stream);
 
 /* sigma points (gs_ukf.py:69-80 / :332-346): out SoA (55, ld_out), row s*5 + j. */
 int gse_gsf_sigma_points(gse_ctx* ctx, const float* mean_dev, const float* cov_dev, int64_t ld,
@@ -192,7 +210,7 @@ int gse_gsf_sigma_points(gse_ctx* ctx, const float* mean_dev, const float* cov_d
 /* point_estimate / point_covariance (gs_ukf.py:173-183 / :438-449): as gse_pf_moments on the
  * means, plus out_dev[26..40] = sum_i w_i P_i (lower triangle).  41 doubles. */
 int gse_gsf_moments(gse_ctx* ctx, const float* mean_dev, const float* cov_dev, int64_t ld,
-                    int64_t n, const float* loglik_dev, const double* base_dev,
+                    int64_t n, const int32_t* idx_dev, const float* loglik_dev, const double* base_dev,
                     const double* stats_dev, double* out_dev, void* stream);
 
 /* ---- introspection ------------------------------------------------------------------------------ */

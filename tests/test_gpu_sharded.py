@@ -1,0 +1,112 @@
+"""-m gpu tests of the sharded particle filter (gpu_se_b200/sharded.py) over NCCL.
+
+* world size 1 (always runs): the sharded driver must reproduce the single-GPU filter bit for bit.
+* world size 2 (needs two GPUs; skipped otherwise): two shards of one population must reproduce
+  the single-GPU run of the same seed bit for bit -- Philox is keyed by the global row index and the
+  cumulative weights are integers, so neither the noise nor the resample depends on the split.
+"""
+import os
+import socket
+import sys
+
+import numpy
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _run_cycles(pf, n_cycles, seed):
+    rng = numpy.random.default_rng(seed)
+    out = []
+    from oracle import bioreactor
+    x = bioreactor.X_STEADY.copy()
+    for c in range(n_cycles):
+        u = numpy.array([rng.uniform(0.03, 0.09), rng.uniform(0.1, 0.3)])
+        x = x + bioreactor.increment(x, u, 0.5)
+        z = bioreactor.outputs(x, round32=False) + rng.normal(size=2) * numpy.array([0.2, 0.25])
+        r = float(rng.uniform())
+        pf.predict(u, 0.5)
+        pf.update(u, z)
+        est_u = pf.point_estimate(normalised=True)
+        pf.resample(r=r)
+        out.append((est_u, pf.point_estimate(), pf.point_covariance()))
+    return out
+
+
+def _worker(rank, world, port, n, q):
+    try:
+        sys.path.insert(0, ROOT)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import torch
+        import torch.distributed as dist
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        torch.cuda.set_device(rank)
+        dev = torch.device("cuda", rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        import gpu_se_b200 as g
+        from gpu_common import make_pdfs
+        from gpu_se_b200.sharded import ShardedParticleFilter
+        x0, state, meas = make_pdfs(g)
+        f, gg = g.Bioreactor.homeostatic_DEs, g.Bioreactor.static_outputs
+        spf = ShardedParticleFilter(f, gg, n, x0, state, meas, device=dev, seed=77)
+        got = _run_cycles(spf, 4, seed=3)
+        exchanged = spf.exchanged_rows
+        parts = [torch.empty((b - a, 5), dtype=torch.float32, device=dev) for a, b in spf.bounds]
+        for s in range(world):
+            if s == rank:
+                parts[s].copy_(spf.particles)
+            dist.broadcast(parts[s], src=s)
+        full = torch.cat(parts).cpu().numpy()
+        if rank == 0:
+            pf = g.ParticleFilter(f, gg, n, x0, state, meas, device=dev, seed=77)
+            ref = _run_cycles(pf, 4, seed=3)
+            assert numpy.array_equal(full, pf.particles.get()), "sharded particles differ from the single-GPU run"
+            # identical rows and weights; only the float64 summation order of the moments differs
+            for (a0, a1, a2), (b0, b1, b2) in zip(got, ref):
+                assert numpy.allclose(a0, b0, rtol=1e-10, atol=1e-10)
+                assert numpy.allclose(a1, b1, rtol=1e-10, atol=1e-10)
+                assert a2 == pytest.approx(b2, rel=1e-8)
+        q.put((rank, "ok", exchanged))
+        dist.destroy_process_group()
+    except Exception as e:      # noqa: BLE001
+        import traceback
+        q.put((rank, "fail", traceback.format_exc() + repr(e)))
+
+
+def _launch(world, n):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(rank, world, port, n, q)) for rank in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, status, info in results:
+        assert status == "ok", "rank %d: %s" % (rank, info)
+    return results
+
+
+@pytest.mark.parametrize("n", [4096, 100003])
+def test_world1_equals_single_gpu(n):
+    _launch(1, n)
+
+
+@pytest.mark.parametrize("n", [8192, 1000003])
+def test_world2_equals_single_gpu(n):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    results = _launch(2, n)
+    assert any(info > 0 for _, _, info in results), "informative measurement: shards must exchange rows"
