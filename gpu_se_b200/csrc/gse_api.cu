@@ -193,7 +193,7 @@ extern "C" int gse_ctx_create(int device, int model_id, int64_t n_max, const gse
 
     // workspace: sized for the largest grid any kernel uses on n_max rows
     c->max_blocks = gse_div_up(n_max, 128) + 8;        // >= blocks of any kernel (GS-UKF: 128 components per block)
-    c->max_tiles = gse_div_up(n_max, 1024) + 8;        // scan tiles / merge partitions (>= 2n/4096)
+    c->max_tiles = gse_div_up(n_max, 512) + 16;        // scan warp runs (<= n/512 + 1) / merge partitions (2n/4096 + 1)
     size_t off = 0;
     const size_t o_bmax = off; off = align_up(off + sizeof(float) * c->max_blocks, 256);
     const size_t o_bsum = off; off = align_up(off + sizeof(float) * c->max_blocks, 256);

@@ -102,7 +102,6 @@ struct gse_ctx {
     unsigned int* tile_flag;  // scan: (epoch << 2) | state
     int64_t* part;            // merge-path split points
     unsigned int scan_epoch;
-    int search_smem_opt_in;   // cudaFuncSetAttribute(k_resample_search, MaxDynamicSharedMemorySize) done on this device
     int64_t max_blocks;
     int64_t max_tiles;
 };

@@ -59,7 +59,7 @@ extern "C" int gse_mixture_draw(gse_ctx* ctx, const gse_mixture* mix, float* x_d
 // K1: predict.  x += f(x, u, dt) (n_sub Euler sub-steps), then x += noise (particle.py:65-67).
 // ------------------------------------------------------------------------------------------------
 template <bool DIAG, bool HOST_NOISE, bool ONE_STEP, int ND, bool GATHER>
-__global__ void __launch_bounds__(PF_THREADS)
+__global__ void __launch_bounds__(PF_THREADS, 5)
 k_pf_predict(const float* xs, int64_t lds, const int32_t* __restrict__ idx, float* xd, int64_t ldd, int64_t n,
              ModelInputs in, int n_sub, const __grid_constant__ MixSampler5 sp, uint32_t k0, uint32_t k1,
              uint32_t step, int64_t index0, const float* __restrict__ noise, int64_t ldn) {

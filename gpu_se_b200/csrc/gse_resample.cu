@@ -343,20 +343,40 @@ k_resample_partition(const ResampleArgs a, int64_t* __restrict__ part, int64_t n
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4: search.  Per block: stage the source window of cumulative weights in shared memory together
-// with the EXACT integer threshold q*(u_i) of every output of the window (gse_threshold: one
-// 64 x 64 -> 128-bit product per output, no division), so that "source k precedes output i" is the
-// single integer compare C_k < q*_i from here on.  The <= 4096 merged elements are split between
-// the threads (merge path, binary search in shared memory) and every thread merges its 16 elements
-// serially.  idx_i = number of sources merged before output i; written back coalesced as int32.
+// K4: search by rank-and-fill.  Block b owns the merged elements [b*W, (b+1)*W): a window of ns
+// sources and no outputs (ns + no <= 4096).  With g_k = fl(C_k / T) and u_j = (j + r) / N evaluated
+// exactly as the reference does (particle.py:90,97), source k precedes output j iff g_k < u_j, and
+// u_j is non-decreasing in j.  So every SOURCE computes its rank among the block's outputs
+//     e_k = #{ j : u_j <= g_k } = first j with u_j > g_k
+// directly: one float64 division, a float64 guess  floor(g_k N - r) + 1  and one or two exact
+// evaluations of u around it -- no search at all.  Output j then has idx_j = a0 + #{k : e_k <= j}:
+// the last source of every distinct rank drops the marker k + 1 at position e_k and a block-wide
+// prefix maximum fills the runs.  Blocks without outputs (sources without offspring) return at
+// once; blocks with few sources (heavy ancestors) cost a fill only.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(RS_THREADS)
+template <bool POW2>
+__device__ __forceinline__ double sample_pos(const ResampleArgs& a, double di) {
+    return gse_sample_position(di, a.r, a.n_total, a.inv_n, POW2);
+}
+
+// first global output index i in [dbase, dend] with u_i > g = fl(cd / Td), starting from a guess
+template <bool POW2>
+__device__ __noinline__ double rank_exact(const ResampleArgs& a, double cd, double Td, double di, double dbase,
+                                          double dend) {
+    const double g = __ddiv_rn(cd, Td);                            // cumsum / cumsum[-1]   (:90)
+    di = fmin(fmax(di, dbase), dend);
+    while (di > dbase && sample_pos<POW2>(a, di - 1.0) > g) di -= 1.0;
+    while (di < dend && !(sample_pos<POW2>(a, di) > g)) di += 1.0;
+    return di;
+}
+
+template <bool POW2>
+__global__ void __launch_bounds__(RS_THREADS, 4)
 k_resample_search(const ResampleArgs a, const int64_t* __restrict__ part, int32_t* __restrict__ idx_out) {
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    uint64_t* s_c = reinterpret_cast<uint64_t*>(s_raw);                 // [RS_WORK] local cumulative weights
-    uint64_t* s_q = s_c + RS_WORK;                                      // [RS_WORK] local thresholds, then idx
-    int* s_split = reinterpret_cast<int*>(s_q + RS_WORK);               // [RS_THREADS + 1]
-    const int tid = threadIdx.x;
+    __shared__ int s_e[RS_WORK + 1];                       // rank of source k among the block's outputs
+    __shared__ __align__(16) int s_mark[RS_WORK];          // markers, then their prefix maximum
+    __shared__ int s_warp[RS_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int64_t b = blockIdx.x;
     const int64_t total = a.n_src + a.n_out;
     int64_t d0 = b * RS_WORK, d1 = d0 + RS_WORK;
@@ -366,56 +386,90 @@ k_resample_search(const ResampleArgs a, const int64_t* __restrict__ part, int32_
     if (o1 <= o0) return;                                  // a stretch of sources with no offspring
     const int ns = (int)(a1 - a0);
     const int no = (int)(o1 - o0);
-    const int nm = ns + no;
     const uint64_t off = a.offtot[0];
-    const uint64_t T = a.offtot[1];
+    const double Td = __ull2double_rn(a.offtot[1]);
     const double dbase = (double)(a.out0 + o0);            // global index of the block's first output
-    for (int k = tid; k < ns; k += RS_THREADS) s_c[k] = a.cumsum[a0 + k];
-    for (int j = tid; j < no; j += RS_THREADS) {
-        const uint64_t q = gse_threshold(sample_u(a, dbase + (double)j), T);
-        s_q[j] = q > off ? q - off : 0ull;                 // C_k + off < q*  <=>  C_k < q* - off
+    const double dend = dbase + (double)no;
+#pragma unroll
+    for (int m = 0; m < RS_VT / 4; ++m)
+        *reinterpret_cast<int4*>(s_mark + 4 * tid + m * (4 * RS_THREADS)) = make_int4(0, 0, 0, 0);
+    // Fast path: with t* = (C/T) N - r in real arithmetic, u_i <= g_k  <=>  i <= t* up to the rounding
+    // of u_i and g_k, which moves the boundary by less than 3 N 2^-53; t below is within another
+    // 3 N 2^-53 of t*.  So when t is further than eps = N 2^-48 from an integer the rank is
+    // floor(t) + 1, no division needed; otherwise (ties, ~2 eps of all sources) settle it exactly.
+    const double inv_T = 1.0 / Td;
+    const double eps = a.n_total * 3.5527136788005009e-15;         // N * 2^-48
+    for (int mb = 0; mb < RS_VT && mb * RS_THREADS < ns; mb += 8) {      // 8 loads in flight per thread
+    uint64_t c[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        const int k = tid + (mb + m) * RS_THREADS;
+        c[m] = k < ns ? __ldg(a.cumsum + a0 + k) : 0ull;
     }
-    __syncthreads();
-    // split point of diagonal d: smallest s with NOT (C[s] < q[d - 1 - s])
-    {
-        const int d = min(tid * RS_VT, nm);
-        int lo = max(0, d - no), hi = min(d, ns);
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (s_c[mid] < s_q[d - 1 - mid]) lo = mid + 1; else hi = mid;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        const int k = tid + (mb + m) * RS_THREADS;
+        if (k < ns) {
+            const double cd = __ull2double_rn(c[m] + off);
+            const double t = __fma_rn(__dmul_rn(cd, inv_T), a.n_total, -a.r);
+            const double fl = floor(t);
+            const double fr = t - fl;
+            double di = fl + 1.0;
+            if (!(fr > eps && fr < 1.0 - eps)) di = rank_exact<POW2>(a, cd, Td, di, dbase, dend);
+            di = fmin(fmax(di, dbase), dend);
+            s_e[k] = (int)(di - dbase);
         }
-        s_split[tid] = lo;
-        if (tid == 0) s_split[RS_THREADS] = ns;
+    }
+    }
+    if (tid == 0) s_e[ns] = -1;                            // differs from every rank
+    __syncthreads();
+    for (int k = tid; k < ns; k += RS_THREADS) {
+        const int e = s_e[k];
+        if (e < no && s_e[k + 1] != e) s_mark[e] = k + 1;  // one writer per distinct rank
     }
     __syncthreads();
+    // prefix maximum of the markers: every warp scans a contiguous run of 512 positions
+    int v[RS_VT];
     {
-        const int d = min(tid * RS_VT, nm), d_end = min((tid + 1) * RS_VT, nm);
-        int sa = s_split[tid];
-        const int sa_end = s_split[tid + 1];
-        int sb = d - sa;
-        const int sb_end = d_end - sa_end;
-        int32_t* s_idx = reinterpret_cast<int32_t*>(s_q);          // low word of s_q[j]: written by its owner only
-        const int base = (int)a0;
-        uint64_t c = sa < sa_end ? s_c[sa] : ~0ull;                // exhausted side never wins the compare
-        uint64_t q = sb < sb_end ? s_q[sb] : ~0ull;
-        for (int step = d; step < d_end; ++step) {
-            if (c < q) {
-                ++sa;
-                c = sa < sa_end ? s_c[sa] : ~0ull;
-            } else {
-                s_idx[2 * sb] = base + sa;
-                ++sb;
-                q = sb < sb_end ? s_q[sb] : ~0ull;
+        int carry = 0;
+#pragma unroll
+        for (int m = 0; m < RS_VT / 4; ++m) {
+            const int4 x = *reinterpret_cast<const int4*>(s_mark + wid * (RS_VT * 32) + m * 128 + 4 * lane);
+            v[4 * m + 0] = x.x;
+            v[4 * m + 1] = max(v[4 * m + 0], x.y);
+            v[4 * m + 2] = max(v[4 * m + 1], x.z);
+            v[4 * m + 3] = max(v[4 * m + 2], x.w);
+            int incl = v[4 * m + 3];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl = max(incl, t);
             }
+            int excl = __shfl_up_sync(0xffffffffu, incl, 1);
+            excl = max(lane == 0 ? 0 : excl, carry);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) v[4 * m + r] = max(v[4 * m + r], excl);
+            carry = max(carry, __shfl_sync(0xffffffffu, incl, 31));
         }
+        if (lane == 0) s_warp[wid] = carry;
     }
     __syncthreads();
-    const int32_t* s_idx = reinterpret_cast<const int32_t*>(s_q);
-    const int last = (int)(a.n_src - 1);                           // > last only through a degenerate total
-    for (int j = tid; j < no; j += RS_THREADS) idx_out[o0 + j] = min(s_idx[2 * j], last);
+    {
+        int wbase = 0;
+#pragma unroll
+        for (int w = 0; w < RS_THREADS / 32; ++w) wbase = max(wbase, w < wid ? s_warp[w] : 0);
+#pragma unroll
+        for (int m = 0; m < RS_VT / 4; ++m)
+            *reinterpret_cast<int4*>(s_mark + wid * (RS_VT * 32) + m * 128 + 4 * lane) =
+                make_int4(max(v[4 * m], wbase), max(v[4 * m + 1], wbase), max(v[4 * m + 2], wbase), max(v[4 * m + 3], wbase));
+    }
+    __syncthreads();
+    const int64_t last = a.n_src - 1;                      // > last only through a degenerate total
+    for (int j = tid; j < no; j += RS_THREADS) {
+        const int64_t g = a0 + s_mark[j];
+        idx_out[o0 + j] = (int32_t)(g > last ? last : g);
+    }
 }
-
-#define RS_SMEM (2 * RS_WORK * sizeof(uint64_t) + (RS_THREADS + 1) * sizeof(int))
 
 extern "C" int gse_resample_search(gse_ctx* ctx, const uint64_t* cumsum_dev, int64_t n_src,
                                    const uint64_t* offtot_dev, double r, int64_t n_total, int64_t out0,
@@ -442,11 +496,10 @@ extern "C" int gse_resample_search(gse_ctx* ctx, const uint64_t* cumsum_dev, int
     cudaStream_t s = (cudaStream_t)stream;
     k_resample_partition<<<(unsigned)gse_div_up((nparts + 1) * 32, 128), 128, 0, s>>>(a, ctx->part, nparts);
     GSE_CHECK_LAUNCH(ctx);
-    if (!ctx->search_smem_opt_in) {        // > 48 KB of dynamic shared memory needs the opt-in (per device)
-        GSE_CHECK_CUDA(cudaFuncSetAttribute(k_resample_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM));
-        ctx->search_smem_opt_in = 1;
-    }
-    k_resample_search<<<(unsigned)nparts, RS_THREADS, RS_SMEM, s>>>(a, ctx->part, idx_out_dev);
+    if (a.n_pow2)
+        k_resample_search<true><<<(unsigned)nparts, RS_THREADS, 0, s>>>(a, ctx->part, idx_out_dev);
+    else
+        k_resample_search<false><<<(unsigned)nparts, RS_THREADS, 0, s>>>(a, ctx->part, idx_out_dev);
     GSE_CHECK_LAUNCH(ctx);
     return GSE_OK;
 }
