@@ -37,6 +37,12 @@ __device__ __forceinline__ int quantisation_exponent(double S) {
     return GSE_TOTAL_BITS - e;
 }
 
+// q = rint(exp(l - M) * 2^sexp): the one expression both passes (K3a, K3b) evaluate, with explicit
+// round-to-nearest operations so that no contraction can make them differ
+__device__ __forceinline__ uint64_t quantise1(float l, float M, float scale) {
+    return __float2ull_rn(__fmul_rn(__expf(__fsub_rn(l, M)), scale));
+}
+
 // Quantised weights of the 16 consecutive rows owned by this thread.
 template <bool HAS_LL, bool HAS_BASE>
 __device__ __forceinline__ void quantise16(const float* __restrict__ loglik, const double* __restrict__ base,
@@ -53,12 +59,12 @@ __device__ __forceinline__ void quantise16(const float* __restrict__ loglik, con
             for (int r = 0; r < TILE_ITEMS; ++r) l[r] = (row0 + r < n) ? loglik[row0 + r] : -INFINITY;
         }
 #pragma unroll
-        for (int r = 0; r < TILE_ITEMS; ++r) e[r] = __expf(l[r] - M);
+        for (int r = 0; r < TILE_ITEMS; ++r) e[r] = __expf(__fsub_rn(l[r], M));
     }
     if (!HAS_BASE) {
         const float scale = __int_as_float((127 + sexp) << 23);       // 2^sexp, 0 <= sexp <= 52
 #pragma unroll
-        for (int r = 0; r < TILE_ITEMS; ++r) q[r] = __float2ull_rn(e[r] * scale);
+        for (int r = 0; r < TILE_ITEMS; ++r) q[r] = __float2ull_rn(__fmul_rn(e[r], scale));
         if (!full) {
 #pragma unroll
             for (int r = 0; r < TILE_ITEMS; ++r) if (row0 + r >= n) q[r] = 0;
@@ -137,13 +143,29 @@ k_weight_tile_sums(const float* __restrict__ loglik, const double* __restrict__ 
         const int64_t t0 = (int64_t)w * geo.tiles_per_warp;
         const int64_t t1 = min(t0 + geo.tiles_per_warp, geo.ntiles);
         uint64_t sum = 0;
-        for (int64_t t = t0; t < t1; ++t) {
-            const int64_t row0 = t * WTILE_ROWS + (int64_t)lane * TILE_ITEMS;
-            if (row0 < n) {
-                uint64_t q[TILE_ITEMS];
-                quantise16<HAS_LL, HAS_BASE>(loglik, base, M, sexp, row0, n, q);
+        if (HAS_LL && !HAS_BASE) {
+            // the sum does not care about the order: 128-bit loads, 4 groups in flight per lane
+            const float scale = __int_as_float((127 + sexp) << 23);
+            const int64_t r0 = t0 * WTILE_ROWS, r1 = min(t1 * WTILE_ROWS, n);
+            const int64_t r1_full = r0 + ((r1 - r0) & ~(int64_t)127);
+            int64_t row = r0 + 4 * lane;
+#pragma unroll 4
+            for (; row < r1_full; row += 128) {
+                const float4 l = ld_stream4(loglik + row);
+                sum += quantise1(l.x, M, scale) + quantise1(l.y, M, scale) + quantise1(l.z, M, scale) +
+                       quantise1(l.w, M, scale);
+            }
+            for (int r = 0; r < 4; ++r)
+                if (row + r < r1) sum += quantise1(loglik[row + r], M, scale);
+        } else {
+            for (int64_t t = t0; t < t1; ++t) {
+                const int64_t row0 = t * WTILE_ROWS + (int64_t)lane * TILE_ITEMS;
+                if (row0 < n) {
+                    uint64_t q[TILE_ITEMS];
+                    quantise16<HAS_LL, HAS_BASE>(loglik, base, M, sexp, row0, n, q);
 #pragma unroll
-                for (int r = 0; r < TILE_ITEMS; ++r) sum += q[r];
+                    for (int r = 0; r < TILE_ITEMS; ++r) sum += q[r];
+                }
             }
         }
         sum = warp_sum_u64(sum);
@@ -371,9 +393,8 @@ __device__ __noinline__ double rank_exact(const ResampleArgs& a, double cd, doub
 }
 
 template <bool POW2>
-__global__ void __launch_bounds__(RS_THREADS, 4)
+__global__ void __launch_bounds__(RS_THREADS, 6)
 k_resample_search(const ResampleArgs a, const int64_t* __restrict__ part, int32_t* __restrict__ idx_out) {
-    __shared__ int s_e[RS_WORK + 1];                       // rank of source k among the block's outputs
     __shared__ __align__(16) int s_mark[RS_WORK];          // markers, then their prefix maximum
     __shared__ int s_warp[RS_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -399,76 +420,98 @@ k_resample_search(const ResampleArgs a, const int64_t* __restrict__ part, int32_
     // floor(t) + 1, no division needed; otherwise (ties, ~2 eps of all sources) settle it exactly.
     const double inv_T = 1.0 / Td;
     const double eps = a.n_total * 3.5527136788005009e-15;         // N * 2^-48
-    for (int mb = 0; mb < RS_VT && mb * RS_THREADS < ns; mb += 8) {      // 8 loads in flight per thread
-    uint64_t c[8];
+    const double one_m_eps = 1.0 - eps;
+    const double one_m_base = 1.0 - dbase;
+    // warp w owns the sources [512 w, 512 w + 512) of the window; lane l holds k = 512 w + 32 m + l
+    const int kw = wid * (RS_VT * 32) + lane;
+    int e[RS_VT];
+    if (wid * (RS_VT * 32) < ns) {
+        const uint64_t* src = a.cumsum + a0 + kw;
 #pragma unroll
-    for (int m = 0; m < 8; ++m) {
-        const int k = tid + (mb + m) * RS_THREADS;
-        c[m] = k < ns ? __ldg(a.cumsum + a0 + k) : 0ull;
-    }
+        for (int h = 0; h < RS_VT; h += 8) {                // 8 loads in flight per thread
+            uint64_t c[8];
 #pragma unroll
-    for (int m = 0; m < 8; ++m) {
-        const int k = tid + (mb + m) * RS_THREADS;
-        if (k < ns) {
-            const double cd = __ull2double_rn(c[m] + off);
-            const double t = __fma_rn(__dmul_rn(cd, inv_T), a.n_total, -a.r);
-            const double fl = floor(t);
-            const double fr = t - fl;
-            double di = fl + 1.0;
-            if (!(fr > eps && fr < 1.0 - eps)) di = rank_exact<POW2>(a, cd, Td, di, dbase, dend);
-            di = fmin(fmax(di, dbase), dend);
-            s_e[k] = (int)(di - dbase);
+            for (int m = 0; m < 8; ++m) c[m] = (kw + 32 * (h + m) < ns) ? __ldg(src + 32 * (h + m)) : 0ull;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                int r = -2;                                 // no source: equals no rank
+                if (kw + 32 * (h + m) < ns) {
+                    // (the cvt / floor instructions run on the XU pipe, 7-14 lanes/clk/SM, but exponent-trick
+                    // replacements on the ALU pipe measured slower: tools/ubench_xu.cu, profiles/)
+                    const double cd = __ull2double_rn(c[m] + off);
+                    const double t = __fma_rn(__dmul_rn(cd, inv_T), a.n_total, -a.r);
+                    const double fl = floor(t);
+                    const double fr = t - fl;
+                    if (fr > eps && fr < one_m_eps)
+                        r = __double2int_rz(fl + one_m_base);      // saturating; the rank is floor(t) + 1 - dbase
+                    else
+                        r = __double2int_rz(rank_exact<POW2>(a, cd, Td, fl + 1.0, dbase, dend) - dbase);
+                    r = min(max(r, 0), no);
+                }
+                e[h + m] = r;
+            }
         }
     }
+    __syncthreads();                                        // markers are zeroed
+    if (wid * (RS_VT * 32) < ns) {
+        // the last source of every distinct rank drops its marker: the successor's rank comes from the
+        // next lane (or lane 0 of the next round); the warp's very last source cannot see its successor
+        // and uses a maximum instead (a later writer of the same rank always carries a larger k)
+#pragma unroll
+        for (int m = 0; m < RS_VT; ++m) {
+            int nxt = __shfl_down_sync(0xffffffffu, e[m], 1);
+            const int wrap = __shfl_sync(0xffffffffu, e[m + 1 < RS_VT ? m + 1 : m], 0);
+            if (lane == 31) nxt = wrap;
+            const int r = e[m];
+            if (r >= 0 && r < no) {
+                if (m == RS_VT - 1 && lane == 31) atomicMax(&s_mark[r], kw + 32 * m + 1);
+                else if (nxt != r) s_mark[r] = kw + 32 * m + 1;
+            }
+        }
     }
-    if (tid == 0) s_e[ns] = -1;                            // differs from every rank
     __syncthreads();
-    for (int k = tid; k < ns; k += RS_THREADS) {
-        const int e = s_e[k];
-        if (e < no && s_e[k + 1] != e) s_mark[e] = k + 1;  // one writer per distinct rank
-    }
-    __syncthreads();
-    // prefix maximum of the markers: every warp scans a contiguous run of 512 positions
+    // prefix maximum of the markers: lane l of warp w owns positions [512 w + 16 l, + 16)
     int v[RS_VT];
-    {
-        int carry = 0;
+    const bool active = wid * (RS_VT * 32) < no;           // warps beyond the outputs have nothing to fill
+    if (active) {
+        const int4* p = reinterpret_cast<const int4*>(s_mark + wid * (RS_VT * 32) + RS_VT * lane);
 #pragma unroll
         for (int m = 0; m < RS_VT / 4; ++m) {
-            const int4 x = *reinterpret_cast<const int4*>(s_mark + wid * (RS_VT * 32) + m * 128 + 4 * lane);
-            v[4 * m + 0] = x.x;
-            v[4 * m + 1] = max(v[4 * m + 0], x.y);
-            v[4 * m + 2] = max(v[4 * m + 1], x.z);
-            v[4 * m + 3] = max(v[4 * m + 2], x.w);
-            int incl = v[4 * m + 3];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl = max(incl, t);
-            }
-            int excl = __shfl_up_sync(0xffffffffu, incl, 1);
-            excl = max(lane == 0 ? 0 : excl, carry);
-#pragma unroll
-            for (int r = 0; r < 4; ++r) v[4 * m + r] = max(v[4 * m + r], excl);
-            carry = max(carry, __shfl_sync(0xffffffffu, incl, 31));
+            const int4 x = p[m];
+            v[4 * m + 0] = x.x; v[4 * m + 1] = x.y; v[4 * m + 2] = x.z; v[4 * m + 3] = x.w;
         }
-        if (lane == 0) s_warp[wid] = carry;
+#pragma unroll
+        for (int r = 1; r < RS_VT; ++r) v[r] = max(v[r], v[r - 1]);
+        int incl = v[RS_VT - 1];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl = max(incl, t);
+        }
+        int excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 0;
+#pragma unroll
+        for (int r = 0; r < RS_VT; ++r) v[r] = max(v[r], excl);
+        if (lane == 31) s_warp[wid] = incl;
     }
     __syncthreads();
-    {
+    if (active) {
         int wbase = 0;
 #pragma unroll
-        for (int w = 0; w < RS_THREADS / 32; ++w) wbase = max(wbase, w < wid ? s_warp[w] : 0);
+        for (int w = 0; w < RS_THREADS / 32 - 1; ++w) wbase = max(wbase, w < wid ? s_warp[w] : 0);
+        int4* p = reinterpret_cast<int4*>(s_mark + wid * (RS_VT * 32) + RS_VT * lane);
 #pragma unroll
         for (int m = 0; m < RS_VT / 4; ++m)
-            *reinterpret_cast<int4*>(s_mark + wid * (RS_VT * 32) + m * 128 + 4 * lane) =
-                make_int4(max(v[4 * m], wbase), max(v[4 * m + 1], wbase), max(v[4 * m + 2], wbase), max(v[4 * m + 3], wbase));
+            p[m] = make_int4(max(v[4 * m], wbase), max(v[4 * m + 1], wbase), max(v[4 * m + 2], wbase), max(v[4 * m + 3], wbase));
     }
     __syncthreads();
-    const int64_t last = a.n_src - 1;                      // > last only through a degenerate total
-    for (int j = tid; j < no; j += RS_THREADS) {
-        const int64_t g = a0 + s_mark[j];
-        idx_out[o0 + j] = (int32_t)(g > last ? last : g);
-    }
+    // idx = a0 + (sources of this block merged before the output), clamped to n_src - 1 (only reachable
+    // through a degenerate total)
+    const int64_t room = a.n_src - 1 - a0;
+    const int cap = room < 0 ? 0 : (room > RS_WORK ? RS_WORK : (int)room);
+    const int base = (int)(a0 + (room < 0 ? room : 0));
+    int32_t* out = idx_out + o0;
+    for (int j = tid; j < no; j += RS_THREADS) out[j] = base + min(s_mark[j], cap);
 }
 
 extern "C" int gse_resample_search(gse_ctx* ctx, const uint64_t* cumsum_dev, int64_t n_src,
