@@ -38,6 +38,8 @@ U_NOMINAL = numpy.array([0.06, 0.2])
 # predict reads its rows through the int32 ancestor index, so K5's gather rides inside K1):
 #   predict 4 R idx + 20 R + 20 W, update 8 R + 4 W, scan 4 R + 8 W, search 8 R + 4 W
 STAGE_BYTES = {"predict": 44, "update": 12, "scan": 12, "search": 12}
+# sharded run: the same, plus the all-gather of the shard totals ("offsets", no HBM traffic to speak of)
+STAGE_BYTES_SHARDED = {"predict": 44, "update": 12, "scan": 12, "offsets": 0, "search": 12}
 STEP_BYTES = sum(STAGE_BYTES.values())          # 80 B per particle-step (SURVEY §8(d) counted 128 B with a materialised gather)
 
 
@@ -203,7 +205,7 @@ def run_reference(args):
                                        "travel to the GPU box), 2^%d particles x %d steps" % (log2n, args.steps)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.perf_counter() - t0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -278,18 +280,18 @@ def run_ours(args):
 
     for k in range(W):
         step(k, False)
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
+    barrier()                                   # after the sampler warm-up: every rank enters the timed region together
     launches0 = pf._ctx.launches
     t_wall0 = time.perf_counter()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for k in range(W, W + K):
         step(k, True)
-    getattr(pf, "local", pf)._materialise()     # the last resample's pending gather belongs to the timed region
+    pf._materialise()                           # the last resample's pending gather belongs to the timed region
     ev1.record(stream)
     barrier()
     t_wall1 = time.perf_counter()
@@ -324,12 +326,16 @@ def run_ours(args):
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
         dist.all_reduce(lsum, op=dist.ReduceOp.SUM)
     dev_ms, e2e_ms = float(times[0]), float(times[1])
+    if hasattr(pf, "close"):
+        pf.close()                              # collective: unmap peer buffers before anyone frees them
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
     peak, peak_src = measured_peak_gbs()
+    STAGE_BYTES = globals()["STAGE_BYTES_SHARDED" if world > 1 else "STAGE_BYTES"]
+    STEP_BYTES = sum(STAGE_BYTES.values())
     value = n_total * K / (dev_ms * 1e-3)
     dom = max(stage_avg, key=stage_avg.get) if stage_avg else "predict"
     dom_ms = stage_avg.get(dom, dev_ms / K)
@@ -364,12 +370,21 @@ def run_ours(args):
     }
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(args.cpu_log2n)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def emit(line):
+    """The one JSON line goes to the real stdout; everything else that lands on fd 1 (NCCL's version
+    banner, library chatter) was redirected to stderr at start-up."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 if __name__ == "__main__":
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)

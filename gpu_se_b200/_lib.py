@@ -9,7 +9,7 @@ import os
 
 GSE_NX, GSE_NU, GSE_NY, GSE_NSIGMA, GSE_NCOV, GSE_MAX_ND = 5, 2, 2, 11, 15, 8
 GSE_MODEL_BIOREACTOR = 1
-GSE_ABI_VERSION = 2
+GSE_ABI_VERSION = 3
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgse_b200.so")
 
@@ -29,7 +29,17 @@ class gse_mixture(ctypes.Structure):
                 ("covs", ctypes.c_double * (GSE_MAX_ND * GSE_NX * GSE_NX))]
 
 
+GSE_MAX_SHARDS, GSE_IPC_HANDLE_BYTES = 8, 64
+
+
+class gse_shards(ctypes.Structure):
+    _fields_ = [("nshards", ctypes.c_int32), ("rows", ctypes.c_int64 * (GSE_MAX_SHARDS + 1)),
+                ("cumsum_dev", ctypes.c_void_p * GSE_MAX_SHARDS), ("state_dev", ctypes.c_void_p * GSE_MAX_SHARDS),
+                ("ld", ctypes.c_int64 * GSE_MAX_SHARDS), ("offsets_dev", ctypes.c_void_p)]
+
+
 c_mix_p = ctypes.POINTER(gse_mixture)
+c_shards_p = ctypes.POINTER(gse_shards)
 
 # name -> (restype, argtypes); mirrors include/gse.h one to one (tests/test_abi.py checks the two
 # against each other)
@@ -49,6 +59,16 @@ SIGNATURES = {
     "gse_scan_weights": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "gse_resample_search": (c_int, [c_vp, c_vp, c_i64, c_vp, c_dbl, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "gse_gather_rows": (c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_vp]),
+    "gse_peer_alloc": (c_int, [c_int, c_i64, ctypes.POINTER(c_vp), ctypes.c_char_p]),
+    "gse_peer_free": (c_int, [c_int, c_vp]),
+    "gse_peer_open": (c_int, [c_int, ctypes.c_char_p, ctypes.POINTER(c_vp)]),
+    "gse_peer_close": (c_int, [c_int, c_vp]),
+    "gse_resample_search_sharded": (c_int, [c_vp, c_shards_p, c_dbl, c_i64, c_i64, c_vp, c_vp]),
+    "gse_gather_rows_sharded": (c_int, [c_vp, c_shards_p, c_vp, c_i64, c_vp, c_i64, c_int, c_vp]),
+    "gse_pf_predict_sharded": (c_int, [c_vp, c_shards_p, c_vp, c_vp, c_i64, c_i64, c_dbl_p, c_dbl, c_int, c_u64, c_u64,
+                                       c_i64, c_vp, c_i64, c_vp]),
+    "gse_pf_moments_sharded": (c_int, [c_vp, c_shards_p, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "gse_merge_stats": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp]),
     "gse_count_outputs_below": (c_i64, [c_u64, c_u64, c_dbl, c_i64]),
     "gse_threshold_u64": (c_u64, [c_dbl, c_u64]),
     "gse_gsf_predict": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_dbl_p, c_dbl, c_u64, c_u64,

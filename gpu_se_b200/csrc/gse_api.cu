@@ -239,6 +239,49 @@ extern "C" int gse_ctx_destroy(gse_ctx* ctx) {
     return GSE_OK;
 }
 
+// ---- peer memory ----------------------------------------------------------------------------------
+extern "C" int gse_peer_alloc(int device, int64_t bytes, void** ptr_out, unsigned char handle_out[GSE_IPC_HANDLE_BYTES]) {
+    GSE_REQUIRE(ptr_out != NULL && handle_out != NULL && bytes > 0, "bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == GSE_IPC_HANDLE_BYTES, "IPC handle size");
+    GSE_CHECK_CUDA(cudaSetDevice(device));
+    void* p = NULL;
+    GSE_CHECK_CUDA(cudaMalloc(&p, (size_t)bytes));
+    cudaError_t e = cudaMemset(p, 0, (size_t)bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        gse_set_error("peer allocation of %lld bytes failed: %s", (long long)bytes, cudaGetErrorString(e));
+        cudaFree(p);
+        return GSE_ECUDA;
+    }
+    memcpy(handle_out, &h, GSE_IPC_HANDLE_BYTES);
+    *ptr_out = p;
+    return GSE_OK;
+}
+
+extern "C" int gse_peer_free(int device, void* ptr) {
+    if (!ptr) return GSE_OK;
+    GSE_CHECK_CUDA(cudaSetDevice(device));
+    GSE_CHECK_CUDA(cudaFree(ptr));
+    return GSE_OK;
+}
+
+extern "C" int gse_peer_open(int device, const unsigned char handle[GSE_IPC_HANDLE_BYTES], void** ptr_out) {
+    GSE_REQUIRE(ptr_out != NULL && handle != NULL, "bad arguments");
+    GSE_CHECK_CUDA(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, GSE_IPC_HANDLE_BYTES);
+    GSE_CHECK_CUDA(cudaIpcOpenMemHandle(ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return GSE_OK;
+}
+
+extern "C" int gse_peer_close(int device, void* ptr) {
+    if (!ptr) return GSE_OK;
+    GSE_CHECK_CUDA(cudaSetDevice(device));
+    GSE_CHECK_CUDA(cudaIpcCloseMemHandle(ptr));
+    return GSE_OK;
+}
+
 extern "C" int64_t gse_launch_count(const gse_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 // Host evaluation of the device's output-count predicate (see gse_common.cuh): number of outputs

@@ -112,6 +112,29 @@ int gse_build_densityN(const gse_mixture* m, MixDensityN* out);
 
 static inline int64_t gse_div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// State rows of a sharded population (kernel parameter): shard s holds the global rows
+// [seg_row[s], seg_row[s+1]) in its own SoA buffer -- local memory for this rank's shard, peer
+// memory (NVLink) for the others.
+struct GatherShards {
+    int nseg;
+    int64_t seg_row[GSE_MAX_SHARDS + 1];
+    const float* state[GSE_MAX_SHARDS];
+    int64_t ld[GSE_MAX_SHARDS];
+};
+
+static inline int gse_build_gather_shards(const gse_shards* sh, const void* dst, GatherShards* g) {
+    GSE_REQUIRE(sh != NULL && sh->nshards >= 1 && sh->nshards <= GSE_MAX_SHARDS, "bad shard table");
+    memset(g, 0, sizeof(*g));
+    g->nseg = sh->nshards;
+    for (int t = 0; t <= sh->nshards; ++t) g->seg_row[t] = sh->rows[t];
+    for (int t = 0; t < sh->nshards; ++t) {
+        GSE_REQUIRE(sh->state_dev[t] != NULL && (const void*)sh->state_dev[t] != dst, "bad shard state pointer");
+        g->state[t] = sh->state_dev[t];
+        g->ld[t] = sh->ld[t];
+    }
+    return GSE_OK;
+}
+
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11).  Counter-based: the stream of row i at step t
@@ -467,6 +490,15 @@ __device__ __forceinline__ void block_max_sumexp_finalize(const float vals[NV], 
     MaxSumExp acc;
     acc.add<NV>(vals, valid);
     block_merge_max_sumexp<THREADS>(acc.m, acc.s, block_max, block_sum, ticket, stats);
+}
+
+// column 0 of global row k and the leading dimension of the shard that owns it
+__device__ __forceinline__ const float* shard_row(const GatherShards& g, int64_t k, int64_t& ld) {
+    int s = 0;
+#pragma unroll
+    for (int t = 1; t < GSE_MAX_SHARDS; ++t) s += (t < g.nseg && k >= g.seg_row[t]) ? 1 : 0;
+    ld = g.ld[s];
+    return g.state[s] + (k - g.seg_row[s]);
 }
 
 // streaming 128-bit accesses for touch-once columns

@@ -58,16 +58,30 @@ extern "C" int gse_mixture_draw(gse_ctx* ctx, const gse_mixture* mix, float* x_d
 // ------------------------------------------------------------------------------------------------
 // K1: predict.  x += f(x, u, dt) (n_sub Euler sub-steps), then x += noise (particle.py:65-67).
 // ------------------------------------------------------------------------------------------------
-template <bool DIAG, bool HOST_NOISE, bool ONE_STEP, int ND, bool GATHER>
+// GMODE: 0 rows in place, 1 rows through a local ancestor index, 2 rows through a GLOBAL ancestor
+// index into the shards of a multi-GPU population (peer memory)
+template <bool DIAG, bool HOST_NOISE, bool ONE_STEP, int ND, int GMODE>
 __global__ void __launch_bounds__(PF_THREADS, 5)
-k_pf_predict(const float* xs, int64_t lds, const int32_t* __restrict__ idx, float* xd, int64_t ldd, int64_t n,
+k_pf_predict(const float* xs, int64_t lds, const int32_t* __restrict__ idx, const __grid_constant__ GatherShards shards,
+             float* xd, int64_t ldd, int64_t n,
              ModelInputs in, int n_sub, const __grid_constant__ MixSampler5 sp, uint32_t k0, uint32_t k1,
              uint32_t step, int64_t index0, const float* __restrict__ noise, int64_t ldn) {
     const int64_t g = (int64_t)blockIdx.x * PF_THREADS + threadIdx.x;
     const int64_t row0 = g * ROWS_PER_THREAD;
     if (row0 >= n) return;
     float v[5][4];
-    if (GATHER) {
+    if (GMODE == 2) {
+        const int4 id4 = *reinterpret_cast<const int4*>(idx + row0);
+        const int id[4] = {id4.x, (row0 + 1 < n) ? id4.y : id4.x, (row0 + 2 < n) ? id4.z : id4.x,
+                           (row0 + 3 < n) ? id4.w : id4.x};
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            int64_t ld;
+            const float* p = shard_row(shards, id[r], ld);
+#pragma unroll
+            for (int j = 0; j < 5; ++j) v[j][r] = p[j * ld];
+        }
+    } else if (GMODE == 1) {
         // rows of the resampled population are read through the ancestor index (the pending
         // particles[sample_index] of the last resample, particle.py:102): idx is non-decreasing, so a
         // warp's reads fall into one short window of each column
@@ -116,16 +130,18 @@ k_pf_predict(const float* xs, int64_t lds, const int32_t* __restrict__ idx, floa
         st_stream4(xd + j * ldd + row0, make_float4(v[j][0], v[j][1], v[j][2], v[j][3]));
 }
 
-extern "C" int gse_pf_predict(gse_ctx* ctx, const float* x_src_dev, int64_t ld_src, const int32_t* idx_dev,
-                              float* x_dst_dev, int64_t ld_dst, int64_t n, const double u[GSE_NU], double dt,
-                              int n_sub, uint64_t seed, uint64_t step, int64_t index0, const float* noise_dev,
-                              int64_t ld_noise, void* stream) {
+static int launch_predict(gse_ctx* ctx, const float* x_src_dev, int64_t ld_src, const int32_t* idx_dev,
+                          const GatherShards* shards, bool sharded, float* x_dst_dev, int64_t ld_dst, int64_t n,
+                          const double u[GSE_NU], double dt, int n_sub, uint64_t seed, uint64_t step, int64_t index0,
+                          const float* noise_dev, int64_t ld_noise, void* stream) {
     GSE_REQUIRE(ctx != NULL && u != NULL, "ctx / u is NULL");
     GSE_REQUIRE(n >= 0 && n <= ctx->n_max, "n out of range for this context");
     GSE_REQUIRE(n_sub >= 1, "n_sub must be >= 1");
     if (n == 0) return GSE_OK;
     CHECK_SOA(x_dst_dev, ld_dst, n);
-    if (idx_dev) {
+    if (sharded) {
+        GSE_REQUIRE(idx_dev != NULL && aligned16(idx_dev), "idx must be non-NULL and 16-byte aligned");
+    } else if (idx_dev) {
         GSE_REQUIRE(x_src_dev != NULL && x_src_dev != x_dst_dev, "a gathering predict cannot run in place");
         GSE_REQUIRE(aligned16(idx_dev), "idx must be 16-byte aligned");
     } else {
@@ -140,12 +156,16 @@ extern "C" int gse_pf_predict(gse_ctx* ctx, const float* x_src_dev, int64_t ld_s
     const unsigned blocks = (unsigned)gse_div_up(groups, PF_THREADS);
     cudaStream_t s = (cudaStream_t)stream;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-#define LAUNCH_PREDICT_G(DIAG, HOST, ONE, ND, GATHER)                                                            \
-    k_pf_predict<DIAG, HOST, ONE, ND, GATHER><<<blocks, PF_THREADS, 0, s>>>(                                     \
-        x_src_dev, ld_src, idx_dev, x_dst_dev, ld_dst, n, in, n_sub, ctx->state_sampler, k0, k1, (uint32_t)step, \
-        index0, noise_dev, ld_noise)
+#define LAUNCH_PREDICT_G(DIAG, HOST, ONE, ND, GMODE)                                                             \
+    k_pf_predict<DIAG, HOST, ONE, ND, GMODE><<<blocks, PF_THREADS, 0, s>>>(                                      \
+        x_src_dev, ld_src, idx_dev, *shards, x_dst_dev, ld_dst, n, in, n_sub, ctx->state_sampler, k0, k1,        \
+        (uint32_t)step, index0, noise_dev, ld_noise)
 #define LAUNCH_PREDICT(DIAG, HOST, ONE, ND)                                                                      \
-    do { if (idx_dev) LAUNCH_PREDICT_G(DIAG, HOST, ONE, ND, true); else LAUNCH_PREDICT_G(DIAG, HOST, ONE, ND, false); } while (0)
+    do {                                                                                                         \
+        if (sharded) LAUNCH_PREDICT_G(DIAG, HOST, ONE, ND, 2);                                                   \
+        else if (idx_dev) LAUNCH_PREDICT_G(DIAG, HOST, ONE, ND, 1);                                              \
+        else LAUNCH_PREDICT_G(DIAG, HOST, ONE, ND, 0);                                                           \
+    } while (0)
     const bool one = (n_sub == 1);
     const int nd = ctx->state_sampler.nd;
     if (noise_dev) { if (one) LAUNCH_PREDICT(true, true, true, 0); else LAUNCH_PREDICT(true, true, false, 0); }
@@ -157,6 +177,27 @@ extern "C" int gse_pf_predict(gse_ctx* ctx, const float* x_src_dev, int64_t ld_s
 #undef LAUNCH_PREDICT_G
     GSE_CHECK_LAUNCH(ctx);
     return GSE_OK;
+}
+
+extern "C" int gse_pf_predict(gse_ctx* ctx, const float* x_src_dev, int64_t ld_src, const int32_t* idx_dev,
+                              float* x_dst_dev, int64_t ld_dst, int64_t n, const double u[GSE_NU], double dt,
+                              int n_sub, uint64_t seed, uint64_t step, int64_t index0, const float* noise_dev,
+                              int64_t ld_noise, void* stream) {
+    GatherShards none;
+    memset(&none, 0, sizeof(none));
+    return launch_predict(ctx, x_src_dev, ld_src, idx_dev, &none, false, x_dst_dev, ld_dst, n, u, dt, n_sub, seed, step,
+                          index0, noise_dev, ld_noise, stream);
+}
+
+extern "C" int gse_pf_predict_sharded(gse_ctx* ctx, const gse_shards* shards, const int32_t* idx_dev, float* x_dst_dev,
+                                      int64_t ld_dst, int64_t n, const double u[GSE_NU], double dt, int n_sub,
+                                      uint64_t seed, uint64_t step, int64_t index0, const float* noise_dev,
+                                      int64_t ld_noise, void* stream) {
+    GatherShards g;
+    int rc = gse_build_gather_shards(shards, x_dst_dev, &g);
+    if (rc) return rc;
+    return launch_predict(ctx, NULL, 0, idx_dev, &g, true, x_dst_dev, ld_dst, n, u, dt, n_sub, seed, step, index0,
+                          noise_dev, ld_noise, stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -263,6 +304,26 @@ extern "C" int gse_loglik_max(gse_ctx* ctx, const float* loglik_dev, int64_t n, 
     return GSE_OK;
 }
 
+// Sharded run: combine the per-shard (M_s, S_s) pairs (all-gathered on the stream) into the global
+// stats[0] = M = max_s M_s, stats[1] = S = sum_s S_s exp(M_s - M), in shard order.
+__global__ void k_merge_stats(const double* __restrict__ pairs, int nshards, double* __restrict__ stats) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double M = -INFINITY;
+    for (int s = 0; s < nshards; ++s) M = fmax(M, pairs[2 * s]);
+    double S = 0.0;
+    for (int s = 0; s < nshards; ++s)
+        if (pairs[2 * s] > -INFINITY) S += pairs[2 * s + 1] * exp(pairs[2 * s] - M);
+    stats[0] = M;
+    stats[1] = S;
+}
+
+extern "C" int gse_merge_stats(gse_ctx* ctx, const double* pairs_dev, int nshards, double* stats_dev, void* stream) {
+    GSE_REQUIRE(ctx != NULL && pairs_dev != NULL && stats_dev != NULL && nshards >= 1, "bad arguments");
+    k_merge_stats<<<1, 32, 0, (cudaStream_t)stream>>>(pairs_dev, nshards, stats_dev);
+    GSE_CHECK_LAUNCH(ctx);
+    return GSE_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // weights read-back: base * exp(loglik) * scale in float64 (the reference's `weights` attribute)
 // ------------------------------------------------------------------------------------------------
@@ -291,16 +352,25 @@ extern "C" int gse_weights_linear(gse_ctx* ctx, const float* loglik_dev, const d
 // out: [0] S0, [1..5] S1, [6..20] S2 lower triangle, [21..25] pivot; (GSF: [26..40] sum w P)
 // ------------------------------------------------------------------------------------------------
 #define MOM_THREADS 256
-template <int NEXTRA, bool GATHER>
+template <int NEXTRA, int GMODE>      // GMODE as in k_pf_predict
 __global__ void __launch_bounds__(MOM_THREADS)
 k_moments(const float* __restrict__ x, const float* __restrict__ extra, int64_t ld, int64_t n,
-          const int32_t* __restrict__ idx, const float* __restrict__ loglik, const double* __restrict__ base,
+          const int32_t* __restrict__ idx, const __grid_constant__ GatherShards shards,
+          const float* __restrict__ loglik, const double* __restrict__ base,
           const double* __restrict__ stats, double* partials, unsigned int* ticket, double* out) {
     constexpr int NV = 21 + NEXTRA;
     const float M = (float)stats[0];
     float p[5];
 #pragma unroll
-    for (int j = 0; j < 5; ++j) p[j] = __ldg(x + j * ld + (GATHER ? idx[0] : 0));
+    for (int j = 0; j < 5; ++j) {
+        if (GMODE == 2) {
+            int64_t l0;
+            const float* q = shard_row(shards, idx[0], l0);
+            p[j] = q[j * l0];
+        } else {
+            p[j] = __ldg(x + j * ld + (GMODE == 1 ? idx[0] : 0));
+        }
+    }
     double acc[NV];
 #pragma unroll
     for (int k = 0; k < NV; ++k) acc[k] = 0.0;
@@ -309,14 +379,24 @@ k_moments(const float* __restrict__ x, const float* __restrict__ extra, int64_t 
         const int64_t row0 = g * 4;
         float4 c[5];
         int id[4] = {0, 0, 0, 0};
-        if (GATHER) {
+        if (GMODE != 0) {
             const int4 id4 = *reinterpret_cast<const int4*>(idx + row0);
             id[0] = id4.x; id[1] = (row0 + 1 < n) ? id4.y : id4.x; id[2] = (row0 + 2 < n) ? id4.z : id4.x;
             id[3] = (row0 + 3 < n) ? id4.w : id4.x;
+            if (GMODE == 2) {
+                int64_t l0, l1, l2, l3;
+                const float* q0 = shard_row(shards, id[0], l0);
+                const float* q1 = shard_row(shards, id[1], l1);
+                const float* q2 = shard_row(shards, id[2], l2);
+                const float* q3 = shard_row(shards, id[3], l3);
 #pragma unroll
-            for (int j = 0; j < 5; ++j)
-                c[j] = make_float4(__ldg(x + j * ld + id[0]), __ldg(x + j * ld + id[1]), __ldg(x + j * ld + id[2]),
-                                   __ldg(x + j * ld + id[3]));
+                for (int j = 0; j < 5; ++j) c[j] = make_float4(q0[j * l0], q1[j * l1], q2[j * l2], q3[j * l3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 5; ++j)
+                    c[j] = make_float4(__ldg(x + j * ld + id[0]), __ldg(x + j * ld + id[1]), __ldg(x + j * ld + id[2]),
+                                       __ldg(x + j * ld + id[3]));
+            }
         } else {
 #pragma unroll
             for (int j = 0; j < 5; ++j) c[j] = ld_stream4(x + j * ld + row0);
@@ -344,7 +424,7 @@ k_moments(const float* __restrict__ x, const float* __restrict__ extra, int64_t 
                 if (NEXTRA > 0) {
 #pragma unroll
                     for (int k = 0; k < NEXTRA; ++k)
-                        acc[21 + k] = fma(w, (double)extra[k * ld + (GATHER ? (int64_t)id[r] : row0 + r)], acc[21 + k]);
+                        acc[21 + k] = fma(w, (double)extra[k * ld + (GMODE == 1 ? (int64_t)id[r] : row0 + r)], acc[21 + k]);
                 }
             }
         }
@@ -380,11 +460,15 @@ k_moments(const float* __restrict__ x, const float* __restrict__ extra, int64_t 
 }
 
 static int launch_moments(gse_ctx* ctx, const float* x, const float* extra, int64_t ld, int64_t n,
-                          const int32_t* idx, const float* loglik, const double* base, const double* stats, double* out,
+                          const int32_t* idx, const GatherShards* shards, const float* loglik, const double* base, const double* stats, double* out,
                           void* stream) {
     GSE_REQUIRE(ctx != NULL && stats != NULL && out != NULL, "ctx / stats / out is NULL");
     GSE_REQUIRE(n >= 1 && n <= ctx->n_max, "n out of range for this context");
     if (idx == NULL) { CHECK_SOA(x, ld, n); }
+    GatherShards none;
+    memset(&none, 0, sizeof(none));
+    const GatherShards& sh = shards ? *shards : none;
+    GSE_REQUIRE(shards == NULL || (idx != NULL && extra == NULL), "sharded moments need idx and no extra columns");
     const int64_t groups = gse_div_up(n, 4);
     int64_t blocks = gse_div_up(groups, MOM_THREADS);
     const int64_t cap = (int64_t)ctx->num_sms * 8;
@@ -392,11 +476,12 @@ static int launch_moments(gse_ctx* ctx, const float* x, const float* extra, int6
     if (blocks > 2048) blocks = 2048;
     GSE_REQUIRE(idx == NULL || aligned16(idx), "idx must be 16-byte aligned");
 #define LAUNCH_MOM(NE, G, EX)                                                                                \
-    k_moments<NE, G><<<(unsigned)blocks, MOM_THREADS, 0, (cudaStream_t)stream>>>(x, EX, ld, n, idx, loglik, base, \
-                                                                                 stats, ctx->red_partials,     \
+    k_moments<NE, G><<<(unsigned)blocks, MOM_THREADS, 0, (cudaStream_t)stream>>>(x, EX, ld, n, idx, sh, loglik,  \
+                                                                                 base, stats, ctx->red_partials, \
                                                                                  ctx->ticket + 2, out)
-    if (extra) { if (idx) LAUNCH_MOM(15, true, extra); else LAUNCH_MOM(15, false, extra); }
-    else { if (idx) LAUNCH_MOM(0, true, NULL); else LAUNCH_MOM(0, false, NULL); }
+    if (extra) { if (idx) LAUNCH_MOM(15, 1, extra); else LAUNCH_MOM(15, 0, extra); }
+    else if (shards) LAUNCH_MOM(0, 2, NULL);
+    else { if (idx) LAUNCH_MOM(0, 1, NULL); else LAUNCH_MOM(0, 0, NULL); }
 #undef LAUNCH_MOM
     GSE_CHECK_LAUNCH(ctx);
     return GSE_OK;
@@ -405,14 +490,23 @@ static int launch_moments(gse_ctx* ctx, const float* x, const float* extra, int6
 extern "C" int gse_pf_moments(gse_ctx* ctx, const float* x_dev, int64_t ld, int64_t n, const int32_t* idx_dev,
                               const float* loglik_dev, const double* base_dev, const double* stats_dev,
                               double* out_dev, void* stream) {
-    return launch_moments(ctx, x_dev, NULL, ld, n, idx_dev, loglik_dev, base_dev, stats_dev, out_dev, stream);
+    return launch_moments(ctx, x_dev, NULL, ld, n, idx_dev, NULL, loglik_dev, base_dev, stats_dev, out_dev, stream);
+}
+
+extern "C" int gse_pf_moments_sharded(gse_ctx* ctx, const gse_shards* shards, const int32_t* idx_dev, int64_t n,
+                                      const float* loglik_dev, const double* base_dev, const double* stats_dev,
+                                      double* out_dev, void* stream) {
+    GatherShards g;
+    int rc = gse_build_gather_shards(shards, NULL, &g);
+    if (rc) return rc;
+    return launch_moments(ctx, NULL, NULL, 0, n, idx_dev, &g, loglik_dev, base_dev, stats_dev, out_dev, stream);
 }
 
 extern "C" int gse_gsf_moments(gse_ctx* ctx, const float* mean_dev, const float* cov_dev, int64_t ld, int64_t n,
                                const int32_t* idx_dev, const float* loglik_dev, const double* base_dev,
                                const double* stats_dev, double* out_dev, void* stream) {
     GSE_REQUIRE(cov_dev != NULL, "cov is NULL");
-    return launch_moments(ctx, mean_dev, cov_dev, ld, n, idx_dev, loglik_dev, base_dev, stats_dev, out_dev, stream);
+    return launch_moments(ctx, mean_dev, cov_dev, ld, n, idx_dev, NULL, loglik_dev, base_dev, stats_dev, out_dev, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -286,8 +286,12 @@ extern "C" int gse_scan_weights(gse_ctx* ctx, const float* loglik_dev, const dou
 #define RS_WORK (RS_THREADS * RS_VT)      // 4096 merged elements per block
 
 struct ResampleArgs {
-    const uint64_t* cumsum;
-    const uint64_t* offtot;    // [0] offset of this shard's cumulative weights, [1] global total
+    const uint64_t* cumsum;    // single segment: the local cumulative weights
+    const uint64_t* offtot;    // [s] offset of segment s's cumulative weights, [nseg] the global total
+    // segmented sources (sharded run, peer memory): segment s holds global rows [seg_row[s], seg_row[s+1])
+    int nseg;
+    int64_t seg_row[GSE_MAX_SHARDS + 1];
+    const uint64_t* seg_cumsum[GSE_MAX_SHARDS];
     int64_t n_src;
     int64_t n_out;
     int64_t out0;              // global index of local output 0
@@ -304,6 +308,17 @@ struct ResampleArgs {
 // compares against q_lo = qa - 2 (local: minus the shard offset, saturating at 0) and q_lo + 4,
 // except inside that window, where the float64 division is evaluated for real.  The spacing of
 // consecutive cumulative weights is ~T / n, so the window is hit with probability ~5 n / 2^52.
+// global cumulative weight of global source row k: the owning shard's local value (read from that
+// GPU's memory over NVLink when it is a peer) plus the shard's offset
+template <bool SEG>
+__device__ __forceinline__ uint64_t source_weight(const ResampleArgs& a, int64_t k, uint64_t off0) {
+    if (!SEG) return __ldg(a.cumsum + k) + off0;
+    int s = 0;
+#pragma unroll
+    for (int t = 1; t < GSE_MAX_SHARDS; ++t) s += (t < a.nseg && k >= a.seg_row[t]) ? 1 : 0;
+    return a.seg_cumsum[s][k - a.seg_row[s]] + a.offtot[s];
+}
+
 __device__ __forceinline__ double sample_u(const ResampleArgs& a, double di) {
     return gse_sample_position(di, a.r, a.n_total, a.inv_n, a.n_pow2 != 0);
 }
@@ -320,13 +335,15 @@ __device__ __forceinline__ bool precedes(const ResampleArgs& a, uint64_t c, uint
     return __ddiv_rn(__ull2double_rn(c + off), Td) < sample_u(a, di);
 }
 
+template <bool SEG>
 __global__ void __launch_bounds__(128)
 k_resample_partition(const ResampleArgs a, int64_t* __restrict__ part, int64_t nparts) {
     const int lane = threadIdx.x & 31;
     const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (b > nparts) return;
-    const uint64_t off = a.offtot[0];
-    const double Td = __ull2double_rn(a.offtot[1]);
+    const uint64_t off0 = SEG ? 0ull : a.offtot[0];
+    const uint64_t off = 0;                                     // source_weight() returns global weights
+    const double Td = __ull2double_rn(a.offtot[SEG ? a.nseg : 1]);
     int64_t diag = b * RS_WORK;
     const int64_t total = a.n_src + a.n_out;
     if (diag > total) diag = total;
@@ -347,7 +364,7 @@ k_resample_partition(const ResampleArgs a, int64_t* __restrict__ part, int64_t n
         }
         bool pred = false;
         if (active) {
-            const uint64_t c = a.cumsum[mid];
+            const uint64_t c = source_weight<SEG>(a, mid, off0);
             const double di = (double)(a.out0 + (diag - 1 - mid));
             pred = precedes(a, c, output_qlo(a, di, off, Td), di, off, Td);
         }
@@ -392,7 +409,7 @@ __device__ __noinline__ double rank_exact(const ResampleArgs& a, double cd, doub
     return di;
 }
 
-template <bool POW2>
+template <bool POW2, bool SEG>
 __global__ void __launch_bounds__(RS_THREADS, 6)
 k_resample_search(const ResampleArgs a, const int64_t* __restrict__ part, int32_t* __restrict__ idx_out) {
     __shared__ __align__(16) int s_mark[RS_WORK];          // markers, then their prefix maximum
@@ -407,8 +424,20 @@ k_resample_search(const ResampleArgs a, const int64_t* __restrict__ part, int32_
     if (o1 <= o0) return;                                  // a stretch of sources with no offspring
     const int ns = (int)(a1 - a0);
     const int no = (int)(o1 - o0);
-    const uint64_t off = a.offtot[0];
-    const double Td = __ull2double_rn(a.offtot[1]);
+    // sharded: a window inside one shard (all but G - 1 of them) is read like a local one
+    int seg = 0;
+    bool direct = true;
+    if (SEG && ns > 0) {
+        int seg_last = 0;
+#pragma unroll
+        for (int t = 1; t < GSE_MAX_SHARDS; ++t) {
+            seg += (t < a.nseg && a0 >= a.seg_row[t]) ? 1 : 0;
+            seg_last += (t < a.nseg && a1 - 1 >= a.seg_row[t]) ? 1 : 0;
+        }
+        direct = seg == seg_last;
+    }
+    const uint64_t off = SEG ? (direct ? a.offtot[seg] : 0ull) : a.offtot[0];
+    const double Td = __ull2double_rn(a.offtot[SEG ? a.nseg : 1]);
     const double dbase = (double)(a.out0 + o0);            // global index of the block's first output
     const double dend = dbase + (double)no;
 #pragma unroll
@@ -426,12 +455,16 @@ k_resample_search(const ResampleArgs a, const int64_t* __restrict__ part, int32_
     const int kw = wid * (RS_VT * 32) + lane;
     int e[RS_VT];
     if (wid * (RS_VT * 32) < ns) {
-        const uint64_t* src = a.cumsum + a0 + kw;
+        const uint64_t* src = (SEG ? a.seg_cumsum[seg] + (a0 - a.seg_row[seg]) : a.cumsum + a0) + kw;
 #pragma unroll
         for (int h = 0; h < RS_VT; h += 8) {                // 8 loads in flight per thread
             uint64_t c[8];
 #pragma unroll
-            for (int m = 0; m < 8; ++m) c[m] = (kw + 32 * (h + m) < ns) ? __ldg(src + 32 * (h + m)) : 0ull;
+            for (int m = 0; m < 8; ++m) {
+                c[m] = 0ull;
+                if (kw + 32 * (h + m) < ns)
+                    c[m] = direct ? __ldg(src + 32 * (h + m)) : source_weight<true>(a, a0 + kw + 32 * (h + m), 0ull);
+            }
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
                 int r = -2;                                 // no source: equals no rank
@@ -514,6 +547,61 @@ k_resample_search(const ResampleArgs a, const int64_t* __restrict__ part, int32_
     for (int j = tid; j < no; j += RS_THREADS) out[j] = base + min(s_mark[j], cap);
 }
 
+static int launch_search(gse_ctx* ctx, const ResampleArgs& a, int64_t nparts, int32_t* idx_out_dev, bool seg,
+                         cudaStream_t s) {
+    const unsigned pgrid = (unsigned)gse_div_up((nparts + 1) * 32, 128);
+    if (seg) k_resample_partition<true><<<pgrid, 128, 0, s>>>(a, ctx->part, nparts);
+    else k_resample_partition<false><<<pgrid, 128, 0, s>>>(a, ctx->part, nparts);
+    GSE_CHECK_LAUNCH(ctx);
+    const unsigned g = (unsigned)nparts;
+    if (seg) {
+        if (a.n_pow2) k_resample_search<true, true><<<g, RS_THREADS, 0, s>>>(a, ctx->part, idx_out_dev);
+        else k_resample_search<false, true><<<g, RS_THREADS, 0, s>>>(a, ctx->part, idx_out_dev);
+    } else {
+        if (a.n_pow2) k_resample_search<true, false><<<g, RS_THREADS, 0, s>>>(a, ctx->part, idx_out_dev);
+        else k_resample_search<false, false><<<g, RS_THREADS, 0, s>>>(a, ctx->part, idx_out_dev);
+    }
+    GSE_CHECK_LAUNCH(ctx);
+    return GSE_OK;
+}
+
+static void fill_common(ResampleArgs& a, double r, int64_t n_total, int64_t out0, int64_t n_out) {
+    a.n_out = n_out;
+    a.out0 = out0;
+    a.r = r;
+    a.n_total = (double)n_total;
+    a.inv_n = 1.0 / (double)n_total;
+    a.n_pow2 = ((n_total & (n_total - 1)) == 0) ? 1 : 0;
+}
+
+// Sharded run: the sources are the rows of ALL shards (their cumulative-weight arrays are peer
+// memory mapped into this process), the outputs are this shard's own slots.  One kernel does the
+// search and, through source_weight(), the communication: nothing is staged or sent.
+extern "C" int gse_resample_search_sharded(gse_ctx* ctx, const gse_shards* sh, double r, int64_t out0, int64_t n_out,
+                                           int32_t* idx_out_dev, void* stream) {
+    GSE_REQUIRE(ctx != NULL && sh != NULL && idx_out_dev != NULL, "ctx / shards / idx is NULL");
+    GSE_REQUIRE(sh->nshards >= 1 && sh->nshards <= GSE_MAX_SHARDS && sh->offsets_dev != NULL, "bad shard table");
+    const int64_t n_total = sh->rows[sh->nshards];
+    GSE_REQUIRE(sh->rows[0] == 0 && n_total >= 1 && n_total <= 0x7fffffff, "global row count out of range (int32 index)");
+    GSE_REQUIRE(n_out >= 0 && n_out <= ctx->n_max && out0 >= 0 && out0 + n_out <= n_total, "output range out of range");
+    GSE_REQUIRE(r >= 0.0 && r < 1.0, "r must be in [0, 1)");
+    if (n_out == 0) return GSE_OK;
+    ResampleArgs a;
+    memset(&a, 0, sizeof(a));
+    a.offtot = sh->offsets_dev;
+    a.n_src = n_total;
+    a.nseg = sh->nshards;
+    for (int t = 0; t <= sh->nshards; ++t) a.seg_row[t] = sh->rows[t];
+    for (int t = 0; t < sh->nshards; ++t) {
+        GSE_REQUIRE(sh->cumsum_dev[t] != NULL && sh->rows[t + 1] > sh->rows[t], "bad shard entry");
+        a.seg_cumsum[t] = sh->cumsum_dev[t];
+    }
+    fill_common(a, r, n_total, out0, n_out);
+    const int64_t nparts = gse_div_up(a.n_src + n_out, RS_WORK);
+    GSE_REQUIRE(nparts + 1 <= ctx->max_tiles + 2, "workspace too small (create the context with n_max >= global rows)");
+    return launch_search(ctx, a, nparts, idx_out_dev, true, (cudaStream_t)stream);
+}
+
 extern "C" int gse_resample_search(gse_ctx* ctx, const uint64_t* cumsum_dev, int64_t n_src,
                                    const uint64_t* offtot_dev, double r, int64_t n_total, int64_t out0,
                                    int64_t n_out, int32_t* idx_out_dev, void* stream) {
@@ -525,24 +613,16 @@ extern "C" int gse_resample_search(gse_ctx* ctx, const uint64_t* cumsum_dev, int
     GSE_REQUIRE(r >= 0.0 && r < 1.0, "r must be in [0, 1)");
     if (n_out == 0) return GSE_OK;
     ResampleArgs a;
+    memset(&a, 0, sizeof(a));
     a.cumsum = cumsum_dev;
     a.offtot = offtot_dev;
     a.n_src = n_src;
-    a.n_out = n_out;
-    a.out0 = out0;
-    a.r = r;
-    a.n_total = (double)n_total;
-    a.inv_n = 1.0 / (double)n_total;
-    a.n_pow2 = ((n_total & (n_total - 1)) == 0) ? 1 : 0;
+    a.nseg = 1;
+    fill_common(a, r, n_total, out0, n_out);
     const int64_t nparts = gse_div_up(n_src + n_out, RS_WORK);
     GSE_REQUIRE(nparts + 1 <= ctx->max_tiles + 2, "workspace too small");
     cudaStream_t s = (cudaStream_t)stream;
-    k_resample_partition<<<(unsigned)gse_div_up((nparts + 1) * 32, 128), 128, 0, s>>>(a, ctx->part, nparts);
-    GSE_CHECK_LAUNCH(ctx);
-    if (a.n_pow2)
-        k_resample_search<true><<<(unsigned)nparts, RS_THREADS, 0, s>>>(a, ctx->part, idx_out_dev);
-    else
-        k_resample_search<false><<<(unsigned)nparts, RS_THREADS, 0, s>>>(a, ctx->part, idx_out_dev);
+    return launch_search(ctx, a, nparts, idx_out_dev, false, s);
     GSE_CHECK_LAUNCH(ctx);
     return GSE_OK;
 }
@@ -584,6 +664,59 @@ k_gather_rows(const int32_t* __restrict__ idx, int64_t n_out, const float* __res
         for (int c = 0; c < ncols; ++c) dst[c * ld_dst + i] = __ldg(src + c * ld_src + k);
         if (loglik_out) loglik_out[i] = 0.0f;
     }
+}
+
+// dst[:, i] = state of global row idx[i], pulled from whichever shard owns it (peer memory over NVLink)
+template <bool VEC>
+__global__ void __launch_bounds__(GR_THREADS)
+k_gather_rows_sharded(const __grid_constant__ GatherShards g, const int32_t* __restrict__ idx, int64_t n_out,
+                      float* __restrict__ dst, int64_t ld_dst, int ncols) {
+    if (VEC) {
+        const int64_t row0 = ((int64_t)blockIdx.x * GR_THREADS + threadIdx.x) * 4;
+        if (row0 >= n_out) return;
+        if (row0 + 4 <= n_out) {
+            const int4 id = *reinterpret_cast<const int4*>(idx + row0);
+            int64_t l0, l1, l2, l3;
+            const float* p0 = shard_row(g, id.x, l0);
+            const float* p1 = shard_row(g, id.y, l1);
+            const float* p2 = shard_row(g, id.z, l2);
+            const float* p3 = shard_row(g, id.w, l3);
+            for (int c = 0; c < ncols; ++c)
+                st_stream4(dst + c * ld_dst + row0, make_float4(p0[c * l0], p1[c * l1], p2[c * l2], p3[c * l3]));
+            return;
+        }
+        for (int64_t i = row0; i < n_out; ++i) {
+            int64_t ld;
+            const float* src = shard_row(g, idx[i], ld);
+            for (int c = 0; c < ncols; ++c) dst[c * ld_dst + i] = src[c * ld];
+        }
+    } else {
+        const int64_t i = (int64_t)blockIdx.x * GR_THREADS + threadIdx.x;
+        if (i >= n_out) return;
+        int64_t ld;
+        const float* src = shard_row(g, idx[i], ld);
+        for (int c = 0; c < ncols; ++c) dst[c * ld_dst + i] = src[c * ld];
+    }
+}
+
+extern "C" int gse_gather_rows_sharded(gse_ctx* ctx, const gse_shards* sh, const int32_t* idx_dev, int64_t n_out,
+                                       float* dst_dev, int64_t ld_dst, int ncols, void* stream) {
+    GSE_REQUIRE(ctx != NULL && sh != NULL && idx_dev != NULL && dst_dev != NULL, "NULL argument");
+    GSE_REQUIRE(sh->nshards >= 1 && sh->nshards <= GSE_MAX_SHARDS, "bad shard table");
+    GSE_REQUIRE(n_out >= 0 && ncols >= 1 && ld_dst >= n_out, "n_out / ncols / ld out of range");
+    if (n_out == 0) return GSE_OK;
+    GatherShards g;
+    int rc = gse_build_gather_shards(sh, dst_dev, &g);
+    if (rc) return rc;
+    const bool vec = (((uintptr_t)idx_dev | (uintptr_t)dst_dev) & 15u) == 0 && ld_dst % 4 == 0;
+    if (vec)
+        k_gather_rows_sharded<true><<<(unsigned)gse_div_up(gse_div_up(n_out, 4), GR_THREADS), GR_THREADS, 0,
+                                      (cudaStream_t)stream>>>(g, idx_dev, n_out, dst_dev, ld_dst, ncols);
+    else
+        k_gather_rows_sharded<false><<<(unsigned)gse_div_up(n_out, GR_THREADS), GR_THREADS, 0, (cudaStream_t)stream>>>(
+            g, idx_dev, n_out, dst_dev, ld_dst, ncols);
+    GSE_CHECK_LAUNCH(ctx);
+    return GSE_OK;
 }
 
 extern "C" int gse_gather_rows(gse_ctx* ctx, const int32_t* idx_dev, int64_t n_out, const float* src_dev,

@@ -79,7 +79,7 @@ class WeightedEnsemble:
 
     NCOLS = 5
 
-    def _init_ensemble(self, N, state_pdf, measurement_pdf, device, seed, workspace_rows=None):
+    def _init_ensemble(self, N, state_pdf, measurement_pdf, device, seed, workspace_rows=None, peer=False):
         self.N_particles = int(N)
         if self.N_particles < 1:
             raise ValueError("N_particles must be >= 1")
@@ -92,8 +92,14 @@ class WeightedEnsemble:
         n = self.N_particles
         self._ld = _device.round_up(n, 64)
         dev = self.device
-        self._state = torch.zeros((self.NCOLS, self._ld), dtype=torch.float32, device=dev)
-        self._state_alt = torch.zeros((self.NCOLS, self._ld), dtype=torch.float32, device=dev)
+        self._peer_bufs = {}
+        if peer:        # sharded run: buffers other ranks read live in IPC-exportable memory (gpu_se_b200/_peer.py)
+            from gpu_se_b200 import _peer
+            self._state, self._peer_bufs["state"] = _peer.peer_zeros(dev, (self.NCOLS, self._ld), torch.float32)
+            self._state_alt, self._peer_bufs["state_alt"] = _peer.peer_zeros(dev, (self.NCOLS, self._ld), torch.float32)
+        else:
+            self._state = torch.zeros((self.NCOLS, self._ld), dtype=torch.float32, device=dev)
+            self._state_alt = torch.zeros((self.NCOLS, self._ld), dtype=torch.float32, device=dev)
         self._loglik = torch.zeros(self._ld, dtype=torch.float32, device=dev)
         self._loglik_zero = True       # logically all zero; the buffer need not be
         self._idx = torch.zeros(self._ld, dtype=torch.int32, device=dev)      # ancestor index of the last resample
@@ -104,7 +110,11 @@ class WeightedEnsemble:
         self._loglik_dirty = False
         self._stats = torch.tensor([0.0, float(n), 0.0, 0.0], dtype=torch.float64, device=dev)
         self._stats_uniform = self._stats.clone()
-        self._cumsum = torch.zeros(self._ld, dtype=torch.int64, device=dev)      # uint64 payload
+        if peer:
+            from gpu_se_b200 import _peer
+            self._cumsum, self._peer_bufs["cumsum"] = _peer.peer_zeros(dev, (self._ld,), torch.int64)
+        else:
+            self._cumsum = torch.zeros(self._ld, dtype=torch.int64, device=dev)  # uint64 payload
         self._offtot = torch.zeros(2, dtype=torch.int64, device=dev)             # [offset, total]
         self._mom = torch.zeros(48, dtype=torch.float64, device=dev)
         self._mom_host = torch.zeros(48, dtype=torch.float64).pin_memory()

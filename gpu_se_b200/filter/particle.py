@@ -26,16 +26,17 @@ class ParallelParticleFilter(WeightedEnsemble):
     particles : (N, 5) array, initial particles instead of ``x0.draw(N)``
     index0 : int, global index of row 0 when this filter is one shard of a larger population
     workspace_rows : int, size the library workspace for this many rows (>= N_particles)
+    peer : bool, keep state and cumulative weights in memory other ranks can map (sharded runs)
     """
 
     NCOLS = 5
 
     def __init__(self, f, g, N_particles, x0, state_pdf, measurement_pdf, *, device=None, seed=None,
-                 n_sub=1, particles=None, index0=0, workspace_rows=None):
+                 n_sub=1, particles=None, index0=0, workspace_rows=None, peer=False):
         self.f = f
         self.g = g
         self._model_id = model_id_for(f, g)
-        self._init_ensemble(N_particles, state_pdf, measurement_pdf, device, seed, workspace_rows)
+        self._init_ensemble(N_particles, state_pdf, measurement_pdf, device, seed, workspace_rows, peer)
         self._index0 = int(index0)     # global index of local row 0 (sharded runs): keys the Philox stream
         self._n_sub = int(n_sub)
         n = self.N_particles

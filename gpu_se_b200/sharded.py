@@ -11,15 +11,30 @@ The reference has no multi-GPU path; this is the north-s
   weights with the same fixed-point scale (csrc/gse_resample.cu) -- the cumulative weights are
   integers, hence independent of how the rows are split over GPUs.
 * ``resample``: local scan -> all-gather of the G shard totals T_s (uint64) -> exclusive offsets
-  O_s and total T.  Shard s is the *source* of the global outputs ``[a_s, b_s)`` whose sample
-  position falls in ``(O_s, O_s + T_s] / T`` (closed form through the device's exact predicate,
-  ``gse_count_outputs_below``); it runs the search + gather for that range, writes the part it
-  owns itself straight into its own state and ships the rest as contiguous column slabs to the
-  owning shards (grouped NCCL send/recv, received in place -- no packing copies).
+  O_s and total T.  Two exchange modes:
+
+  ``exchange="peer"`` (default on GPUs with peer access): every rank keeps its state and
+  cumulative-weight buffers in IPC-exportable memory and maps every other rank's once.  Each rank
+  then searches the rows of ALL shards for its own output slots and gathers the ancestors'
+  rows, both kernels reading the other GPUs' memory directly over NVLink / NVSwitch
+  (``gse_resample_search_sharded`` / ``gse_gather_rows_sharded``): the compute kernels ARE the
+  communication.  The offsets stay on the device (all-gather + cumsum on the stream), so a step
+  never synchronises the host; the collectives that every step contains anyway order the
+  buffer reuse between ranks.
+
+  ``exchange="slabs"``: host-planned.  Shard s is the *source* of the global outputs
+  ``[a_s, b_s)`` whose sample position falls in ``(O_s, O_s + T_s] / T`` (closed form through the
+  device's exact predicate, ``gse_count_outputs_below``); it runs the search + gather for that
+  range, writes the part it owns itself straight into its own state and ships the rest as
+  contiguous column slabs to the owning shards (grouped NCCL send/recv, received in place).
+  Needs one device-to-host read of the G totals per resample; kept for GPUs without peer
+  access and as the cross-check of the peer path.
 
 ``plan_resample`` and ``exchange_columns`` are pure host / ``torch.distributed`` code and run on
 CPU tensors over ``gloo`` as well (tests/test_sharded_cpu.py).
 """
+import ctypes
+
 import numpy
 import torch
 import torch.distributed as dist
@@ -120,7 +135,7 @@ class ShardedParticleFilter:
     ``particles`` / ``weights`` are this rank's shard."""
 
     def __init__(self, f, g, N_particles, x0, state_pdf, measurement_pdf, *, device=None, seed=0, n_sub=1,
-                 group=None, particles=None):
+                 group=None, particles=None, exchange="peer"):
         if not dist.is_initialized():
             raise RuntimeError("ShardedParticleFilter needs an initialised torch.distributed process group")
         self.group = group
@@ -134,14 +149,121 @@ class ShardedParticleFilter:
         local_particles = None
         if particles is not None:
             local_particles = _device.to_numpy(particles)[lo:hi]
+        if exchange not in ("peer", "slabs"):
+            raise ValueError("exchange must be 'peer' or 'slabs'")
+        if self.world > _lib.GSE_MAX_SHARDS:
+            raise ValueError("at most %d shards" % _lib.GSE_MAX_SHARDS)
+        self.exchange = exchange
+        widest = max(b - a for a, b in self.bounds)
         self.local = ParallelParticleFilter(f, g, hi - lo, x0, state_pdf, measurement_pdf, device=device, seed=seed,
                                             n_sub=n_sub, particles=local_particles, index0=lo,
-                                            workspace_rows=max(b - a for a, b in self.bounds))
+                                            workspace_rows=max(widest, self.N_particles // 4 + 4096),
+                                            peer=(exchange == "peer"))
         self.device = self.local.device
         self._set_uniform()
+        if exchange == "peer":
+            self._open_peers()
         self.last_plan = None
         self.exchanged_rows = 0
         self._stage_hook = None
+        self._pending = False
+
+    # -- peer memory -----------------------------------------------------------------------------
+    def _open_peers(self):
+        """Exchange the IPC handles of (state, state_alt, cumsum) and map every other rank's buffers."""
+        from gpu_se_b200 import _peer
+        loc = self.local
+        if self.N_particles > 2 ** 31 - 1:
+            raise ValueError("peer exchange indexes global rows with int32")
+        mine = tuple(loc._peer_bufs[k].handle for k in ("state", "state_alt", "cumsum")) + (loc._ld,)
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=self.group)
+        self._mappings = []
+        self._peer_ptr = []                  # per rank: (state, state_alt, cumsum) device pointers, ld
+        for s, (h0, h1, hc, ld) in enumerate(everyone):
+            if s == self.rank:
+                self._peer_ptr.append((loc._peer_bufs["state"].ptr, loc._peer_bufs["state_alt"].ptr,
+                                       loc._peer_bufs["cumsum"].ptr, ld))
+            else:
+                maps = [_peer.PeerMapping(self.device, h) for h in (h0, h1, hc)]
+                self._mappings += maps
+                self._peer_ptr.append((maps[0].ptr, maps[1].ptr, maps[2].ptr, ld))
+        self._parity = 0                     # which of (state, state_alt) is current -- flips on every rank together
+        self._offsets = torch.zeros(self.world + 1, dtype=torch.int64, device=self.device)
+        self._totals = torch.zeros(self.world, dtype=torch.int64, device=self.device)
+        self._shards = []
+        for parity in (0, 1):
+            sh = _lib.gse_shards()
+            sh.nshards = self.world
+            for s, (a, b) in enumerate(self.bounds):
+                sh.rows[s] = a
+                sh.cumsum_dev[s] = self._peer_ptr[s][2]
+                sh.state_dev[s] = self._peer_ptr[s][parity]
+                sh.ld[s] = self._peer_ptr[s][3]
+            sh.rows[self.world] = self.N_particles
+            sh.offsets_dev = self._offsets.data_ptr()
+            self._shards.append(sh)
+        self._idx_global = torch.zeros(_device.round_up(loc.N_particles, 64), dtype=torch.int32, device=self.device)
+        dist.barrier(group=self.group)
+
+    def close(self):
+        """Unmap the other ranks' buffers (collective: every rank must call it before any frees its own)."""
+        if getattr(self, "_mappings", None):
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)
+            for m in self._mappings:
+                m.close()
+            self._mappings = []
+            dist.barrier(group=self.group)
+
+    def _resample_peer(self, r, return_index):
+        loc = self.local
+        n_loc = loc.N_particles
+        lo, hi = self.bounds[self.rank]
+        loc._scan()                                               # local cumsum, T_s -> _offtot[1]
+        if self._stage_hook is not None:
+            self._stage_hook("scan")
+        dist.all_gather_into_tensor(self._totals, loc._offtot[1:2], group=self.group)
+        torch.cumsum(self._totals, 0, out=self._offsets[1:])      # offsets[0] stays 0; offsets[G] = total
+        if self._stage_hook is not None:
+            self._stage_hook("offsets")
+        sh = self._shards[self._parity]
+        _lib.check(_lib.lib.gse_resample_search_sharded(loc._ctx.handle, ctypes.byref(sh), r, lo, n_loc,
+                                                        self._idx_global.data_ptr(), loc._stream()))
+        # lazy, as on one GPU: the rows move when the next kernel reads them (predict / moments pull them
+        # out of the owning shard's memory through the global ancestor index)
+        self._pending = True
+        loc._loglik_zero = True
+        loc._reset_uniform()
+        self._set_uniform()
+        loc._touch()
+        self.exchanged_rows = None                                # known on the device only: see rows_from_peers()
+        return self._idx_global[:n_loc].to(torch.int64) if return_index else None
+
+    def _materialise(self):
+        """Apply a pending sharded resample: pull the ancestors' rows into this shard's other buffer."""
+        if getattr(self, "_pending", False):
+            loc = self.local
+            sh = self._shards[self._parity]
+            _lib.check(_lib.lib.gse_gather_rows_sharded(loc._ctx.handle, ctypes.byref(sh),
+                                                        self._idx_global.data_ptr(), loc.N_particles,
+                                                        loc._state_alt.data_ptr(), loc._ld, loc.NCOLS, loc._stream()))
+            self._swap()
+
+    def _swap(self):
+        loc = self.local
+        loc._state, loc._state_alt = loc._state_alt, loc._state
+        self._parity ^= 1
+        self._pending = False
+        loc._touch()
+
+    def rows_from_peers(self):
+        """Rows of the last resample whose ancestor lives on another GPU (device-to-host read)."""
+        if self.exchange != "peer":
+            return self.exchanged_rows
+        lo, hi = self.bounds[self.rank]
+        idx = self._idx_global[:self.local.N_particles]
+        return int(((idx < lo) | (idx >= hi)).sum().item())
 
     # -- weights ---------------------------------------------------------------------------------
     def _set_uniform(self):
@@ -152,6 +274,7 @@ class ShardedParticleFilter:
 
     @property
     def particles(self):
+        self._materialise()
         return self.local.particles
 
     @property
@@ -170,34 +293,59 @@ class ShardedParticleFilter:
         self.local._base_max = full.max()
 
     def _allreduce_stats(self):
-        st = self.local._stats
-        m = st[0:1].clone()
-        dist.all_reduce(m, op=dist.ReduceOp.MAX, group=self.group)
-        s = st[1:2] * torch.exp(st[0:1] - m)
-        dist.all_reduce(s, op=dist.ReduceOp.SUM, group=self.group)
-        st[0:1] = m
-        st[1:2] = s
+        """Global (M, S) from the shards' (M_s, S_s): one all-gather of a pair + one tiny kernel."""
+        loc = self.local
+        if self.world == 1:
+            return
+        if not hasattr(self, "_stat_pairs"):
+            self._stat_pairs = torch.zeros(2 * self.world, dtype=torch.float64, device=self.device)
+        dist.all_gather_into_tensor(self._stat_pairs, loc._stats[0:2], group=self.group)
+        _lib.check(_lib.lib.gse_merge_stats(loc._ctx.handle, self._stat_pairs.data_ptr(), self.world,
+                                            loc._stats.data_ptr(), loc._stream()))
 
     # -- the three stages ------------------------------------------------------------------------
     def predict(self, u, dt, noise=None):
+        lo, hi = self.bounds[self.rank]
         if noise is not None:
-            lo, hi = self.bounds[self.rank]
             noise = _device.to_numpy(noise)[lo:hi]
-        self.local.predict(u, dt, noise=noise)
+        if not getattr(self, "_pending", False):
+            self.local.predict(u, dt, noise=noise)
+            return
+        # pending sharded resample: read row idx[i] out of whichever GPU holds it, write the other buffer
+        loc = self.local
+        n = loc.N_particles
+        if noise is None:
+            noise = loc._host_noise(loc.state_pdf, n)
+        nz_ptr, ld_nz, nz = None, 0, None
+        if noise is not None:
+            nz = torch.zeros((5, loc._ld), dtype=torch.float32, device=self.device)
+            nz[:, :n].copy_(torch.as_tensor(numpy.ascontiguousarray(_device.to_numpy(noise), dtype=numpy.float32)
+                                            .reshape(n, 5), device=self.device).t())
+            nz_ptr, ld_nz = nz.data_ptr(), loc._ld
+        sh = self._shards[self._parity]
+        _lib.check(_lib.lib.gse_pf_predict_sharded(loc._ctx.handle, ctypes.byref(sh), self._idx_global.data_ptr(),
+                                                   loc._state_alt.data_ptr(), loc._ld, n, _lib.as_double2(u), float(dt),
+                                                   loc._n_sub, loc._seed, loc._step, loc._index0, nz_ptr, ld_nz,
+                                                   loc._stream()))
+        loc._step += 1
+        self._swap()
 
     def update(self, u, z):
+        self._materialise()
         self.local.update(u, z)
         self._allreduce_stats()
 
     def resample(self, r=None, return_index=False):
         loc = self.local
-        loc._materialise()
+        self._materialise()
         if r is None:
             rt = torch.tensor([numpy.random.rand()], dtype=torch.float64, device=self.device)
             dist.broadcast(rt, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0,
                            group=self.group)
             r = float(rt.item())
         r = float(r)
+        if self.exchange == "peer":
+            return self._resample_peer(r, return_index)
         n_loc = loc.N_particles
         lo, hi = self.bounds[self.rank]
         loc._scan()                                               # local cumsum, T_s -> _offtot[1]
@@ -244,7 +392,14 @@ class ShardedParticleFilter:
     # -- estimates -------------------------------------------------------------------------------
     def _global_moments(self):
         loc = self.local
-        loc._launch_moments()
+        if getattr(self, "_pending", False):
+            sh = self._shards[self._parity]
+            _lib.check(_lib.lib.gse_pf_moments_sharded(
+                loc._ctx.handle, ctypes.byref(sh), self._idx_global.data_ptr(), loc.N_particles, loc._loglik_ptr(),
+                loc._base.data_ptr() if loc._base is not None else None, loc._stats.data_ptr(), loc._mom.data_ptr(),
+                loc._stream()))
+        else:
+            loc._launch_moments()
         loc._mom[41:43].copy_(loc._stats[0:2])
         allm = [torch.empty_like(loc._mom) for _ in range(self.world)]
         dist.all_gather(allm, loc._mom, group=self.group)

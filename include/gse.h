@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define GSE_ABI_VERSION 2
+#define GSE_ABI_VERSION 3
 
 #define GSE_NX 5        /* states  (Cg, Cx, Cfa, Ce, Ch)   model/BioreactorModel.py:191 */
 #define GSE_NU 2        /* inputs  (Fg_in, Fm_in)          model/BioreactorModel.py:195 */
@@ -52,6 +52,8 @@ extern "C" {
 #define GSE_NSIGMA 11   /* 2*Nx+1 sigma points             filter/gs_ukf.py:61 */
 #define GSE_NCOV 15     /* lower triangle of a 5x5 covariance, row-major (00,10,11,20,21,22,...) */
 #define GSE_MAX_ND 8    /* mixture components supported */
+#define GSE_MAX_SHARDS 8   /* GPUs of one node a population can be sharded over */
+#define GSE_IPC_HANDLE_BYTES 64
 
 #define GSE_MODEL_BIOREACTOR 1   /* Bioreactor.homeostatic_DEs / static_outputs */
 
@@ -172,6 +174,57 @@ int gse_resample_search(gse_ctx* ctx, const uint64_t* cumsum_dev, int64_t n_src,
 int gse_gather_rows(gse_ctx* ctx, const int32_t* idx_dev, int64_t n_out, const float* src_dev,
                     int64_t ld_src, float* dst_dev, int64_t ld_dst, int ncols, float* loglik_out_dev,
                     void* stream);
+
+/* ---- sharded populations: peer memory over NVLink / NVSwitch (no reference counterpart: the
+ * reference is single-GPU) ---------------------------------------------------- */
+
+/* Device memory other processes of the node can map (cudaMalloc + cudaIpcGetMemHandle).  The
+ * sharded filter keeps its state and cumulative-weight buffers here; every rank opens every other
+ * rank's buffers once and the resample kernels then read them directly. */
+int gse_peer_alloc(int device, int64_t bytes, void** ptr_out, unsigned char handle_out[GSE_IPC_HANDLE_BYTES]);
+int gse_peer_free(int device, void* ptr);
+int gse_peer_open(int device, const unsigned char handle[GSE_IPC_HANDLE_BYTES], void** ptr_out);
+int gse_peer_close(int device, void* ptr);
+
+/* The shards of one population: shard s owns the global rows [rows[s], rows[s+1]); cumsum_dev[s] /
+ * state_dev[s] are its local cumulative weights (gse_scan_weights) and SoA state (leading
+ * dimension ld[s]) -- the caller's own buffers for its own shard, gse_peer_open mappings for the
+ * others.  offsets_dev is a DEVICE array of nshards + 1 uint64: the exclusive prefix of the shard
+ * totals and, last, the global total (all-gathered on the stream, never seen by the host). */
+typedef struct gse_shards {
+    int32_t nshards;
+    int64_t rows[GSE_MAX_SHARDS + 1];
+    const uint64_t* cumsum_dev[GSE_MAX_SHARDS];
+    const float* state_dev[GSE_MAX_SHARDS];
+    int64_t ld[GSE_MAX_SHARDS];
+    const uint64_t* offsets_dev;
+} gse_shards;
+
+/* gse_resample_search over the rows of ALL shards for the outputs [out0, out0 + n_out) (this
+ * shard's own slots): idx_out_dev[i - out0] = GLOBAL ancestor row (int32).  The kernel reads the
+ * other shards' cumulative weights through peer memory -- search and communication are one
+ * kernel, nothing is staged and the host never synchronises. */
+int gse_resample_search_sharded(gse_ctx* ctx, const gse_shards* shards, double r, int64_t out0,
+                                int64_t n_out, int32_t* idx_out_dev, void* stream);
+
+/* dst[:, i] = state row idx[i] (global) pulled from the owning shard's memory, ncols SoA columns. */
+int gse_gather_rows_sharded(gse_ctx* ctx, const gse_shards* shards, const int32_t* idx_dev,
+                            int64_t n_out, float* dst_dev, int64_t ld_dst, int ncols, void* stream);
+
+/* stats_dev[0..1] = (max_s M_s, sum_s S_s exp(M_s - M)) from the nshards all-gathered pairs
+ * pairs_dev[2 s .. 2 s + 1] = (M_s, S_s) written by each shard's update kernel. */
+int gse_merge_stats(gse_ctx* ctx, const double* pairs_dev, int nshards, double* stats_dev, void* stream);
+
+/* gse_pf_predict / gse_pf_moments reading row idx[i] (GLOBAL ancestor row from
+ * gse_resample_search_sharded) straight out of the owning shard's memory: the lazy resample of a
+ * sharded population -- the rows cross NVLink inside the kernel that consumes them. */
+int gse_pf_predict_sharded(gse_ctx* ctx, const gse_shards* shards, const int32_t* idx_dev, float* x_dst_dev,
+                           int64_t ld_dst, int64_t n, const double u[GSE_NU], double dt, int n_sub,
+                           uint64_t seed, uint64_t step, int64_t index0, const float* noise_dev,
+                           int64_t ld_noise, void* stream);
+int gse_pf_moments_sharded(gse_ctx* ctx, const gse_shards* shards, const int32_t* idx_dev, int64_t n,
+                           const float* loglik_dev, const double* base_dev, const double* stats_dev,
+                           double* out_dev, void* stream);
 
 /* Number of outputs i in [0, n_total) whose u_i maps at or below integer cumulative weight
  * `bound` of `total`, i.e. #{ i : fl(fl(bound)/fl(total)) >= u_i }: host helper used by the sharded

@@ -1,6 +1,7 @@
 """-m gpu tests of the sharded particle filter (gpu_se_b200/sharded.py) over NCCL.
 
 * world size 1 (always runs): the sharded driver must reproduce the single-GPU filter bit for bit.
+* both exchange modes: "peer" (kernels read the other GPUs' memory over NVLink) and "slabs" (NCCL send/recv)
 * world size 2 (needs two GPUs; skipped otherwise): two shards of one population must reproduce
   the single-GPU run of the same seed bit for bit -- Philox is keyed by the global row index and the
   cumulative weights are integers, so neither the noise nor the resample depends on the split.
@@ -37,11 +38,13 @@ def _run_cycles(pf, n_cycles, seed):
         pf.update(u, z)
         est_u = pf.point_estimate(normalised=True)
         pf.resample(r=r)
-        out.append((est_u, pf.point_estimate(), pf.point_covariance()))
+        out.append((est_u, pf.point_estimate(), pf.point_covariance()))      # moments through the pending index
+    pf.update(u, z)                           # update straight after a resample: the pending gather is applied first
+    out.append((pf.point_estimate(normalised=True), pf.point_estimate(), pf.point_covariance()))
     return out
 
 
-def _worker(rank, world, port, n, q):
+def _worker(rank, world, port, n, exchange, q):
     try:
         sys.path.insert(0, ROOT)
         sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -57,9 +60,9 @@ def _worker(rank, world, port, n, q):
         from gpu_se_b200.sharded import ShardedParticleFilter
         x0, state, meas = make_pdfs(g)
         f, gg = g.Bioreactor.homeostatic_DEs, g.Bioreactor.static_outputs
-        spf = ShardedParticleFilter(f, gg, n, x0, state, meas, device=dev, seed=77)
+        spf = ShardedParticleFilter(f, gg, n, x0, state, meas, device=dev, seed=77, exchange=exchange)
         got = _run_cycles(spf, 4, seed=3)
-        exchanged = spf.exchanged_rows
+        exchanged = spf.rows_from_peers()
         parts = [torch.empty((b - a, 5), dtype=torch.float32, device=dev) for a, b in spf.bounds]
         for s in range(world):
             if s == rank:
@@ -75,6 +78,7 @@ def _worker(rank, world, port, n, q):
                 assert numpy.allclose(a0, b0, rtol=1e-10, atol=1e-10)
                 assert numpy.allclose(a1, b1, rtol=1e-10, atol=1e-10)
                 assert a2 == pytest.approx(b2, rel=1e-8)
+        spf.close()
         q.put((rank, "ok", exchanged))
         dist.destroy_process_group()
     except Exception as e:      # noqa: BLE001
@@ -82,12 +86,12 @@ def _worker(rank, world, port, n, q):
         q.put((rank, "fail", traceback.format_exc() + repr(e)))
 
 
-def _launch(world, n):
+def _launch(world, n, exchange):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(rank, world, port, n, q)) for rank in range(world)]
+    procs = [ctx.Process(target=_worker, args=(rank, world, port, n, exchange, q)) for rank in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=300) for _ in procs]
@@ -98,15 +102,17 @@ def _launch(world, n):
     return results
 
 
+@pytest.mark.parametrize("exchange", ["peer", "slabs"])
 @pytest.mark.parametrize("n", [4096, 100003])
-def test_world1_equals_single_gpu(n):
-    _launch(1, n)
+def test_world1_equals_single_gpu(n, exchange):
+    _launch(1, n, exchange)
 
 
+@pytest.mark.parametrize("exchange", ["peer", "slabs"])
 @pytest.mark.parametrize("n", [8192, 1000003])
-def test_world2_equals_single_gpu(n):
+def test_world2_equals_single_gpu(n, exchange):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
-    results = _launch(2, n)
+    results = _launch(2, n, exchange)
     assert any(info > 0 for _, _, info in results), "informative measurement: shards must exchange rows"
