@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--log2n", type=float, default=24.0, help="log2 of particles per GPU")
     ap.add_argument("--cpu-log2n", type=int, default=13, help="log2 of the CPU-baseline sample size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sharded", action="store_true",
+                    help="use the sharded driver even on one GPU (profiling the peer-memory kernels under ncu)")
     return ap.parse_args()
 
 
@@ -225,6 +227,10 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    elif args.sharded:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
 
     import gpu_se_b200 as g
     from gpu_se_b200.model.BioreactorModel import X_STEADY
@@ -238,7 +244,7 @@ def run_ours(args):
                                      [0.85, 0.15])
     x0 = g.MultivariateGaussianSum(state_means + numpy.array(X_STEADY)[None, :], state_covs, [0.75, 0.25])
     f, gg = g.Bioreactor.homeostatic_DEs, g.Bioreactor.static_outputs
-    if world > 1:
+    if world > 1 or args.sharded:
         from gpu_se_b200.sharded import ShardedParticleFilter
         pf = ShardedParticleFilter(f, gg, n_total, x0, state, meas, device=dev, seed=1234)
     else:

@@ -53,7 +53,7 @@ SIGNATURES = {
     "gse_pf_predict": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_dbl_p, c_dbl, c_int, c_u64, c_u64, c_i64,
                                c_vp, c_i64, c_vp]),
     "gse_pf_update": (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_dbl_p, c_dbl_p, c_vp, c_vp]),
-    "gse_pf_moments": (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "gse_pf_moments": (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]),
     "gse_loglik_max": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
     "gse_weights_linear": (c_int, [c_vp, c_vp, c_vp, c_i64, c_dbl, c_vp, c_vp]),
     "gse_scan_weights": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
@@ -67,7 +67,7 @@ SIGNATURES = {
     "gse_gather_rows_sharded": (c_int, [c_vp, c_shards_p, c_vp, c_i64, c_vp, c_i64, c_int, c_vp]),
     "gse_pf_predict_sharded": (c_int, [c_vp, c_shards_p, c_vp, c_vp, c_i64, c_i64, c_dbl_p, c_dbl, c_int, c_u64, c_u64,
                                        c_i64, c_vp, c_i64, c_vp]),
-    "gse_pf_moments_sharded": (c_int, [c_vp, c_shards_p, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "gse_pf_moments_sharded": (c_int, [c_vp, c_shards_p, c_vp, c_i64, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]),
     "gse_merge_stats": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp]),
     "gse_count_outputs_below": (c_i64, [c_u64, c_u64, c_dbl, c_i64]),
     "gse_threshold_u64": (c_u64, [c_dbl, c_u64]),

@@ -492,11 +492,15 @@ __device__ __forceinline__ void block_max_sumexp_finalize(const float vals[NV], 
     block_merge_max_sumexp<THREADS>(acc.m, acc.s, block_max, block_sum, ticket, stats);
 }
 
-// column 0 of global row k and the leading dimension of the shard that owns it
-__device__ __forceinline__ const float* shard_row(const GatherShards& g, int64_t k, int64_t& ld) {
+__device__ __forceinline__ int shard_of(const GatherShards& g, int64_t k) {
     int s = 0;
 #pragma unroll
     for (int t = 1; t < GSE_MAX_SHARDS; ++t) s += (t < g.nseg && k >= g.seg_row[t]) ? 1 : 0;
+    return s;
+}
+// column 0 of global row k and the leading dimension of the shard that owns it
+__device__ __forceinline__ const float* shard_row(const GatherShards& g, int64_t k, int64_t& ld) {
+    const int s = shard_of(g, k);
     ld = g.ld[s];
     return g.state[s] + (k - g.seg_row[s]);
 }

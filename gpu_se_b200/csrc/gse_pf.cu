@@ -74,12 +74,25 @@ k_pf_predict(const float* xs, int64_t lds, const int32_t* __restrict__ idx, cons
         const int4 id4 = *reinterpret_cast<const int4*>(idx + row0);
         const int id[4] = {id4.x, (row0 + 1 < n) ? id4.y : id4.x, (row0 + 2 < n) ? id4.z : id4.x,
                            (row0 + 3 < n) ? id4.w : id4.x};
+        // idx is non-decreasing: when the first and the last ancestor sit in one shard (all but a
+        // handful of threads) one look-up serves the four rows
+        const int s0 = shard_of(shards, id[0]);
+        if (id[3] < shards.seg_row[s0 + 1]) {
+            const int64_t ld0 = shards.ld[s0];
+            const float* base = shards.state[s0] - shards.seg_row[s0];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            int64_t ld;
-            const float* p = shard_row(shards, id[r], ld);
+            for (int r = 0; r < 4; ++r) {
 #pragma unroll
-            for (int j = 0; j < 5; ++j) v[j][r] = p[j * ld];
+                for (int j = 0; j < 5; ++j) v[j][r] = base[j * ld0 + id[r]];
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                int64_t ld;
+                const float* p = shard_row(shards, id[r], ld);
+#pragma unroll
+                for (int j = 0; j < 5; ++j) v[j][r] = p[j * ld];
+            }
         }
     } else if (GMODE == 1) {
         // rows of the resampled population are read through the ancestor index (the pending
@@ -352,13 +365,15 @@ extern "C" int gse_weights_linear(gse_ctx* ctx, const float* loglik_dev, const d
 // out: [0] S0, [1..5] S1, [6..20] S2 lower triangle, [21..25] pivot; (GSF: [26..40] sum w P)
 // ------------------------------------------------------------------------------------------------
 #define MOM_THREADS 256
+// NEXTRA: 0 particle filter, 15 GS-UKF (+ sum w P), -1 means only (S0, S1: point_estimate alone)
 template <int NEXTRA, int GMODE>      // GMODE as in k_pf_predict
-__global__ void __launch_bounds__(MOM_THREADS)
+__global__ void __launch_bounds__(MOM_THREADS, NEXTRA < 0 ? 4 : (NEXTRA == 0 ? 2 : 1))
 k_moments(const float* __restrict__ x, const float* __restrict__ extra, int64_t ld, int64_t n,
           const int32_t* __restrict__ idx, const __grid_constant__ GatherShards shards,
           const float* __restrict__ loglik, const double* __restrict__ base,
           const double* __restrict__ stats, double* partials, unsigned int* ticket, double* out) {
-    constexpr int NV = 21 + NEXTRA;
+    constexpr bool MEAN = NEXTRA < 0;
+    constexpr int NV = MEAN ? 6 : 21 + NEXTRA;
     const float M = (float)stats[0];
     float p[5];
 #pragma unroll
@@ -418,8 +433,10 @@ k_moments(const float* __restrict__ x, const float* __restrict__ extra, int64_t 
                 for (int j = 0; j < 5; ++j) {
                     const double wd = w * d[j];
                     acc[1 + j] += wd;
+                    if (!MEAN) {
 #pragma unroll
-                    for (int k = 0; k <= j; ++k) { acc[t] = fma(wd, d[k], acc[t]); ++t; }
+                        for (int k = 0; k <= j; ++k) { acc[t] = fma(wd, d[k], acc[t]); ++t; }
+                    }
                 }
                 if (NEXTRA > 0) {
 #pragma unroll
@@ -460,7 +477,7 @@ k_moments(const float* __restrict__ x, const float* __restrict__ extra, int64_t 
 }
 
 static int launch_moments(gse_ctx* ctx, const float* x, const float* extra, int64_t ld, int64_t n,
-                          const int32_t* idx, const GatherShards* shards, const float* loglik, const double* base, const double* stats, double* out,
+                          const int32_t* idx, const GatherShards* shards, bool mean_only, const float* loglik, const double* base, const double* stats, double* out,
                           void* stream) {
     GSE_REQUIRE(ctx != NULL && stats != NULL && out != NULL, "ctx / stats / out is NULL");
     GSE_REQUIRE(n >= 1 && n <= ctx->n_max, "n out of range for this context");
@@ -480,7 +497,11 @@ static int launch_moments(gse_ctx* ctx, const float* x, const float* extra, int6
                                                                                  base, stats, ctx->red_partials, \
                                                                                  ctx->ticket + 2, out)
     if (extra) { if (idx) LAUNCH_MOM(15, 1, extra); else LAUNCH_MOM(15, 0, extra); }
-    else if (shards) LAUNCH_MOM(0, 2, NULL);
+    else if (mean_only) {
+        if (shards) LAUNCH_MOM(-1, 2, NULL);
+        else if (idx) LAUNCH_MOM(-1, 1, NULL);
+        else LAUNCH_MOM(-1, 0, NULL);
+    } else if (shards) LAUNCH_MOM(0, 2, NULL);
     else { if (idx) LAUNCH_MOM(0, 1, NULL); else LAUNCH_MOM(0, 0, NULL); }
 #undef LAUNCH_MOM
     GSE_CHECK_LAUNCH(ctx);
@@ -489,24 +510,27 @@ static int launch_moments(gse_ctx* ctx, const float* x, const float* extra, int6
 
 extern "C" int gse_pf_moments(gse_ctx* ctx, const float* x_dev, int64_t ld, int64_t n, const int32_t* idx_dev,
                               const float* loglik_dev, const double* base_dev, const double* stats_dev,
-                              double* out_dev, void* stream) {
-    return launch_moments(ctx, x_dev, NULL, ld, n, idx_dev, NULL, loglik_dev, base_dev, stats_dev, out_dev, stream);
+                              int mean_only, double* out_dev, void* stream) {
+    return launch_moments(ctx, x_dev, NULL, ld, n, idx_dev, NULL, mean_only != 0, loglik_dev, base_dev, stats_dev,
+                          out_dev, stream);
 }
 
 extern "C" int gse_pf_moments_sharded(gse_ctx* ctx, const gse_shards* shards, const int32_t* idx_dev, int64_t n,
                                       const float* loglik_dev, const double* base_dev, const double* stats_dev,
-                                      double* out_dev, void* stream) {
+                                      int mean_only, double* out_dev, void* stream) {
     GatherShards g;
     int rc = gse_build_gather_shards(shards, NULL, &g);
     if (rc) return rc;
-    return launch_moments(ctx, NULL, NULL, 0, n, idx_dev, &g, loglik_dev, base_dev, stats_dev, out_dev, stream);
+    return launch_moments(ctx, NULL, NULL, 0, n, idx_dev, &g, mean_only != 0, loglik_dev, base_dev, stats_dev, out_dev,
+                          stream);
 }
 
 extern "C" int gse_gsf_moments(gse_ctx* ctx, const float* mean_dev, const float* cov_dev, int64_t ld, int64_t n,
                                const int32_t* idx_dev, const float* loglik_dev, const double* base_dev,
                                const double* stats_dev, double* out_dev, void* stream) {
     GSE_REQUIRE(cov_dev != NULL, "cov is NULL");
-    return launch_moments(ctx, mean_dev, cov_dev, ld, n, idx_dev, NULL, loglik_dev, base_dev, stats_dev, out_dev, stream);
+    return launch_moments(ctx, mean_dev, cov_dev, ld, n, idx_dev, NULL, false, loglik_dev, base_dev, stats_dev, out_dev,
+                          stream);
 }
 
 // ------------------------------------------------------------------------------------------------

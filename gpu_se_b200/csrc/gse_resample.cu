@@ -350,6 +350,31 @@ k_resample_partition(const ResampleArgs a, int64_t* __restrict__ part, int64_t n
     int64_t lo = diag > a.n_out ? diag - a.n_out : 0;
     int64_t hi = diag < a.n_src ? diag : a.n_src;
     // smallest s in [lo, hi] with NOT precedes(C[s], output diag - 1 - s); true on a prefix
+    if (SEG) {
+        // the last row of shard t - 1 carries exactly the offset of shard t: probe the shard boundaries
+        // with the offsets alone, so that the search below stays inside one shard's array
+        for (int t = 1; t < a.nseg; ++t) {
+            const int64_t mid = a.seg_row[t] - 1;
+            if (mid < lo || mid >= hi) continue;
+            const double di = (double)(a.out0 + (diag - 1 - mid));
+            if (precedes(a, a.offtot[t], output_qlo(a, di, off, Td), di, off, Td)) lo = mid + 1; else hi = mid;
+        }
+    }
+    // end points first (one round of loads): diagonals that lie entirely among sources without offspring
+    // -- the other shards' rows in a sharded run, the tail of a degenerate weight vector -- finish here
+    if (lo < hi) {
+        const int64_t mid = lane == 0 ? lo : hi - 1;
+        bool pred = false;
+        if (lane < 2) {
+            const uint64_t c = source_weight<SEG>(a, mid, off0);
+            const double di = (double)(a.out0 + (diag - 1 - mid));
+            pred = precedes(a, c, output_qlo(a, di, off, Td), di, off, Td);
+        }
+        const unsigned int bal = __ballot_sync(0xffffffffu, pred);
+        if (!(bal & 1u)) hi = lo;                      // the first candidate already does not precede
+        else if (bal & 2u) lo = hi;                    // every candidate precedes
+        else { lo = lo + 1; hi = hi - 1; }
+    }
     while (lo < hi) {
         const int64_t span = hi - lo;
         int64_t mid;

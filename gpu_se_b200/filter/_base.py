@@ -119,6 +119,8 @@ class WeightedEnsemble:
         self._mom = torch.zeros(48, dtype=torch.float64, device=dev)
         self._mom_host = torch.zeros(48, dtype=torch.float64).pin_memory()
         self._mom_valid = False
+        self._mom_full = False         # the cached moments include the second moments
+        self._want_cov = False         # a caller asked for point_covariance before: compute both in one pass
         self._seed = int(seed) if seed is not None else int(numpy.random.randint(0, 2 ** 31 - 1))
         self._step = 0
         self.last_sample_index = None
@@ -247,12 +249,21 @@ class WeightedEnsemble:
         return c, int(c[-1])
 
     # -- moments -------------------------------------------------------------------------
-    def _launch_moments(self):
+    MEAN_ONLY_KERNEL = False
+
+    def _launch_moments(self, mean_only=False):
         raise NotImplementedError
 
-    def _moments(self):
-        if not self._mom_valid:
-            self._launch_moments()
+    def _moments(self, need_cov=False):
+        """Weighted moments of the population, cached until the state changes.  point_estimate alone
+        runs the means-only kernel; once a caller has asked for point_covariance (sim_base.py:291-295
+        does both every step) both are computed in one pass."""
+        if need_cov:
+            self._want_cov = True
+        if not self._mom_valid or (need_cov and not self._mom_full):
+            full = need_cov or self._want_cov or not self.MEAN_ONLY_KERNEL
+            self._launch_moments(mean_only=not full)
+            self._mom_full = full
             self._mom[41:43].copy_(self._stats[0:2])        # M, S ride along in the same read-back
             self._mom_host.copy_(self._mom, non_blocking=True)
             torch.cuda.current_stream(self.device).synchronize()
@@ -277,8 +288,8 @@ class WeightedEnsemble:
                 t += 1
         return m
 
-    def _estimate_parts(self):
-        mom = self._moments()
+    def _estimate_parts(self, need_cov=False):
+        mom = self._moments(need_cov)
         S0, S1, S2 = mom[0], mom[1:6], self._unpack_sym(mom[6:21])
         p = mom[21:26]
         A = self._weight_prefactor(mom)
@@ -293,7 +304,7 @@ class WeightedEnsemble:
         return A * (S0 * p + S1)
 
     def _scatter_about(self, normalised):
-        mom, S0, S1, S2, p, A = self._estimate_parts()
+        mom, S0, S1, S2, p, A = self._estimate_parts(need_cov=True)
         if normalised:
             d = S1 / S0
             return (S2 / S0 - numpy.outer(d, d)), mom, 1.0 / S0

@@ -132,7 +132,7 @@ class ParallelGaussianSumUnscentedKalmanFilter(WeightedEnsemble):
     # resample(): WeightedEnsemble.resample gathers all 20 rows (gs_ukf.py:409-436)
 
     # -- estimates -----------------------------------------------------------------------
-    def _launch_moments(self):
+    def _launch_moments(self, mean_only=False):
         _lib.check(_lib.lib.gse_gsf_moments(
             self._ctx.handle, self._mean_ptr(), self._cov_ptr(), self._ld, self.N_particles, self._idx_ptr(),
             self._loglik_ptr(), self._base.data_ptr() if self._base is not None else None,

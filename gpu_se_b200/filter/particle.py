@@ -106,10 +106,12 @@ class ParallelParticleFilter(WeightedEnsemble):
     # resample(): WeightedEnsemble.resample  (particle.py:296-316)
 
     # -- estimates -----------------------------------------------------------------------
-    def _launch_moments(self):
+    MEAN_ONLY_KERNEL = True
+
+    def _launch_moments(self, mean_only=False):
         _lib.check(_lib.lib.gse_pf_moments(
             self._ctx.handle, self._state.data_ptr(), self._ld, self.N_particles, self._idx_ptr(), self._loglik_ptr(),
-            self._base.data_ptr() if self._base is not None else None, self._stats.data_ptr(),
+            self._base.data_ptr() if self._base is not None else None, self._stats.data_ptr(), int(mean_only),
             self._mom.data_ptr(), self._stream()))
 
     # point_estimate(): WeightedEnsemble.point_estimate  (particle.py:318-320)

@@ -390,16 +390,19 @@ class ShardedParticleFilter:
         return idx
 
     # -- estimates -------------------------------------------------------------------------------
-    def _global_moments(self):
+    def _global_moments(self, need_cov=True):
         loc = self.local
+        if need_cov:
+            self._want_cov = True
+        mean_only = not (need_cov or getattr(self, "_want_cov", False))
         if getattr(self, "_pending", False):
             sh = self._shards[self._parity]
             _lib.check(_lib.lib.gse_pf_moments_sharded(
                 loc._ctx.handle, ctypes.byref(sh), self._idx_global.data_ptr(), loc.N_particles, loc._loglik_ptr(),
-                loc._base.data_ptr() if loc._base is not None else None, loc._stats.data_ptr(), loc._mom.data_ptr(),
-                loc._stream()))
+                loc._base.data_ptr() if loc._base is not None else None, loc._stats.data_ptr(), int(mean_only),
+                loc._mom.data_ptr(), loc._stream()))
         else:
-            loc._launch_moments()
+            loc._launch_moments(mean_only=mean_only)
         loc._mom[41:43].copy_(loc._stats[0:2])
         allm = [torch.empty_like(loc._mom) for _ in range(self.world)]
         dist.all_gather(allm, loc._mom, group=self.group)
@@ -416,7 +419,7 @@ class ShardedParticleFilter:
         return S0, S1, S2, p, A
 
     def point_estimate(self, normalised=False):
-        S0, S1, S2, p, A = self._global_moments()
+        S0, S1, S2, p, A = self._global_moments(need_cov=False)
         return p + S1 / S0 if normalised else A * (S0 * p + S1)
 
     def covariance_matrix(self, normalised=False):

@@ -129,10 +129,11 @@ int gse_pf_update(gse_ctx* ctx, const float* x_dev, int64_t ld, int64_t n, const
  * idx[i] (or i) of x:
  * out_dev[0] = S = sum_i w_i, out_dev[1..5] = sum_i w_i (x_i - p), out_dev[6..20] = lower triangle of
  * sum_i w_i (x_i - p)(x_i - p)' with pivot p = out_dev[21..25] (written by the kernel: row 0),
- * where w_i = base_i * exp(loglik_i - stats_dev[0]).  26 doubles. */
+ * where w_i = base_i * exp(loglik_i - stats_dev[0]).  26 doubles.  mean_only != 0 skips the second
+ * moments (out_dev[6..20] untouched): point_estimate alone at a quarter of the float64 work. */
 int gse_pf_moments(gse_ctx* ctx, const float* x_dev, int64_t ld, int64_t n, const int32_t* idx_dev,
                    const float* loglik_dev, const double* base_dev, const double* stats_dev,
-                   double* out_dev, void* stream);
+                   int mean_only, double* out_dev, void* stream);
 
 /* ---- weights and systematic resampling (shared by PF and GS-UKF) ------------------------------ */
 
@@ -224,7 +225,7 @@ int gse_pf_predict_sharded(gse_ctx* ctx, const gse_shards* shards, const int32_t
                            int64_t ld_noise, void* stream);
 int gse_pf_moments_sharded(gse_ctx* ctx, const gse_shards* shards, const int32_t* idx_dev, int64_t n,
                            const float* loglik_dev, const double* base_dev, const double* stats_dev,
-                           double* out_dev, void* stream);
+                           int mean_only, double* out_dev, void* stream);
 
 /* Number of outputs i in [0, n_total) whose u_i maps at or below integer cumulative weight
  * `bound` of `total`, i.e. #{ i : fl(fl(bound)/fl(total)) >= u_i }: host helper used by the sharded
