@@ -101,6 +101,7 @@ struct gse_ctx {
     uint64_t* tile_inc;       // scan: per-tile inclusive prefix
     unsigned int* tile_flag;  // scan: (epoch << 2) | state
     int64_t* part;            // merge-path split points
+    int64_t* range;           // [k_lo, k_hi): sources that interleave with a shard's outputs
     unsigned int scan_epoch;
     int64_t max_blocks;
     int64_t max_tiles;

@@ -289,6 +289,7 @@ struct ResampleArgs {
     const uint64_t* cumsum;    // single segment: the local cumulative weights
     const uint64_t* offtot;    // [s] offset of segment s's cumulative weights, [nseg] the global total
     // segmented sources (sharded run, peer memory): segment s holds global rows [seg_row[s], seg_row[s+1])
+    const int64_t* range;      // device [k_lo, k_hi): the sources that interleave with the outputs (NULL = all)
     int nseg;
     int64_t seg_row[GSE_MAX_SHARDS + 1];
     const uint64_t* seg_cumsum[GSE_MAX_SHARDS];
@@ -335,39 +336,32 @@ __device__ __forceinline__ bool precedes(const ResampleArgs& a, uint64_t c, uint
     return __ddiv_rn(__ull2double_rn(c + off), Td) < sample_u(a, di);
 }
 
+// Warp-cooperative search for the smallest s in [lo, hi] with NOT precedes(C[s], output j(s)), where the
+// predicate holds on a prefix; j(s) = fixed_out when that is >= 0 (split for one output), otherwise
+// diag - 1 - (s - s_base) (merge-path diagonal).  32-ary: ~5 rounds of dependent loads at 2^24.
 template <bool SEG>
-__global__ void __launch_bounds__(128)
-k_resample_partition(const ResampleArgs a, int64_t* __restrict__ part, int64_t nparts) {
-    const int lane = threadIdx.x & 31;
-    const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (b > nparts) return;
-    const uint64_t off0 = SEG ? 0ull : a.offtot[0];
+__device__ __forceinline__ int64_t warp_split(const ResampleArgs& a, int64_t lo, int64_t hi, int64_t diag,
+                                              int64_t s_base, int64_t fixed_out, uint64_t off0, double Td, int lane) {
     const uint64_t off = 0;                                     // source_weight() returns global weights
-    const double Td = __ull2double_rn(a.offtot[SEG ? a.nseg : 1]);
-    int64_t diag = b * RS_WORK;
-    const int64_t total = a.n_src + a.n_out;
-    if (diag > total) diag = total;
-    int64_t lo = diag > a.n_out ? diag - a.n_out : 0;
-    int64_t hi = diag < a.n_src ? diag : a.n_src;
-    // smallest s in [lo, hi] with NOT precedes(C[s], output diag - 1 - s); true on a prefix
+#define GSE_OUT_OF(mid) (double)(a.out0 + (fixed_out >= 0 ? fixed_out : diag - 1 - ((mid) - s_base)))
     if (SEG) {
         // the last row of shard t - 1 carries exactly the offset of shard t: probe the shard boundaries
         // with the offsets alone, so that the search below stays inside one shard's array
         for (int t = 1; t < a.nseg; ++t) {
             const int64_t mid = a.seg_row[t] - 1;
             if (mid < lo || mid >= hi) continue;
-            const double di = (double)(a.out0 + (diag - 1 - mid));
+            const double di = GSE_OUT_OF(mid);
             if (precedes(a, a.offtot[t], output_qlo(a, di, off, Td), di, off, Td)) lo = mid + 1; else hi = mid;
         }
     }
-    // end points first (one round of loads): diagonals that lie entirely among sources without offspring
+    // end points first (one round of loads): ranges that lie entirely among sources without offspring
     // -- the other shards' rows in a sharded run, the tail of a degenerate weight vector -- finish here
     if (lo < hi) {
         const int64_t mid = lane == 0 ? lo : hi - 1;
         bool pred = false;
         if (lane < 2) {
             const uint64_t c = source_weight<SEG>(a, mid, off0);
-            const double di = (double)(a.out0 + (diag - 1 - mid));
+            const double di = GSE_OUT_OF(mid);
             pred = precedes(a, c, output_qlo(a, di, off, Td), di, off, Td);
         }
         const unsigned int bal = __ballot_sync(0xffffffffu, pred);
@@ -390,7 +384,7 @@ k_resample_partition(const ResampleArgs a, int64_t* __restrict__ part, int64_t n
         bool pred = false;
         if (active) {
             const uint64_t c = source_weight<SEG>(a, mid, off0);
-            const double di = (double)(a.out0 + (diag - 1 - mid));
+            const double di = GSE_OUT_OF(mid);
             pred = precedes(a, c, output_qlo(a, di, off, Td), di, off, Td);
         }
         const unsigned int bal = __ballot_sync(0xffffffffu, pred);
@@ -403,7 +397,43 @@ k_resample_partition(const ResampleArgs a, int64_t* __restrict__ part, int64_t n
         if (ntrue < nact) hi = mid_first_false;
         else if (span <= 32) hi = lo;                               // every candidate was true
     }
-    if (lane == 0) part[b] = lo;
+#undef GSE_OUT_OF
+    return lo;
+}
+
+// Sharded run: only the sources between the ancestor of this shard's first output and the ancestor of
+// its last output interleave with its outputs.  Two warps find that range [k_lo, k_hi) so that the
+// partition and the search below cost what they cost on one GPU, whatever the number of shards.
+template <bool SEG>
+__global__ void __launch_bounds__(64)
+k_resample_source_range(const ResampleArgs a, int64_t* __restrict__ range) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint64_t off0 = SEG ? 0ull : a.offtot[0];
+    const double Td = __ull2double_rn(a.offtot[SEG ? a.nseg : 1]);
+    const int64_t s = warp_split<SEG>(a, 0, a.n_src, 0, 0, w == 0 ? 0 : a.n_out - 1, off0, Td, lane);
+    if (lane == 0) range[w] = (w == 0) ? s : min(s + 1, a.n_src);
+}
+
+template <bool SEG>
+__global__ void __launch_bounds__(128)
+k_resample_partition(const ResampleArgs a, int64_t* __restrict__ part, int64_t nparts) {
+    const int lane = threadIdx.x & 31;
+    const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (b > nparts) return;
+    const int64_t k_lo = a.range ? a.range[0] : 0;
+    const int64_t span = a.range ? a.range[1] - k_lo : a.n_src;
+    const uint64_t off0 = SEG ? 0ull : a.offtot[0];
+    const double Td = __ull2double_rn(a.offtot[SEG ? a.nseg : 1]);
+    int64_t diag = b * RS_WORK;
+    const int64_t total = span + a.n_out;
+    if (diag >= total) {                                         // beyond the merged sequence: an empty window
+        if (lane == 0) part[b] = k_lo + span;
+        return;
+    }
+    const int64_t lo = k_lo + (diag > a.n_out ? diag - a.n_out : 0);
+    const int64_t hi = k_lo + (diag < span ? diag : span);
+    const int64_t s = warp_split<SEG>(a, lo, hi, diag, k_lo, -1, off0, Td, lane);
+    if (lane == 0) part[b] = s;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -441,11 +471,13 @@ k_resample_search(const ResampleArgs a, const int64_t* __restrict__ part, int32_
     __shared__ int s_warp[RS_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int64_t b = blockIdx.x;
-    const int64_t total = a.n_src + a.n_out;
+    const int64_t k_lo = a.range ? a.range[0] : 0;
+    const int64_t total = (a.range ? a.range[1] - k_lo : a.n_src) + a.n_out;
     int64_t d0 = b * RS_WORK, d1 = d0 + RS_WORK;
+    if (d0 >= total) return;                               // beyond the sources that matter to these outputs
     if (d1 > total) d1 = total;
     const int64_t a0 = part[b], a1 = part[b + 1];
-    const int64_t o0 = d0 - a0, o1 = d1 - a1;
+    const int64_t o0 = d0 - (a0 - k_lo), o1 = d1 - (a1 - k_lo);
     if (o1 <= o0) return;                                  // a stretch of sources with no offspring
     const int ns = (int)(a1 - a0);
     const int no = (int)(o1 - o0);
@@ -575,8 +607,13 @@ k_resample_search(const ResampleArgs a, const int64_t* __restrict__ part, int32_
 static int launch_search(gse_ctx* ctx, const ResampleArgs& a, int64_t nparts, int32_t* idx_out_dev, bool seg,
                          cudaStream_t s) {
     const unsigned pgrid = (unsigned)gse_div_up((nparts + 1) * 32, 128);
-    if (seg) k_resample_partition<true><<<pgrid, 128, 0, s>>>(a, ctx->part, nparts);
-    else k_resample_partition<false><<<pgrid, 128, 0, s>>>(a, ctx->part, nparts);
+    if (seg) {
+        k_resample_source_range<true><<<1, 64, 0, s>>>(a, ctx->range);
+        GSE_CHECK_LAUNCH(ctx);
+        k_resample_partition<true><<<pgrid, 128, 0, s>>>(a, ctx->part, nparts);
+    } else {
+        k_resample_partition<false><<<pgrid, 128, 0, s>>>(a, ctx->part, nparts);
+    }
     GSE_CHECK_LAUNCH(ctx);
     const unsigned g = (unsigned)nparts;
     if (seg) {
@@ -622,6 +659,7 @@ extern "C" int gse_resample_search_sharded(gse_ctx* ctx, const gse_shards* sh, d
         a.seg_cumsum[t] = sh->cumsum_dev[t];
     }
     fill_common(a, r, n_total, out0, n_out);
+    a.range = ctx->range;
     const int64_t nparts = gse_div_up(a.n_src + n_out, RS_WORK);
     GSE_REQUIRE(nparts + 1 <= ctx->max_tiles + 2, "workspace too small (create the context with n_max >= global rows)");
     return launch_search(ctx, a, nparts, idx_out_dev, true, (cudaStream_t)stream);
