@@ -30,6 +30,7 @@ class gse_mixture(ctypes.Structure):
 
 
 GSE_MAX_SHARDS, GSE_IPC_HANDLE_BYTES = 8, 64
+GSE_MAILBOX_BYTES = 2 * GSE_MAX_SHARDS * 64
 
 
 class gse_shards(ctypes.Structure):
@@ -68,6 +69,8 @@ SIGNATURES = {
     "gse_pf_predict_sharded": (c_int, [c_vp, c_shards_p, c_vp, c_vp, c_i64, c_i64, c_dbl_p, c_dbl, c_int, c_u64, c_u64,
                                        c_i64, c_vp, c_i64, c_vp]),
     "gse_pf_moments_sharded": (c_int, [c_vp, c_shards_p, c_vp, c_i64, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]),
+    "gse_peer_allgather_stats": (c_int, [c_vp, ctypes.POINTER(c_vp), c_int, c_int, ctypes.c_uint, c_vp, c_vp]),
+    "gse_peer_allgather_totals": (c_int, [c_vp, ctypes.POINTER(c_vp), c_int, c_int, ctypes.c_uint, c_vp, c_vp, c_vp]),
     "gse_merge_stats": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp]),
     "gse_count_outputs_below": (c_i64, [c_u64, c_u64, c_dbl, c_i64]),
     "gse_threshold_u64": (c_u64, [c_dbl, c_u64]),

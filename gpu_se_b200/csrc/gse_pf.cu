@@ -317,6 +317,107 @@ extern "C" int gse_loglik_max(gse_ctx* ctx, const float* loglik_dev, int64_t n, 
     return GSE_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// All-gather of one small record per shard over peer-mapped mailboxes: the collective and the
+// reduction that consumes it are ONE single-warp kernel, no NCCL launch, no host involvement.
+// Lane t writes this rank's record and the epoch into slot [rank] of peer t's mailbox (stores over
+// NVLink, payload fenced before the flag), then spins on slot [t] of its own mailbox until peer t's
+// record of the same epoch has landed.  Slots are double-buffered by epoch parity: a peer can only
+// reuse a slot two exchanges later, which needs this rank's next flag, written after it has read.
+// ------------------------------------------------------------------------------------------------
+#define MBOX_SLOT_BYTES 64
+struct MailboxTable {
+    unsigned char* box[GSE_MAX_SHARDS];
+};
+
+__device__ __forceinline__ void mbox_exchange(const MailboxTable& mb, int rank, int nshards, unsigned int epoch,
+                                              unsigned long long w0, unsigned long long w1, int lane,
+                                              unsigned long long& r0, unsigned long long& r1) {
+    r0 = 0; r1 = 0;
+    if (lane < nshards) {
+        const size_t par = (size_t)(epoch & 1u) * GSE_MAX_SHARDS;
+        volatile unsigned long long* dst = (volatile unsigned long long*)(mb.box[lane] + (par + rank) * MBOX_SLOT_BYTES);
+        dst[0] = w0;
+        dst[1] = w1;
+        __threadfence_system();
+        *(volatile unsigned int*)(dst + 4) = epoch;
+        volatile unsigned long long* src = (volatile unsigned long long*)(mb.box[rank] + (par + lane) * MBOX_SLOT_BYTES);
+        while (*(volatile unsigned int*)(src + 4) != epoch) __nanosleep(40);
+        __threadfence_system();
+        r0 = src[0];
+        r1 = src[1];
+    }
+}
+
+// records (M_s, S_s) -> stats[0..1] = (max M_s, sum S_s exp(M_s - M)), merged in shard order
+__global__ void __launch_bounds__(32)
+k_mbox_stats(const __grid_constant__ MailboxTable mb, int rank, int nshards, unsigned int epoch, double* stats) {
+    const int lane = threadIdx.x;
+    unsigned long long r0, r1;
+    mbox_exchange(mb, rank, nshards, epoch, (unsigned long long)__double_as_longlong(stats[0]),
+                  (unsigned long long)__double_as_longlong(stats[1]), lane, r0, r1);
+    const double m_s = lane < nshards ? __longlong_as_double((long long)r0) : -INFINITY;
+    const double s_s = lane < nshards ? __longlong_as_double((long long)r1) : 0.0;
+    double M = m_s;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) M = fmax(M, __shfl_xor_sync(0xffffffffu, M, o));
+    const double term = (m_s > -INFINITY) ? s_s * exp(m_s - M) : 0.0;
+    double S = 0.0;
+    for (int t = 0; t < nshards; ++t) S += __shfl_sync(0xffffffffu, term, t);      // fixed (shard) order
+    if (lane == 0) { stats[0] = M; stats[1] = S; }
+}
+
+// records T_s (uint64) -> offsets[0..nshards] = exclusive prefix of the shard totals, total last
+__global__ void __launch_bounds__(32)
+k_mbox_offsets(const __grid_constant__ MailboxTable mb, int rank, int nshards, unsigned int epoch,
+               const uint64_t* __restrict__ total, uint64_t* __restrict__ offsets) {
+    const int lane = threadIdx.x;
+    unsigned long long r0, r1;
+    mbox_exchange(mb, rank, nshards, epoch, (unsigned long long)total[0], 0ull, lane, r0, r1);
+    unsigned long long incl = r0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane < nshards) offsets[lane + 1] = incl;
+    if (lane == 0) offsets[0] = 0;
+}
+
+static int build_mailboxes(void* const boxes[GSE_MAX_SHARDS], int rank, int nshards, MailboxTable* mb) {
+    GSE_REQUIRE(boxes != NULL && nshards >= 1 && nshards <= GSE_MAX_SHARDS && rank >= 0 && rank < nshards,
+                "bad mailbox arguments");
+    memset(mb, 0, sizeof(*mb));
+    for (int t = 0; t < nshards; ++t) {
+        GSE_REQUIRE(boxes[t] != NULL, "mailbox pointer is NULL");
+        mb->box[t] = (unsigned char*)boxes[t];
+    }
+    return GSE_OK;
+}
+
+extern "C" int gse_peer_allgather_stats(gse_ctx* ctx, void* const mailboxes[GSE_MAX_SHARDS], int rank, int nshards,
+                                        unsigned int epoch, double* stats_dev, void* stream) {
+    GSE_REQUIRE(ctx != NULL && stats_dev != NULL && epoch != 0, "bad arguments");
+    MailboxTable mb;
+    int rc = build_mailboxes(mailboxes, rank, nshards, &mb);
+    if (rc) return rc;
+    k_mbox_stats<<<1, 32, 0, (cudaStream_t)stream>>>(mb, rank, nshards, epoch, stats_dev);
+    GSE_CHECK_LAUNCH(ctx);
+    return GSE_OK;
+}
+
+extern "C" int gse_peer_allgather_totals(gse_ctx* ctx, void* const mailboxes[GSE_MAX_SHARDS], int rank, int nshards,
+                                         unsigned int epoch, const uint64_t* total_dev, uint64_t* offsets_dev,
+                                         void* stream) {
+    GSE_REQUIRE(ctx != NULL && total_dev != NULL && offsets_dev != NULL && epoch != 0, "bad arguments");
+    MailboxTable mb;
+    int rc = build_mailboxes(mailboxes, rank, nshards, &mb);
+    if (rc) return rc;
+    k_mbox_offsets<<<1, 32, 0, (cudaStream_t)stream>>>(mb, rank, nshards, epoch, total_dev, offsets_dev);
+    GSE_CHECK_LAUNCH(ctx);
+    return GSE_OK;
+}
+
 // Sharded run: combine the per-shard (M_s, S_s) pairs (all-gathered on the stream) into the global
 // stats[0] = M = max_s M_s, stats[1] = S = sum_s S_s exp(M_s - M), in shard order.
 __global__ void k_merge_stats(const double* __restrict__ pairs, int nshards, double* __restrict__ stats) {

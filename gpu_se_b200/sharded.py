@@ -175,19 +175,26 @@ class ShardedParticleFilter:
         loc = self.local
         if self.N_particles > 2 ** 31 - 1:
             raise ValueError("peer exchange indexes global rows with int32")
-        mine = tuple(loc._peer_bufs[k].handle for k in ("state", "state_alt", "cumsum")) + (loc._ld,)
+        self._mailbox = _peer.PeerBuffer(self.device, _lib.GSE_MAILBOX_BYTES)
+        mine = tuple(loc._peer_bufs[k].handle for k in ("state", "state_alt", "cumsum")) + (loc._ld,
+                                                                                               self._mailbox.handle)
         everyone = [None] * self.world
         dist.all_gather_object(everyone, mine, group=self.group)
         self._mappings = []
         self._peer_ptr = []                  # per rank: (state, state_alt, cumsum) device pointers, ld
-        for s, (h0, h1, hc, ld) in enumerate(everyone):
+        boxes = (ctypes.c_void_p * _lib.GSE_MAX_SHARDS)()
+        for s, (h0, h1, hc, ld, hm) in enumerate(everyone):
             if s == self.rank:
                 self._peer_ptr.append((loc._peer_bufs["state"].ptr, loc._peer_bufs["state_alt"].ptr,
                                        loc._peer_bufs["cumsum"].ptr, ld))
+                boxes[s] = self._mailbox.ptr
             else:
-                maps = [_peer.PeerMapping(self.device, h) for h in (h0, h1, hc)]
+                maps = [_peer.PeerMapping(self.device, h) for h in (h0, h1, hc, hm)]
                 self._mappings += maps
                 self._peer_ptr.append((maps[0].ptr, maps[1].ptr, maps[2].ptr, ld))
+                boxes[s] = maps[3].ptr
+        self._boxes = boxes
+        self._epoch = 0                      # mailbox exchanges so far: identical on every rank
         self._parity = 0                     # which of (state, state_alt) is current -- flips on every rank together
         self._offsets = torch.zeros(self.world + 1, dtype=torch.int64, device=self.device)
         self._totals = torch.zeros(self.world, dtype=torch.int64, device=self.device)
@@ -223,8 +230,12 @@ class ShardedParticleFilter:
         loc._scan()                                               # local cumsum, T_s -> _offtot[1]
         if self._stage_hook is not None:
             self._stage_hook("scan")
-        dist.all_gather_into_tensor(self._totals, loc._offtot[1:2], group=self.group)
-        torch.cumsum(self._totals, 0, out=self._offsets[1:])      # offsets[0] stays 0; offsets[G] = total
+        # shard totals -> exclusive offsets + global total, on the device: one single-warp kernel that
+        # all-gathers through the peer mailboxes (gse_peer_allgather_totals)
+        self._epoch += 1
+        _lib.check(_lib.lib.gse_peer_allgather_totals(loc._ctx.handle, self._boxes, self.rank, self.world, self._epoch,
+                                                      loc._offtot.data_ptr() + 8, self._offsets.data_ptr(),
+                                                      loc._stream()))
         if self._stage_hook is not None:
             self._stage_hook("offsets")
         sh = self._shards[self._parity]
@@ -296,6 +307,11 @@ class ShardedParticleFilter:
         """Global (M, S) from the shards' (M_s, S_s): one all-gather of a pair + one tiny kernel."""
         loc = self.local
         if self.world == 1:
+            return
+        if self.exchange == "peer":
+            self._epoch += 1
+            _lib.check(_lib.lib.gse_peer_allgather_stats(loc._ctx.handle, self._boxes, self.rank, self.world,
+                                                         self._epoch, loc._stats.data_ptr(), loc._stream()))
             return
         if not hasattr(self, "_stat_pairs"):
             self._stat_pairs = torch.zeros(2 * self.world, dtype=torch.float64, device=self.device)

@@ -212,6 +212,21 @@ int gse_resample_search_sharded(gse_ctx* ctx, const gse_shards* shards, double r
 int gse_gather_rows_sharded(gse_ctx* ctx, const gse_shards* shards, const int32_t* idx_dev,
                             int64_t n_out, float* dst_dev, int64_t ld_dst, int ncols, void* stream);
 
+/* All-gather of one small per-shard record over peer-mapped mailboxes, fused with the reduction
+ * that consumes it: ONE single-warp kernel per exchange, no NCCL launch, nothing on the host.
+ * mailboxes[t] is shard t's mailbox (GSE_MAILBOX_BYTES of gse_peer_alloc memory, zero at start;
+ * the caller's own for t == rank, gse_peer_open mappings otherwise).  `epoch` must be the same on
+ * every rank, non-zero, and increase by one with every exchange (of either kind) on a mailbox set.
+ *   _stats : in/out stats_dev[0..1] = this shard's (M_s, S_s) -> (max_s M_s, sum_s S_s exp(M_s - M))
+ *   _totals: total_dev[0] = this shard's total -> offsets_dev[0..nshards] (exclusive prefix, total last)
+ * Every rank of the population must enqueue the same exchanges in the same order. */
+#define GSE_MAILBOX_BYTES (2 * GSE_MAX_SHARDS * 64)
+int gse_peer_allgather_stats(gse_ctx* ctx, void* const mailboxes[GSE_MAX_SHARDS], int rank, int nshards,
+                             unsigned int epoch, double* stats_dev, void* stream);
+int gse_peer_allgather_totals(gse_ctx* ctx, void* const mailboxes[GSE_MAX_SHARDS], int rank, int nshards,
+                              unsigned int epoch, const uint64_t* total_dev, uint64_t* offsets_dev,
+                              void* stream);
+
 /* stats_dev[0..1] = (max_s M_s, sum_s S_s exp(M_s - M)) from the nshards all-gathered pairs
  * pairs_dev[2 s .. 2 s + 1] = (M_s, S_s) written by each shard's update kernel. */
 int gse_merge_stats(gse_ctx* ctx, const double* pairs_dev, int nshards, double* stats_dev, void* stream);
