@@ -30,6 +30,18 @@ The reference has no multi-GPU path; this is the north-s
   Needs one device-to-host read of the G totals per resample; kept for GPUs without peer
   access and as the cross-check of the peer path.
 
+Ordering between ranks in peer mode (why no extra barrier is needed).  Every rank owns two state
+buffers X (current) and Y.  A step is: predict (reads the peers' X through the pending index, writes
+its own Y; Y becomes current) -> update -> exchange (a) -> scan (writes the local cumulative
+weights) -> exchange (b) -> search (reads the peers' cumulative weights).  A rank leaves an
+exchange only after every peer has written that exchange's flag, and a peer's flag is written by
+a kernel its stream runs after everything it enqueued before.  Hence: (1) the peers' cumulative
+weights are complete before the search reads them (their scan precedes their flag (b));
+(2) the peers' X is final before predict reads it (written one step earlier) and is next
+overwritten by their predict two resamples later, after exchanges that this rank only joins once
+its own predict has finished; (3) a rank's cumulative weights are rewritten by its next scan,
+which follows exchange (a) of the next step, which every peer joins after its search.
+
 ``plan_resample`` and ``exchange_columns`` are pure host / ``torch.distributed`` code and run on
 CPU tensors over ``gloo`` as well (tests/test_sharded_cpu.py).
 """
