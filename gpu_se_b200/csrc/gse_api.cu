@@ -203,7 +203,7 @@ extern "C" int gse_ctx_create(int device, int model_id, int64_t n_max, const gse
     const size_t o_inc = off; off = align_up(off + sizeof(uint64_t) * c->max_tiles, 256);
     const size_t o_flag = off; off = align_up(off + sizeof(unsigned int) * c->max_tiles, 256);
     const size_t o_part = off; off = align_up(off + sizeof(int64_t) * (c->max_tiles + 2), 256);
-    const size_t o_range = off; off = align_up(off + sizeof(int64_t) * 2, 256);
+    const size_t o_range = off; off = align_up(off + sizeof(int64_t) * 8, 256);    // [0..1] range, [4] 1/T
     c->ws_bytes = off;
     cudaError_t e = cudaMalloc(&c->ws, c->ws_bytes);
     if (e != cudaSuccess) {

@@ -128,10 +128,12 @@ k_gsf_predict(const float* mean_src, const float* cov_src, int64_t lds, const in
         }
     }
     // numpy.average divides by the sum of the weights (:101)
-    const double wsum = (double)W_SIGMA_0 + 10.0 * (double)W_SIGMA_I;
+    // (div.rn.f64 issues at 1 lane/clk/SM on B200 -- tools/ubench_xu.cu -- so the constant divisor is inverted
+    // at compile time; the quotient differs from numpy's by at most 1 ulp of float64 before the float32 store)
+    constexpr double inv_wsum = 1.0 / ((double)W_SIGMA_0 + 10.0 * (double)W_SIGMA_I);
     float mn[5];
 #pragma unroll
-    for (int j = 0; j < 5; ++j) mn[j] = (float)(msum[j] / wsum);
+    for (int j = 0; j < 5; ++j) mn[j] = (float)(msum[j] * inv_wsum);
     float C[15];
 #pragma unroll
     for (int j = 0; j < 15; ++j) C[j] = 0.0f;
@@ -199,7 +201,7 @@ k_gsf_update(float* __restrict__ mean, float* __restrict__ cov, int64_t ld, int6
 #pragma unroll
         for (int j = 0; j < 15; ++j) P[j] = cov[j * ld + i];
         cholesky5_retry(P, L);
-        const double wsum = (double)W_SIGMA_0 + 10.0 * (double)W_SIGMA_I;
+        constexpr double inv_wsum = 1.0 / ((double)W_SIGMA_0 + 10.0 * (double)W_SIGMA_I);
         // pass 1: eta mean (:126)
         double eta[GSE_NSIGMA][2];
         double em0 = 0.0, em1 = 0.0;
@@ -213,8 +215,8 @@ k_gsf_update(float* __restrict__ mean, float* __restrict__ cov, int64_t ld, int6
             em0 = fma(w, eta[s][0], em0);
             em1 = fma(w, eta[s][1], em1);
         }
-        em0 /= wsum;
-        em1 /= wsum;
+        em0 *= inv_wsum;
+        em1 *= inv_wsum;
         // pass 2: P_xy (5x2), P_yy (2x2)  (:127-131)
         double pxy[5][2], pyy00 = 0.0, pyy01 = 0.0, pyy11 = 0.0;
 #pragma unroll
@@ -237,7 +239,8 @@ k_gsf_update(float* __restrict__ mean, float* __restrict__ cov, int64_t ld, int6
         }
         // K = P_xy P_yy^-1 (:132-133): closed-form 2x2 inverse
         const double det = pyy00 * pyy11 - pyy01 * pyy01;
-        const double i00 = pyy11 / det, i01 = -pyy01 / det, i11 = pyy00 / det;
+        const double inv_det = 1.0 / det;                               // one division, three products
+        const double i00 = pyy11 * inv_det, i01 = -pyy01 * inv_det, i11 = pyy00 * inv_det;
         double K[5][2];
 #pragma unroll
         for (int a = 0; a < 5; ++a) {

@@ -39,8 +39,12 @@ __device__ __forceinline__ int quantisation_exponent(double S) {
 
 // q = rint(exp(l - M) * 2^sexp): the one expression both passes (K3a, K3b) evaluate, with explicit
 // round-to-nearest operations so that no contraction can make them differ
+// (SMALL = convert through cvt.rni.u32.f32 when the scale is <= 2^31: measured slower than the plain
+// 64-bit conversion, kept only as the documented experiment)
+template <bool SMALL>
 __device__ __forceinline__ uint64_t quantise1(float l, float M, float scale) {
-    return __float2ull_rn(__fmul_rn(__expf(__fsub_rn(l, M)), scale));
+    const float v = __fmul_rn(__expf(__fsub_rn(l, M)), scale);
+    return SMALL ? (uint64_t)__float2uint_rn(v) : __float2ull_rn(v);
 }
 
 // Quantised weights of the 16 consecutive rows owned by this thread.
@@ -152,11 +156,11 @@ k_weight_tile_sums(const float* __restrict__ loglik, const double* __restrict__ 
 #pragma unroll 4
             for (; row < r1_full; row += 128) {
                 const float4 l = ld_stream4(loglik + row);
-                sum += quantise1(l.x, M, scale) + quantise1(l.y, M, scale) + quantise1(l.z, M, scale) +
-                       quantise1(l.w, M, scale);
+                sum += quantise1<false>(l.x, M, scale) + quantise1<false>(l.y, M, scale) +
+                       quantise1<false>(l.z, M, scale) + quantise1<false>(l.w, M, scale);
             }
             for (int r = 0; r < 4; ++r)
-                if (row + r < r1) sum += quantise1(loglik[row + r], M, scale);
+                if (row + r < r1) sum += quantise1<false>(loglik[row + r], M, scale);
         } else {
             for (int64_t t = t0; t < t1; ++t) {
                 const int64_t row0 = t * WTILE_ROWS + (int64_t)lane * TILE_ITEMS;
@@ -290,6 +294,7 @@ struct ResampleArgs {
     const uint64_t* offtot;    // [s] offset of segment s's cumulative weights, [nseg] the global total
     // segmented sources (sharded run, peer memory): segment s holds global rows [seg_row[s], seg_row[s+1])
     const int64_t* range;      // device [k_lo, k_hi): the sources that interleave with the outputs (NULL = all)
+    double* consts;            // device scratch: [0] = 1 / T (written by the partition kernel)
     int nseg;
     int64_t seg_row[GSE_MAX_SHARDS + 1];
     const uint64_t* seg_cumsum[GSE_MAX_SHARDS];
@@ -504,7 +509,8 @@ k_resample_search(const ResampleArgs a, const int64_t* __restrict__ part, int32_
     // of u_i and g_k, which moves the boundary by less than 3 N 2^-53; t below is within another
     // 3 N 2^-53 of t*.  So when t is further than eps = N 2^-48 from an integer the rank is
     // floor(t) + 1, no division needed; otherwise (ties, ~2 eps of all sources) settle it exactly.
-    const double inv_T = 1.0 / Td;
+    const double inv_T = 1.0 / Td;     // (hoisting this division into the partition kernel measured 8 us SLOWER:
+                                       //  it overlaps the window's load latency here, a dependent load does not)
     const double eps = a.n_total * 3.5527136788005009e-15;         // N * 2^-48
     const double one_m_eps = 1.0 - eps;
     const double one_m_base = 1.0 - dbase;
@@ -627,7 +633,8 @@ static int launch_search(gse_ctx* ctx, const ResampleArgs& a, int64_t nparts, in
     return GSE_OK;
 }
 
-static void fill_common(ResampleArgs& a, double r, int64_t n_total, int64_t out0, int64_t n_out) {
+static void fill_common(gse_ctx* ctx, ResampleArgs& a, double r, int64_t n_total, int64_t out0, int64_t n_out) {
+    a.consts = (double*)(ctx->range + 4);
     a.n_out = n_out;
     a.out0 = out0;
     a.r = r;
@@ -658,7 +665,7 @@ extern "C" int gse_resample_search_sharded(gse_ctx* ctx, const gse_shards* sh, d
         GSE_REQUIRE(sh->cumsum_dev[t] != NULL && sh->rows[t + 1] > sh->rows[t], "bad shard entry");
         a.seg_cumsum[t] = sh->cumsum_dev[t];
     }
-    fill_common(a, r, n_total, out0, n_out);
+    fill_common(ctx, a, r, n_total, out0, n_out);
     a.range = ctx->range;
     const int64_t nparts = gse_div_up(a.n_src + n_out, RS_WORK);
     GSE_REQUIRE(nparts + 1 <= ctx->max_tiles + 2, "workspace too small (create the context with n_max >= global rows)");
@@ -681,7 +688,7 @@ extern "C" int gse_resample_search(gse_ctx* ctx, const uint64_t* cumsum_dev, int
     a.offtot = offtot_dev;
     a.n_src = n_src;
     a.nseg = 1;
-    fill_common(a, r, n_total, out0, n_out);
+    fill_common(ctx, a, r, n_total, out0, n_out);
     const int64_t nparts = gse_div_up(n_src + n_out, RS_WORK);
     GSE_REQUIRE(nparts + 1 <= ctx->max_tiles + 2, "workspace too small");
     cudaStream_t s = (cudaStream_t)stream;
