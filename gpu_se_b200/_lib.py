@@ -9,7 +9,7 @@ import os
 
 GSE_NX, GSE_NU, GSE_NY, GSE_NSIGMA, GSE_NCOV, GSE_MAX_ND = 5, 2, 2, 11, 15, 8
 GSE_MODEL_BIOREACTOR = 1
-GSE_ABI_VERSION = 3
+GSE_ABI_VERSION = 4
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgse_b200.so")
 
@@ -37,6 +37,11 @@ class gse_shards(ctypes.Structure):
     _fields_ = [("nshards", ctypes.c_int32), ("rows", ctypes.c_int64 * (GSE_MAX_SHARDS + 1)),
                 ("cumsum_dev", ctypes.c_void_p * GSE_MAX_SHARDS), ("state_dev", ctypes.c_void_p * GSE_MAX_SHARDS),
                 ("ld", ctypes.c_int64 * GSE_MAX_SHARDS), ("offsets_dev", ctypes.c_void_p)]
+
+
+class gse_step_params(ctypes.Structure):
+    _fields_ = [("u", ctypes.c_double * 2), ("dt", ctypes.c_double), ("z", ctypes.c_double * 2),
+                ("r", ctypes.c_double), ("step", ctypes.c_uint64), ("reserved", ctypes.c_uint64)]
 
 
 c_mix_p = ctypes.POINTER(gse_mixture)
@@ -71,6 +76,8 @@ SIGNATURES = {
     "gse_pf_moments_sharded": (c_int, [c_vp, c_shards_p, c_vp, c_i64, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]),
     "gse_peer_allgather_stats": (c_int, [c_vp, ctypes.POINTER(c_vp), c_int, c_int, ctypes.c_uint, c_vp, c_vp]),
     "gse_peer_allgather_totals": (c_int, [c_vp, ctypes.POINTER(c_vp), c_int, c_int, ctypes.c_uint, c_vp, c_vp, c_vp]),
+    "gse_ctx_upload_step_params": (c_int, [c_vp, ctypes.POINTER(gse_step_params), c_vp]),
+    "gse_ctx_use_step_params": (c_int, [c_vp, c_int]),
     "gse_merge_stats": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp]),
     "gse_count_outputs_below": (c_i64, [c_u64, c_u64, c_dbl, c_i64]),
     "gse_threshold_u64": (c_u64, [c_dbl, c_u64]),

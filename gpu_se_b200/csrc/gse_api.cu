@@ -237,6 +237,11 @@ extern "C" int gse_ctx_destroy(gse_ctx* ctx) {
     if (!ctx) return GSE_OK;
     cudaSetDevice(ctx->device);
     if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->params_block) {
+        cudaFree(ctx->params_block);
+        cudaFreeHost(ctx->params_ring);
+        for (int q = 0; q < 4; ++q) cudaEventDestroy(ctx->params_event[q]);
+    }
     free(ctx);
     return GSE_OK;
 }
@@ -281,6 +286,36 @@ extern "C" int gse_peer_close(int device, void* ptr) {
     if (!ptr) return GSE_OK;
     GSE_CHECK_CUDA(cudaSetDevice(device));
     GSE_CHECK_CUDA(cudaIpcCloseMemHandle(ptr));
+    return GSE_OK;
+}
+
+extern "C" int gse_ctx_upload_step_params(gse_ctx* ctx, const gse_step_params* values, void* stream) {
+    GSE_REQUIRE(ctx != NULL && values != NULL, "ctx / values is NULL");
+    if (!ctx->params_block) {
+        GSE_CHECK_CUDA(cudaSetDevice(ctx->device));
+        GSE_CHECK_CUDA(cudaMalloc((void**)&ctx->params_block, sizeof(gse_step_params)));
+        GSE_CHECK_CUDA(cudaHostAlloc((void**)&ctx->params_ring, sizeof(gse_step_params) * GSE_PARAM_RING, cudaHostAllocDefault));
+        for (int q = 0; q < 4; ++q) GSE_CHECK_CUDA(cudaEventCreateWithFlags(&ctx->params_event[q], cudaEventDisableTiming));
+        ctx->params_pos = 0;
+    }
+    const int pos = ctx->params_pos;
+    const int quarter = GSE_PARAM_RING / 4;
+    if (pos % quarter == 0) {
+        // entering a quarter: every copy queued from it a lap ago must have run (a host far ahead of the GPU)
+        GSE_CHECK_CUDA(cudaEventSynchronize(ctx->params_event[pos / quarter]));
+    }
+    ctx->params_ring[pos] = *values;
+    GSE_CHECK_CUDA(cudaMemcpyAsync(ctx->params_block, ctx->params_ring + pos, sizeof(gse_step_params),
+                                   cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    if ((pos + 1) % quarter == 0) GSE_CHECK_CUDA(cudaEventRecord(ctx->params_event[pos / quarter], (cudaStream_t)stream));
+    ctx->params_pos = (pos + 1) % GSE_PARAM_RING;
+    return GSE_OK;
+}
+
+extern "C" int gse_ctx_use_step_params(gse_ctx* ctx, int enable) {
+    GSE_REQUIRE(ctx != NULL, "ctx is NULL");
+    GSE_REQUIRE(!enable || ctx->params_block != NULL, "upload a parameter block first");
+    ctx->step_params = enable ? ctx->params_block : NULL;
     return GSE_OK;
 }
 

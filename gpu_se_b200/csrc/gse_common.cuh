@@ -103,6 +103,11 @@ struct gse_ctx {
     int64_t* part;            // merge-path split points
     int64_t* range;           // [k_lo, k_hi): sources that interleave with a shard's outputs
     unsigned int scan_epoch;
+    const gse_step_params* step_params;   // device block overriding the per-step scalars (CUDA-graph replay), or NULL
+    gse_step_params* params_block;        // the context's device block
+    gse_step_params* params_ring;         // pinned staging ring (GSE_PARAM_RING slots)
+    cudaEvent_t params_event[4];          // one per quarter of the ring: guards against overrunning queued copies
+    int params_pos;
     int64_t max_blocks;
     int64_t max_tiles;
 };
@@ -110,6 +115,8 @@ struct gse_ctx {
 int gse_build_sampler5(const gse_mixture* m, MixSampler5* out);
 int gse_build_density2(const gse_mixture* m, MixDensity2* out);
 int gse_build_densityN(const gse_mixture* m, MixDensityN* out);
+
+#define GSE_PARAM_RING 1024
 
 static inline int64_t gse_div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
@@ -274,6 +281,16 @@ struct ModelInputs {
     float f_out;   // Fg_in + Fm_in           (:197)
     float dt;
 };
+
+// per-step scalars: by value, or from the device block when one is attached to the context
+__device__ __forceinline__ ModelInputs model_inputs(ModelInputs in, const gse_step_params* sp, int n_sub) {
+    if (sp) {
+        in.feed = (float)(sp->u[0] * (5000.0 / 180.0));       // the host's expressions (gse_pf_predict), bit for bit
+        in.f_out = (float)(sp->u[0] + sp->u[1]);
+        in.dt = (float)(sp->dt / n_sub);
+    }
+    return in;
+}
 
 __device__ __forceinline__ void bioreactor_increment(const float x[5], const ModelInputs& in, float d[5]) {
     // :192-193 -- the rate expressions see clamped Cg, Cx, Cfa, Ce; Ch is not clamped

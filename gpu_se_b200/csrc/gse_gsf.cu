@@ -94,11 +94,13 @@ extern "C" int gse_gsf_sigma_points(gse_ctx* ctx, const float* mean_dev, const f
 template <bool DIAG, bool HOST_NOISE>
 __global__ void __launch_bounds__(GSF_THREADS)
 k_gsf_predict(const float* mean_src, const float* cov_src, int64_t lds, const int32_t* __restrict__ idx,
-              float* mean, float* cov, int64_t ld, int64_t n, ModelInputs in,
+              float* mean, float* cov, int64_t ld, int64_t n, ModelInputs in_arg,
               const __grid_constant__ MixSampler5 sp, uint32_t k0, uint32_t k1, uint32_t step, int64_t index0,
-              const float* __restrict__ noise, int64_t ldn) {
+              const float* __restrict__ noise, int64_t ldn, const gse_step_params* __restrict__ params) {
     const int64_t i = (int64_t)blockIdx.x * GSF_THREADS + threadIdx.x;
     if (i >= n) return;
+    const ModelInputs in = model_inputs(in_arg, params, 1);
+    if (params) step = (uint32_t)params->step;
     const int64_t is = idx ? (int64_t)idx[i] : i;          // pending resample: read through the ancestor index
     float m[5], P[15], L[15];
 #pragma unroll
@@ -174,11 +176,11 @@ extern "C" int gse_gsf_predict(gse_ctx* ctx, const float* mean_src_dev, const fl
     cudaStream_t s = (cudaStream_t)stream;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     if (noise_dev)
-        k_gsf_predict<true, true><<<blocks, GSF_THREADS, 0, s>>>(mean_src_dev, cov_src_dev, ld_src, idx_dev, mean_dev, cov_dev, ld, n, in, ctx->state_sampler, k0, k1, (uint32_t)step, index0, noise_dev, ld_noise);
+        k_gsf_predict<true, true><<<blocks, GSF_THREADS, 0, s>>>(mean_src_dev, cov_src_dev, ld_src, idx_dev, mean_dev, cov_dev, ld, n, in, ctx->state_sampler, k0, k1, (uint32_t)step, index0, noise_dev, ld_noise, ctx->step_params);
     else if (ctx->state_sampler.diag)
-        k_gsf_predict<true, false><<<blocks, GSF_THREADS, 0, s>>>(mean_src_dev, cov_src_dev, ld_src, idx_dev, mean_dev, cov_dev, ld, n, in, ctx->state_sampler, k0, k1, (uint32_t)step, index0, NULL, 0);
+        k_gsf_predict<true, false><<<blocks, GSF_THREADS, 0, s>>>(mean_src_dev, cov_src_dev, ld_src, idx_dev, mean_dev, cov_dev, ld, n, in, ctx->state_sampler, k0, k1, (uint32_t)step, index0, NULL, 0, ctx->step_params);
     else
-        k_gsf_predict<false, false><<<blocks, GSF_THREADS, 0, s>>>(mean_src_dev, cov_src_dev, ld_src, idx_dev, mean_dev, cov_dev, ld, n, in, ctx->state_sampler, k0, k1, (uint32_t)step, index0, NULL, 0);
+        k_gsf_predict<false, false><<<blocks, GSF_THREADS, 0, s>>>(mean_src_dev, cov_src_dev, ld_src, idx_dev, mean_dev, cov_dev, ld, n, in, ctx->state_sampler, k0, k1, (uint32_t)step, index0, NULL, 0, ctx->step_params);
     GSE_CHECK_LAUNCH(ctx);
     return GSE_OK;
 }
@@ -190,7 +192,8 @@ extern "C" int gse_gsf_predict(gse_ctx* ctx, const float* mean_src_dev, const fl
 __global__ void __launch_bounds__(GSF_THREADS)
 k_gsf_update(float* __restrict__ mean, float* __restrict__ cov, int64_t ld, int64_t n, const float* loglik_in,
              float* loglik, double z0, double z1, const __grid_constant__ MixDensity2 md, float* block_max, float* block_sum,
-             unsigned int* ticket, double* stats) {
+             unsigned int* ticket, double* stats, const gse_step_params* __restrict__ params) {
+    if (params) { z0 = params->z[0]; z1 = params->z[1]; }
     const int64_t i = (int64_t)blockIdx.x * GSF_THREADS + threadIdx.x;
     float vals[1] = {0.0f};
     bool valid[1] = {false};
@@ -284,7 +287,7 @@ extern "C" int gse_gsf_update(gse_ctx* ctx, float* mean_dev, float* cov_dev, int
     GSE_REQUIRE((int64_t)blocks <= ctx->max_blocks, "workspace too small");
     k_gsf_update<<<blocks, GSF_THREADS, 0, (cudaStream_t)stream>>>(mean_dev, cov_dev, ld, n, loglik_in_dev, loglik_dev, z[0], z[1],
                                                                    ctx->meas_density, ctx->block_max, ctx->block_sum,
-                                                                   ctx->ticket, stats_dev);
+                                                                   ctx->ticket, stats_dev, ctx->step_params);
     GSE_CHECK_LAUNCH(ctx);
     return GSE_OK;
 }

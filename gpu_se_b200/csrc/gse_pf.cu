@@ -64,11 +64,14 @@ template <bool DIAG, bool HOST_NOISE, bool ONE_STEP, int ND, int GMODE>
 __global__ void __launch_bounds__(PF_THREADS, 5)
 k_pf_predict(const float* xs, int64_t lds, const int32_t* __restrict__ idx, const __grid_constant__ GatherShards shards,
              float* xd, int64_t ldd, int64_t n,
-             ModelInputs in, int n_sub, const __grid_constant__ MixSampler5 sp, uint32_t k0, uint32_t k1,
-             uint32_t step, int64_t index0, const float* __restrict__ noise, int64_t ldn) {
+             ModelInputs in_arg, int n_sub, const __grid_constant__ MixSampler5 sp, uint32_t k0, uint32_t k1,
+             uint32_t step, int64_t index0, const float* __restrict__ noise, int64_t ldn,
+             const gse_step_params* __restrict__ params) {
     const int64_t g = (int64_t)blockIdx.x * PF_THREADS + threadIdx.x;
     const int64_t row0 = g * ROWS_PER_THREAD;
     if (row0 >= n) return;
+    const ModelInputs in = model_inputs(in_arg, params, ONE_STEP ? 1 : n_sub);
+    if (params) step = (uint32_t)params->step;
     float v[5][4];
     if (GMODE == 2) {
         const int4 id4 = *reinterpret_cast<const int4*>(idx + row0);
@@ -172,7 +175,7 @@ static int launch_predict(gse_ctx* ctx, const float* x_src_dev, int64_t ld_src, 
 #define LAUNCH_PREDICT_G(DIAG, HOST, ONE, ND, GMODE)                                                             \
     k_pf_predict<DIAG, HOST, ONE, ND, GMODE><<<blocks, PF_THREADS, 0, s>>>(                                      \
         x_src_dev, ld_src, idx_dev, *shards, x_dst_dev, ld_dst, n, in, n_sub, ctx->state_sampler, k0, k1,        \
-        (uint32_t)step, index0, noise_dev, ld_noise)
+        (uint32_t)step, index0, noise_dev, ld_noise, ctx->step_params)
 #define LAUNCH_PREDICT(DIAG, HOST, ONE, ND)                                                                      \
     do {                                                                                                         \
         if (sharded) LAUNCH_PREDICT_G(DIAG, HOST, ONE, ND, 2);                                                   \
@@ -224,7 +227,13 @@ __global__ void __launch_bounds__(PF_THREADS)
 k_pf_update(const float* __restrict__ xg, const float* __restrict__ xfa, const float* loglik_in,
             float* loglik, int64_t n, float z0h, float z0l, float z1h, float z1l,
             const __grid_constant__ MixDensity2f md, float* block_max, float* block_sum, unsigned int* ticket,
-            double* stats) {
+            double* stats, const gse_step_params* __restrict__ params) {
+    if (params) {                                           // the host's hi/lo split of z (gse_pf_update), bit for bit
+        z0h = (float)params->z[0];
+        z1h = (float)params->z[1];
+        z0l = (float)(params->z[0] - (double)z0h);
+        z1l = (float)(params->z[1] - (double)z1h);
+    }
     const int64_t groups = (n + 3) >> 2;
     const int64_t stride = (int64_t)gridDim.x * PF_THREADS;
     MaxSumExp acc;
@@ -271,7 +280,7 @@ extern "C" int gse_pf_update(gse_ctx* ctx, const float* x_dev, int64_t ld, int64
 #define LAUNCH_UPDATE_Z(ND, ZERO)                                                                           \
     k_pf_update<ND, ZERO><<<blocks, PF_THREADS, 0, (cudaStream_t)stream>>>(                                    \
         x_dev + 0 * ld, x_dev + 2 * ld, loglik_in_dev, loglik_dev, n, z0h, z0l, z1h, z1l, ctx->meas_density32, \
-        ctx->block_max, ctx->block_sum, ctx->ticket, stats_dev)
+        ctx->block_max, ctx->block_sum, ctx->ticket, stats_dev, ctx->step_params)
 #define LAUNCH_UPDATE(ND) do { if (loglik_in_dev) LAUNCH_UPDATE_Z(ND, false); else LAUNCH_UPDATE_Z(ND, true); } while (0)
     switch (ctx->meas_density32.nd) {
         case 1: LAUNCH_UPDATE(1); break;

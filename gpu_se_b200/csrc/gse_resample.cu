@@ -302,6 +302,7 @@ struct ResampleArgs {
     int64_t n_out;
     int64_t out0;              // global index of local output 0
     double r;
+    const double* r_dev;       // device override of r (parameter block of a captured graph), or NULL
     double n_total;
     double inv_n;
     int n_pow2;
@@ -325,8 +326,9 @@ __device__ __forceinline__ uint64_t source_weight(const ResampleArgs& a, int64_t
     return a.seg_cumsum[s][k - a.seg_row[s]] + a.offtot[s];
 }
 
+__device__ __forceinline__ double offset_r(const ResampleArgs& a) { return a.r_dev ? __ldg(a.r_dev) : a.r; }
 __device__ __forceinline__ double sample_u(const ResampleArgs& a, double di) {
-    return gse_sample_position(di, a.r, a.n_total, a.inv_n, a.n_pow2 != 0);
+    return gse_sample_position(di, offset_r(a), a.n_total, a.inv_n, a.n_pow2 != 0);
 }
 __device__ __forceinline__ uint64_t output_qlo(const ResampleArgs& a, double di, uint64_t off, double Td) {
     const uint64_t qa = __double2ull_rd(__dmul_rn(sample_u(a, di), Td));
@@ -455,7 +457,7 @@ k_resample_partition(const ResampleArgs a, int64_t* __restrict__ part, int64_t n
 // ------------------------------------------------------------------------------------------------
 template <bool POW2>
 __device__ __forceinline__ double sample_pos(const ResampleArgs& a, double di) {
-    return gse_sample_position(di, a.r, a.n_total, a.inv_n, POW2);
+    return gse_sample_position(di, offset_r(a), a.n_total, a.inv_n, POW2);
 }
 
 // first global output index i in [dbase, dend] with u_i > g = fl(cd / Td), starting from a guess
@@ -509,6 +511,7 @@ k_resample_search(const ResampleArgs a, const int64_t* __restrict__ part, int32_
     // of u_i and g_k, which moves the boundary by less than 3 N 2^-53; t below is within another
     // 3 N 2^-53 of t*.  So when t is further than eps = N 2^-48 from an integer the rank is
     // floor(t) + 1, no division needed; otherwise (ties, ~2 eps of all sources) settle it exactly.
+    const double rr = offset_r(a);
     const double inv_T = 1.0 / Td;     // (hoisting this division into the partition kernel measured 8 us SLOWER:
                                        //  it overlaps the window's load latency here, a dependent load does not)
     const double eps = a.n_total * 3.5527136788005009e-15;         // N * 2^-48
@@ -535,7 +538,7 @@ k_resample_search(const ResampleArgs a, const int64_t* __restrict__ part, int32_
                     // (the cvt / floor instructions run on the XU pipe, 7-14 lanes/clk/SM, but exponent-trick
                     // replacements on the ALU pipe measured slower: tools/ubench_xu.cu, profiles/)
                     const double cd = __ull2double_rn(c[m] + off);
-                    const double t = __fma_rn(__dmul_rn(cd, inv_T), a.n_total, -a.r);
+                    const double t = __fma_rn(__dmul_rn(cd, inv_T), a.n_total, -rr);
                     const double fl = floor(t);
                     const double fr = t - fl;
                     if (fr > eps && fr < one_m_eps)
@@ -635,6 +638,7 @@ static int launch_search(gse_ctx* ctx, const ResampleArgs& a, int64_t nparts, in
 
 static void fill_common(gse_ctx* ctx, ResampleArgs& a, double r, int64_t n_total, int64_t out0, int64_t n_out) {
     a.consts = (double*)(ctx->range + 4);
+    a.r_dev = ctx->step_params ? &ctx->step_params->r : NULL;
     a.n_out = n_out;
     a.out0 = out0;
     a.r = r;

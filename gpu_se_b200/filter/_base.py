@@ -20,6 +20,15 @@ reads row ``idx[i]`` of the pre-resample state for row ``i``, so ``particles[sam
 (``particles`` / ``means`` attributes, ``update`` right after ``resample``) calls ``_materialise()``.
 ``_loglik_zero`` marks the accumulated log-likelihood as all zero (weights just reset, :103) so that
 ``update`` does not read it and nothing has to zero-fill it.
+
+CUDA graphs.  Below ~2^18 rows a predict -> update -> resample cycle is launch-bound (six kernels of
+a few microseconds each behind three Python calls).  ``enable_graphs()`` switches the three calls to
+deferred execution: ``predict`` and ``update`` only record their arguments, and ``resample`` replays
+a CUDA graph of the whole cycle captured once per state-buffer parity.  The per-step scalars (u, dt,
+z, r, the Philox step counter) live in a 64-byte device block the kernels read
+(``gse_ctx_set_step_params``), refreshed by one small H2D copy per step.  Any other access
+(``particles``, ``point_estimate`` between the calls, host-supplied noise ...) flushes the recorded
+calls eagerly first, so results are bit-identical with and without graphs.
 """
 import ctypes
 
@@ -125,6 +134,79 @@ class WeightedEnsemble:
         self._step = 0
         self.last_sample_index = None
         self._stage_hook = None        # bench.py: called with a label between the kernels of resample()
+        self._graph_mode = False
+        self._deferred = []            # recorded ("predict", u, dt) / ("update", u, z) calls
+        self._graphs = {}              # current state buffer -> captured cycle
+        self.graph_replays = 0
+
+    # -- CUDA graphs ---------------------------------------------------------------------
+    def enable_graphs(self, enable=True):
+        """Deferred execution + CUDA-graph replay of predict -> update -> resample (see the module
+        docstring).  Worth it for launch-bound sizes; harmless otherwise."""
+        self._flush()
+        if enable and not self._graph_mode:
+            self._params = _lib.gse_step_params()
+        self._graph_mode = bool(enable)
+
+    def predict(self, u, dt, noise=None):
+        if self._graph_mode and noise is None and not self._deferred and not hasattr(self.state_pdf, "draw_host"):
+            self._deferred = [("predict", (float(u[0]), float(u[1])), float(dt))]      # values, not references
+            return
+        self._flush()
+        self._predict_now(u, dt, noise)
+
+    def update(self, u, z):
+        if self._graph_mode and len(self._deferred) == 1:
+            self._deferred.append(("update", (float(u[0]), float(u[1])), (float(z[0]), float(z[1]))))
+            return
+        self._flush()
+        self._update_now(u, z)
+
+    def _flush(self):
+        """Run the recorded calls eagerly (something other than the graphed cycle is happening)."""
+        if self._deferred:
+            ops, self._deferred = self._deferred, []
+            for op in ops:
+                if op[0] == "predict":
+                    self._predict_now(op[1], op[2], None)
+                else:
+                    self._update_now(op[1], op[2])
+
+    def _replay_cycle(self, r):
+        """predict -> update -> resample as one graph launch."""
+        (_, u, dt), (_, _, z) = self._deferred
+        self._deferred = []
+        p = self._params
+        p.u[0], p.u[1] = u
+        p.dt = dt
+        p.z[0], p.z[1] = z
+        p.r = r
+        p.step = self._step
+        _lib.check(_lib.lib.gse_ctx_upload_step_params(self._ctx.handle, ctypes.byref(p), self._stream()))
+        key = self._state.data_ptr()
+        g = self._graphs.get(key)
+        if g is None:
+            # capture: the eager code path runs once into the capture stream (its host-side state
+            # transitions are the real ones), reading the per-step scalars from the device block
+            _lib.check(_lib.lib.gse_ctx_use_step_params(self._ctx.handle, 1))
+            g = torch.cuda.CUDAGraph()
+            try:
+                with torch.cuda.graph(g):
+                    self._predict_now(u, dt, None)
+                    self._update_now(u, z)
+                    self._resample_now(r, False)
+            finally:
+                _lib.check(_lib.lib.gse_ctx_use_step_params(self._ctx.handle, 0))
+            self._graphs[key] = g
+            g.replay()
+        else:
+            g.replay()
+            # the host-side transitions of the cycle: the gathering predict swapped the buffers and
+            # advanced the Philox step; resample left the weights uniform and the index pending
+            self._state, self._state_alt = self._state_alt, self._state
+            self._step += 1
+            self._touch()
+        self.graph_replays += 1
 
     # -- helpers -------------------------------------------------------------------------
     def _stream(self):
@@ -148,6 +230,7 @@ class WeightedEnsemble:
 
     def _materialise(self):
         """Apply a pending resample: state <- state[:, idx]  (particles[sample_index], particle.py:102)."""
+        self._flush()
         if self._pending:
             n = self.N_particles
             _lib.check(_lib.lib.gse_gather_rows(self._ctx.handle, self._idx.data_ptr(), n, self._state.data_ptr(),
@@ -165,6 +248,7 @@ class WeightedEnsemble:
     # -- weights -------------------------------------------------------------------------
     @property
     def weights(self):
+        self._flush()
         n = self.N_particles
         out = torch.empty(n, dtype=torch.float64, device=self.device)
         _lib.check(_lib.lib.gse_weights_linear(
@@ -174,6 +258,7 @@ class WeightedEnsemble:
 
     @weights.setter
     def weights(self, w):
+        self._flush()
         n = self.N_particles
         if isinstance(w, torch.Tensor):
             w = w.detach().as_subclass(torch.Tensor).to(device=self.device, dtype=torch.float64).reshape(-1)
@@ -223,10 +308,20 @@ class WeightedEnsemble:
         ``numpy.random.rand()`` exactly as the reference's CPU path draws it (:93), so seeding
         numpy reproduces the reference's offset.  Produces the ancestor index only; the rows move
         when the next kernel reads them (see the module docstring)."""
-        n = self.N_particles
         if r is None:
             r = numpy.random.rand()
         r = float(r)
+        if not (0.0 <= r < 1.0):
+            raise ValueError("r must be in [0, 1)")
+        if (self._graph_mode and len(self._deferred) == 2 and not return_index and self._pending
+                and self._base is None and self._stage_hook is None):
+            self._replay_cycle(r)
+            return None
+        self._flush()
+        return self._resample_now(r, return_index)
+
+    def _resample_now(self, r, return_index):
+        n = self.N_particles
         self._materialise()                       # a second resample without a predict in between
         self._scan()
         if self._stage_hook is not None:
@@ -244,6 +339,7 @@ class WeightedEnsemble:
 
     def cumulative_weights(self):
         """(cumsum uint64 as numpy, total) of the current weights -- test / diagnostics hook."""
+        self._flush()
         self._scan()
         c = self._cumsum[:self.N_particles].cpu().numpy().view(numpy.uint64)
         return c, int(c[-1])
@@ -258,6 +354,7 @@ class WeightedEnsemble:
         """Weighted moments of the population, cached until the state changes.  point_estimate alone
         runs the means-only kernel; once a caller has asked for point_covariance (sim_base.py:291-295
         does both every step) both are computed in one pass."""
+        self._flush()
         if need_cov:
             self._want_cov = True
         if not self._mom_valid or (need_cov and not self._mom_full):

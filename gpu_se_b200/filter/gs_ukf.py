@@ -98,7 +98,7 @@ class ParallelGaussianSumUnscentedKalmanFilter(WeightedEnsemble):
                                                  out.data_ptr(), self._ld, self._stream()))
         return _device.wrap(out[:, :n].t().reshape(n, 11, 5))
 
-    def predict(self, u, dt, noise=None):
+    def _predict_now(self, u, dt, noise=None):
         """gs_ukf.py:348-367.  ``noise`` (N, 11, 5): host-supplied draws for cross-checks."""
         n = self.N_particles
         if noise is None:
@@ -120,7 +120,7 @@ class ParallelGaussianSumUnscentedKalmanFilter(WeightedEnsemble):
         self._step += 1
         self._touch()
 
-    def update(self, u, z):
+    def _update_now(self, u, z):
         """gs_ukf.py:369-407."""
         self._materialise()
         _lib.check(_lib.lib.gse_gsf_update(self._ctx.handle, self._mean_ptr(), self._cov_ptr(), self._ld,

@@ -58,6 +58,7 @@ class ParallelParticleFilter(WeightedEnsemble):
 
     @particles.setter
     def particles(self, value):
+        self._flush()
         n = self.N_particles
         if isinstance(value, torch.Tensor):
             v = value.detach().as_subclass(torch.Tensor).to(device=self.device, dtype=torch.float32)
@@ -71,7 +72,7 @@ class ParallelParticleFilter(WeightedEnsemble):
         self._touch()
 
     # -- the three stages ----------------------------------------------------------------
-    def predict(self, u, dt, noise=None):
+    def _predict_now(self, u, dt, noise=None):
         """particle.py:265-277.  ``noise`` (N, 5): host-supplied draws for cross-checks; by default
         the state noise comes from the in-kernel Philox stream (or from the state pdf itself when
         that is a DeterministicGaussianSum)."""
@@ -95,7 +96,7 @@ class ParallelParticleFilter(WeightedEnsemble):
         self._step += 1
         self._touch()
 
-    def update(self, u, z):
+    def _update_now(self, u, z):
         """particle.py:279-294."""
         self._materialise()
         _lib.check(_lib.lib.gse_pf_update(self._ctx.handle, self._state.data_ptr(), self._ld, self.N_particles,
@@ -103,7 +104,7 @@ class ParallelParticleFilter(WeightedEnsemble):
                                           _lib.as_double2(z), self._stats.data_ptr(), self._stream()))
         self._after_update()
 
-    # resample(): WeightedEnsemble.resample  (particle.py:296-316)
+    # predict() / update() / resample(): WeightedEnsemble (eager, or recorded for a CUDA-graph replay)
 
     # -- estimates -----------------------------------------------------------------------
     MEAN_ONLY_KERNEL = True

@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define GSE_ABI_VERSION 3
+#define GSE_ABI_VERSION 4
 
 #define GSE_NX 5        /* states  (Cg, Cx, Cfa, Ce, Ch)   model/BioreactorModel.py:191 */
 #define GSE_NU 2        /* inputs  (Fg_in, Fm_in)          model/BioreactorModel.py:195 */
@@ -90,6 +90,29 @@ const char* gse_last_error(void);
 int gse_ctx_create(int device, int model_id, int64_t n_max, const gse_mixture* state,
                    const gse_mixture* meas, gse_ctx** out);
 int gse_ctx_destroy(gse_ctx* ctx);
+
+/* Per-step scalars in DEVICE memory.  While a context has a parameter block attached
+ * (gse_ctx_set_step_params), every launch made through it reads u, dt, z, r and the Philox step
+ * counter from the block instead of from the by-value arguments of the call.  A captured CUDA
+ * graph of predict -> update -> resample can then be replayed step after step: the host only
+ * refreshes the 64-byte block (one small H2D copy) before each replay.  For the launch-bound sizes
+ * (all of the reference's GS-UKF sweep, particle filters up to ~2^18). */
+typedef struct gse_step_params {
+    double u[GSE_NU];
+    double dt;
+    double z[GSE_NY];
+    double r;
+    uint64_t step;
+    uint64_t reserved;
+} gse_step_params;
+
+/* The context owns one parameter block in device memory and a pinned staging ring.
+ * gse_ctx_upload_step_params copies `values` (host) into the block on `stream` (asynchronous: the
+ * values are staged in the ring first, so the caller's struct may be reused at once);
+ * gse_ctx_use_step_params(ctx, 1) makes every later launch through the context read the block,
+ * (ctx, 0) restores the by-value arguments. */
+int gse_ctx_upload_step_params(gse_ctx* ctx, const gse_step_params* values, void* stream);
+int gse_ctx_use_step_params(gse_ctx* ctx, int enable);
 
 /* ---- sampling / density of a Gaussian sum (MultivariateGaussianSum.py:39-97) ---------------- */
 

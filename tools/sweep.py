@@ -34,8 +34,10 @@ def build(kind, n, dev):
     return cls(g.Bioreactor.homeostatic_DEs, g.Bioreactor.static_outputs, n, x0, state, meas, device=dev, seed=11)
 
 
-def time_filter(kind, n, runs, dev, dt):
+def time_filter(kind, n, runs, dev, dt, graphs=False):
     f = build(kind, n, dev)
+    if graphs:
+        f.enable_graphs()
     us, zs = bench.trajectory(runs + 10, seed=3)
     rs = numpy.random.default_rng(1).random(runs + 10)
     stream = torch.cuda.current_stream(dev)
@@ -44,11 +46,15 @@ def time_filter(kind, n, runs, dev, dt):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         ev[0].record(stream)
         f.predict(us[k], dt)
-        ev[1].record(stream)
+        if not graphs:
+            ev[1].record(stream)
         f.update(us[k], zs[k])
-        ev[2].record(stream)
+        if not graphs:
+            ev[2].record(stream)
         f.resample(r=float(rs[k]))
         ev[3].record(stream)
+        if graphs:                     # the three calls are one graph launch: only the whole step can be timed
+            ev[1] = ev[2] = ev[0]
         if k >= 10:
             rec["predict"].append((ev[0], ev[1]))
             rec["update"].append((ev[1], ev[2]))
@@ -72,19 +78,20 @@ def main():
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.json"))
     ap.add_argument("--pf-max", type=int, default=24)
     ap.add_argument("--gsf-max", type=int, default=20)
+    ap.add_argument("--graphs", action="store_true", help="CUDA-graph replay of the cycle (stage times collapse into 'resample')")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     peak, src = bench.measured_peak_gbs()
-    res = {"hbm_peak_gbs": peak, "peak_source": src, "runs": a.runs, "dt": 1.0, "pf": [], "gsf": [],
+    res = {"hbm_peak_gbs": peak, "peak_source": src, "runs": a.runs, "dt": 1.0, "pf": [], "gsf": [], "cuda_graphs": a.graphs,
            "pf_bytes_per_particle_step": bench.STEP_BYTES, "gsf_bytes_per_comp_step": 80 + 80 + 84 + 84 + 12 + 12 + 4}
     for p in range(10, a.pf_max + 1, 2):
-        r = time_filter("pf", 1 << p, a.runs, dev, 1.0)
+        r = time_filter("pf", 1 << p, a.runs, dev, 1.0, a.graphs)
         r["hbm_frac"] = bench.STEP_BYTES * r["N"] / (r["step_ms_median"] * 1e-3) / 1e9 / peak
         res["pf"].append(r)
         print(json.dumps(r), flush=True)
     for p in list(range(8, min(a.gsf_max, 16) + 1, 2)) + ([18, 20] if a.gsf_max >= 20 else []):
-        r = time_filter("gsf", 1 << p, a.runs, dev, 1.0)
+        r = time_filter("gsf", 1 << p, a.runs, dev, 1.0, a.graphs)
         r["hbm_frac"] = res["gsf_bytes_per_comp_step"] * r["N"] / (r["step_ms_median"] * 1e-3) / 1e9 / peak
         res["gsf"].append(r)
         print(json.dumps(r), flush=True)
