@@ -425,22 +425,26 @@ template <bool SEG>
 __global__ void __launch_bounds__(128)
 k_resample_partition(const ResampleArgs a, int64_t* __restrict__ part, int64_t nparts) {
     const int lane = threadIdx.x & 31;
-    const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (b > nparts) return;
     const int64_t k_lo = a.range ? a.range[0] : 0;
     const int64_t span = a.range ? a.range[1] - k_lo : a.n_src;
     const uint64_t off0 = SEG ? 0ull : a.offtot[0];
     const double Td = __ull2double_rn(a.offtot[SEG ? a.nseg : 1]);
-    int64_t diag = b * RS_WORK;
     const int64_t total = span + a.n_out;
-    if (diag >= total) {                                         // beyond the merged sequence: an empty window
-        if (lane == 0) part[b] = k_lo + span;
-        return;
+    // split points 0 .. ceil(total / W) are needed; the grid covers them with a stride (it is sized for the
+    // expected span of a sharded run, not for all G shards' rows)
+    const int64_t last = min(nparts, (total + RS_WORK - 1) / RS_WORK);
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; b <= last; b += warps) {
+        const int64_t diag = b * RS_WORK;
+        if (diag >= total) {                                     // the end of the merged sequence
+            if (lane == 0) part[b] = k_lo + span;
+            continue;
+        }
+        const int64_t lo = k_lo + (diag > a.n_out ? diag - a.n_out : 0);
+        const int64_t hi = k_lo + (diag < span ? diag : span);
+        const int64_t s = warp_split<SEG>(a, lo, hi, diag, k_lo, -1, off0, Td, lane);
+        if (lane == 0) part[b] = s;
     }
-    const int64_t lo = k_lo + (diag > a.n_out ? diag - a.n_out : 0);
-    const int64_t hi = k_lo + (diag < span ? diag : span);
-    const int64_t s = warp_split<SEG>(a, lo, hi, diag, k_lo, -1, off0, Td, lane);
-    if (lane == 0) part[b] = s;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -460,14 +464,15 @@ __device__ __forceinline__ double sample_pos(const ResampleArgs& a, double di) {
     return gse_sample_position(di, offset_r(a), a.n_total, a.inv_n, POW2);
 }
 
-// first global output index i in [dbase, dend] with u_i > g = fl(cd / Td), starting from a guess
+// first global output index i in [dbase, dend] with u_i > g = fl(cd / Td), starting from a guess.
+// Out of line and fed with scalars only: passing the argument struct would make every thread spill it.
 template <bool POW2>
-__device__ __noinline__ double rank_exact(const ResampleArgs& a, double cd, double Td, double di, double dbase,
-                                          double dend) {
+__device__ __noinline__ double rank_exact(double r, double n_total, double inv_n, double cd, double Td, double di,
+                                          double dbase, double dend) {
     const double g = __ddiv_rn(cd, Td);                            // cumsum / cumsum[-1]   (:90)
     di = fmin(fmax(di, dbase), dend);
-    while (di > dbase && sample_pos<POW2>(a, di - 1.0) > g) di -= 1.0;
-    while (di < dend && !(sample_pos<POW2>(a, di) > g)) di += 1.0;
+    while (di > dbase && gse_sample_position(di - 1.0, r, n_total, inv_n, POW2) > g) di -= 1.0;
+    while (di < dend && !(gse_sample_position(di, r, n_total, inv_n, POW2) > g)) di += 1.0;
     return di;
 }
 
@@ -477,15 +482,18 @@ k_resample_search(const ResampleArgs a, const int64_t* __restrict__ part, int32_
     __shared__ __align__(16) int s_mark[RS_WORK];          // markers, then their prefix maximum
     __shared__ int s_warp[RS_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int64_t b = blockIdx.x;
     const int64_t k_lo = a.range ? a.range[0] : 0;
     const int64_t total = (a.range ? a.range[1] - k_lo : a.n_src) + a.n_out;
+    // windows with a grid stride: one per CTA on one GPU; in a sharded run the grid is sized for the expected
+    // span of sources and the stride absorbs a skewed one
+    int64_t b = blockIdx.x;
+    if (b * RS_WORK >= total) return;
+    do {                                                   // (one pass on one GPU: the grid covers every window)
     int64_t d0 = b * RS_WORK, d1 = d0 + RS_WORK;
-    if (d0 >= total) return;                               // beyond the sources that matter to these outputs
     if (d1 > total) d1 = total;
     const int64_t a0 = part[b], a1 = part[b + 1];
     const int64_t o0 = d0 - (a0 - k_lo), o1 = d1 - (a1 - k_lo);
-    if (o1 <= o0) return;                                  // a stretch of sources with no offspring
+    if (o1 <= o0) continue;                                // a stretch of sources with no offspring
     const int ns = (int)(a1 - a0);
     const int no = (int)(o1 - o0);
     // sharded: a window inside one shard (all but G - 1 of them) is read like a local one
@@ -544,7 +552,7 @@ k_resample_search(const ResampleArgs a, const int64_t* __restrict__ part, int32_
                     if (fr > eps && fr < one_m_eps)
                         r = __double2int_rz(fl + one_m_base);      // saturating; the rank is floor(t) + 1 - dbase
                     else
-                        r = __double2int_rz(rank_exact<POW2>(a, cd, Td, fl + 1.0, dbase, dend) - dbase);
+                        r = __double2int_rz(rank_exact<POW2>(rr, a.n_total, a.inv_n, cd, Td, fl + 1.0, dbase, dend) - dbase);
                     r = min(max(r, 0), no);
                 }
                 e[h + m] = r;
@@ -611,15 +619,25 @@ k_resample_search(const ResampleArgs a, const int64_t* __restrict__ part, int32_
     const int base = (int)(a0 + (room < 0 ? room : 0));
     int32_t* out = idx_out + o0;
     for (int j = tid; j < no; j += RS_THREADS) out[j] = base + min(s_mark[j], cap);
+    if (SEG) __syncthreads();                              // s_mark is reused by the next window
+    } while (SEG && (b += gridDim.x) * RS_WORK < total);
 }
 
-static int launch_search(gse_ctx* ctx, const ResampleArgs& a, int64_t nparts, int32_t* idx_out_dev, bool seg,
+static int launch_search(gse_ctx* ctx, const ResampleArgs& a, int64_t nparts_all, int32_t* idx_out_dev, bool seg,
                          cudaStream_t s) {
+    int64_t nparts = nparts_all;
+    // sharded: the sources that interleave with this shard's outputs are ~n_out of them in steady state
+    // (balanced weights); both kernels stride over the windows, so a grid sized for 2.5 n_out merged
+    // elements is correct for any skew and does not grow with the number of shards
+    if (seg) {
+        const int64_t expected = gse_div_up(a.n_out * 5 / 2 + RS_WORK, RS_WORK);
+        if (nparts > expected) nparts = expected;
+    }
     const unsigned pgrid = (unsigned)gse_div_up((nparts + 1) * 32, 128);
     if (seg) {
         k_resample_source_range<true><<<1, 64, 0, s>>>(a, ctx->range);
         GSE_CHECK_LAUNCH(ctx);
-        k_resample_partition<true><<<pgrid, 128, 0, s>>>(a, ctx->part, nparts);
+        k_resample_partition<true><<<pgrid, 128, 0, s>>>(a, ctx->part, nparts_all);
     } else {
         k_resample_partition<false><<<pgrid, 128, 0, s>>>(a, ctx->part, nparts);
     }

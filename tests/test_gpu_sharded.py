@@ -108,11 +108,12 @@ def test_world1_equals_single_gpu(n, exchange):
     _launch(1, n, exchange)
 
 
-@pytest.mark.parametrize("exchange", ["peer", "slabs"])
-@pytest.mark.parametrize("n", [8192, 1000003])
-def test_world2_equals_single_gpu(n, exchange):
+@pytest.mark.parametrize("world,exchange,n", [(2, "peer", 8192), (2, "peer", 1000003), (2, "slabs", 8192),
+                                              (2, "slabs", 1000003), (4, "peer", 1000003), (4, "slabs", 100003),
+                                              (8, "peer", 2000003)])
+def test_worldN_equals_single_gpu(world, n, exchange):
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs")
-    results = _launch(2, n, exchange)
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    results = _launch(world, n, exchange)
     assert any(info > 0 for _, _, info in results), "informative measurement: shards must exchange rows"
