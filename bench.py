@@ -43,6 +43,18 @@ STAGE_BYTES_SHARDED = {"predict": 44, "update": 12, "scan": 12, "offsets": 0, "s
 STEP_BYTES = sum(STAGE_BYTES.values())          # 80 B per particle-step (SURVEY §8(d) counted 128 B with a materialised gather)
 
 
+def workload_name(log2n):
+    return ("pf_openloop predict+update+resample, BioreactorModel, 2^%g particles per GPU, dt=1.0, "
+            "in-kernel Philox noise" % log2n)
+
+
+# DRAM traffic per launch of each kernel at 2^24 particles (dram__bytes_read.sum + dram__bytes_write.sum of
+# the committed `ncu --set full` capture, profiles/r1_v9_pf_step_2p24_ncu_full.csv), in bytes per row
+NCU_TRAFFIC_BYTES_PER_ROW = {"predict": (335.84e6 + 286.18e6) / 2 ** 24, "update": (134.23e6 + 30.94e6) / 2 ** 24,
+                             "scan": (67.13e6 + 0.34e6 + 67.18e6 + 83.68e6) / 2 ** 24,
+                             "search": (71.70e6 + 1.55e6 + 134.32e6 + 41.06e6) / 2 ** 24}
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -52,6 +64,9 @@ def parse_args():
     ap.add_argument("--log2n", type=float, default=24.0, help="log2 of particles per GPU")
     ap.add_argument("--cpu-log2n", type=int, default=13, help="log2 of the CPU-baseline sample size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="pf", choices=["pf", "gsf"],
+                    help="gsf: GS-UKF components/s at 2^--log2n components (BASELINE configs[3]; give --log2n 16)")
+    ap.add_argument("--graphs", action="store_true", help="CUDA-graph replay of the cycle (launch-bound sizes)")
     ap.add_argument("--sharded", action="store_true",
                     help="use the sharded driver even on one GPU (profiling the peer-memory kernels under ncu)")
     return ap.parse_args()
@@ -199,8 +214,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "pf_openloop predict+update+resample, BioreactorModel, dt=1.0; bounded CPU "
-                                   "sample of 2^%d particles per step (cost is linear in N)" % log2n,
+            "config": {"workload": workload_name(args.log2n),
+                       "sample": "bounded CPU sample of 2^%d particles per step (cost is linear in N)" % log2n,
                        "particles_per_step": n},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
                              "sample": "oracle loop port of filter/particle.py:54-103 (the Python reference cannot "
@@ -247,8 +262,12 @@ def run_ours(args):
     if world > 1 or args.sharded:
         from gpu_se_b200.sharded import ShardedParticleFilter
         pf = ShardedParticleFilter(f, gg, n_total, x0, state, meas, device=dev, seed=1234)
+    elif args.workload == "gsf":
+        pf = g.GaussianSumUnscentedKalmanFilter(f, gg, n_total, x0, state, meas, device=dev, seed=1234)
     else:
         pf = g.ParticleFilter(f, gg, n_total, x0, state, meas, device=dev, seed=1234)
+    if args.graphs:
+        pf.enable_graphs()
 
     K, W = args.steps, max(args.warmup, 3)
     us, zs = trajectory(2 * (K + W), seed=7)
@@ -270,6 +289,7 @@ def run_ours(args):
         stage_events.append((label, ev))
 
     def step(k, record):
+        record = record and not args.graphs     # a graph replay is one launch: only the whole step can be timed
         if record:
             hook("start")
         pf.predict(us[k], DT)
@@ -341,6 +361,8 @@ def run_ours(args):
 
     peak, peak_src = measured_peak_gbs()
     STAGE_BYTES = globals()["STAGE_BYTES_SHARDED" if world > 1 else "STAGE_BYTES"]
+    if args.workload == "gsf":      # 20 floats per component, lazy resample
+        STAGE_BYTES = {"predict": 4 + 80 + 80, "update": 80 + 80 + 4, "scan": 12, "search": 12}
     STEP_BYTES = sum(STAGE_BYTES.values())
     value = n_total * K / (dev_ms * 1e-3)
     dom = max(stage_avg, key=stage_avg.get) if stage_avg else "predict"
@@ -351,16 +373,22 @@ def run_ours(args):
                   "frac": round(STAGE_BYTES.get(k, 0) * n_local / (v * 1e-3) / 1e9 / peak, 4)}
               for k, v in stage_avg.items()}
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "metric": METRIC if args.workload == "pf" else "GSF comps/sec (predict+update+resample)", "value": value,
+        "unit": UNIT if args.workload == "pf" else "components/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "pf_openloop predict+update+resample, BioreactorModel, 2^%g particles per GPU, "
-                               "dt=1.0, in-kernel Philox noise" % args.log2n,
+        "config": {"workload": workload_name(args.log2n) if args.workload == "pf" else
+                   "gsf_openloop predict+update+resample, BioreactorModel, 2^%g components, dt=1.0%s"
+                   % (args.log2n, ", CUDA-graph replay" if args.graphs else ""),
                    "particles_total": n_total, "particles_per_gpu": n_local,
                    "parallelism": "shard%d" % world if world > 1 else "single",
                    "l2": "inputs larger than L2 (state %.0f MB per GPU vs 126 MB L2)" % (n_local * 20 / 1e6)},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak,
+                     "traffic": (NCU_TRAFFIC_BYTES_PER_ROW[dom] * n_local if dom in NCU_TRAFFIC_BYTES_PER_ROW else None),
+                     "traffic_source": "ncu --set full capture at 2^24 rows (profiles/r1_v9_pf_step_2p24_ncu_full.csv), "
+                                       "scaled by rows; per launch of the stage's kernels",
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_particle": STAGE_BYTES.get(dom),
                      "whole_step_frac": STEP_BYTES * n_local / (dev_ms / K * 1e-3) / 1e9 / peak,
                      "whole_step_bytes_per_particle": STEP_BYTES,
@@ -374,7 +402,7 @@ def run_ours(args):
         "clocks": clocks,
         "last_estimate": [float(v) for v in est],
     }
-    if not args.no_cpu_baseline and world == 1:
+    if not args.no_cpu_baseline and world == 1 and args.workload == "pf":
         line["cpu_baseline"] = cpu_baseline(args.cpu_log2n)
     emit(line)
     if world > 1:
