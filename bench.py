@@ -49,7 +49,7 @@ def workload_name(log2n):
 
 
 # DRAM traffic per launch of each kernel at 2^24 particles (dram__bytes_read.sum + dram__bytes_write.sum of
-# the committed `ncu --set full` capture, profiles/r1_v9_pf_step_2p24_ncu_full.csv), in bytes per row
+# the committed `ncu --set full` capture, profiles/r1_final_pf_step_2p24_ncu_full.csv), in bytes per row
 NCU_TRAFFIC_BYTES_PER_ROW = {"predict": (335.84e6 + 286.18e6) / 2 ** 24, "update": (134.23e6 + 30.94e6) / 2 ** 24,
                              "scan": (67.13e6 + 0.34e6 + 67.18e6 + 83.68e6) / 2 ** 24,
                              "search": (71.70e6 + 1.55e6 + 134.32e6 + 41.06e6) / 2 ** 24}
@@ -386,7 +386,7 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,
                      "traffic": (NCU_TRAFFIC_BYTES_PER_ROW[dom] * n_local if dom in NCU_TRAFFIC_BYTES_PER_ROW else None),
-                     "traffic_source": "ncu --set full capture at 2^24 rows (profiles/r1_v9_pf_step_2p24_ncu_full.csv), "
+                     "traffic_source": "ncu --set full capture at 2^24 rows (profiles/r1_final_pf_step_2p24_ncu_full.csv), "
                                        "scaled by rows; per launch of the stage's kernels",
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_particle": STAGE_BYTES.get(dom),
