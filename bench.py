@@ -204,6 +204,29 @@ def cpu_baseline(log2n):
             "vectorised_numpy_sample": "oracle vectorised float64 numpy port, 2^20 particles x 2 steps, %.1f ms/step" % vec_ms}
 
 
+def cpu_baseline_gsf(log2n=10, steps=5):
+    """GS-UKF on the host: the vectorised float64 oracle port of filter/gs_ukf.py:45-171 (the reference's own
+    CPU class loops over N x 11 Python calls of f and is ~30x slower than this)."""
+    from oracle import bioreactor, gs_ukf, mixture
+    n = 1 << log2n
+    state, meas = mixture.benchmark_noise()
+    numpy.random.seed(0)
+    f = gs_ukf.GSUKFOracle(n, mixture.benchmark_x0(bioreactor.X_STEADY), state, meas)
+    us, zs = trajectory(steps + 1, seed=1)
+    times = []
+    for k in range(steps + 1):
+        t = time.perf_counter()
+        f.predict(us[k], DT)
+        f.update(us[k], zs[k])
+        f.resample()
+        if k:
+            times.append(time.perf_counter() - t)
+    total = sum(times)
+    return {"value": n * len(times) / total, "unit": "components/s", "cores": 1, "kind": "port",
+            "sample": "oracle vectorised float64 numpy port of filter/gs_ukf.py:45-171, 2^%d components x %d steps, "
+                      "%.1f ms/step" % (log2n, len(times), 1e3 * total / len(times))}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -402,8 +425,8 @@ def run_ours(args):
         "clocks": clocks,
         "last_estimate": [float(v) for v in est],
     }
-    if not args.no_cpu_baseline and world == 1 and args.workload == "pf":
-        line["cpu_baseline"] = cpu_baseline(args.cpu_log2n)
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline(args.cpu_log2n) if args.workload == "pf" else cpu_baseline_gsf()
     emit(line)
     if world > 1:
         dist.destroy_process_group()
