@@ -273,6 +273,56 @@ __device__ __forceinline__ void draw_mixture5(const MixSampler5& sp, uint64_t in
     }
 }
 
+// State noise of FOUR consecutive rows (a group: global rows 4 g .. 4 g + 3) from six Philox calls instead
+// of eight: 20 normals = 10 Box-Muller pairs (words 0..19) and 4 component selectors (words 20..23).
+//   P_j = philox(ctr = (g_lo, g_hi, step, 0x80000000 + j), key),  j = 0..5;  words w[4 j + {0,1,2,3}] = P_j.{x,y,z,w}
+//   (n[2 p], n[2 p + 1]) = BM(w[2 p], w[2 p + 1]),  p = 0..9;  row r of the group takes n[5 r .. 5 r + 4] and
+//   selector w[20 + r]
+// Still a pure function of the GLOBAL row index (restated in oracle/philox.py: grouped_normals5).
+template <bool DIAG, int ND>
+__device__ __forceinline__ void draw_mixture5_x4(const MixSampler5& sp, uint64_t group, uint32_t step, uint32_t k0,
+                                                 uint32_t k1, float out[4][5]) {
+    uint32_t w[24];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        const Philox4 P = philox4x32_10((uint32_t)group, (uint32_t)(group >> 32), step, 0x80000000u + j, k0, k1);
+        w[4 * j] = P.x; w[4 * j + 1] = P.y; w[4 * j + 2] = P.z; w[4 * j + 3] = P.w;
+    }
+    float z[20];
+#pragma unroll
+    for (int p = 0; p < 10; ++p) box_muller(w[2 * p], w[2 * p + 1], z[2 * p], z[2 * p + 1]);
+    const int dg[5] = {0, 2, 5, 9, 14};
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const float uc = u32_to_unit(w[20 + r]);
+        int comp = 0;
+        if (ND != 1) {
+#pragma unroll
+            for (int d = 0; d < GSE_MAX_ND - 1; ++d)
+                comp += ((ND == 0 ? d < sp.nd - 1 : d < ND - 1) && uc > sp.cdf[d]) ? 1 : 0;
+        }
+        if (ND == 2 && DIAG) {
+            const bool second = comp != 0;
+#pragma unroll
+            for (int j = 0; j < 5; ++j)
+                out[r][j] = fmaf(second ? sp.L[1][dg[j]] : sp.L[0][dg[j]], z[5 * r + j],
+                                 second ? sp.mean[1][j] : sp.mean[0][j]);
+        } else if (DIAG) {
+#pragma unroll
+            for (int j = 0; j < 5; ++j) out[r][j] = fmaf(sp.L[comp][dg[j]], z[5 * r + j], sp.mean[comp][j]);
+        } else {
+            int t = 0;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                float acc = sp.mean[comp][j];
+#pragma unroll
+                for (int m = 0; m <= j; ++m) acc = fmaf(sp.L[comp][t++], z[5 * r + m], acc);
+                out[r][j] = acc;
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Bioreactor model (model/BioreactorModel.py:170-253), float32, hard-coded.
 // ------------------------------------------------------------------------------------------------

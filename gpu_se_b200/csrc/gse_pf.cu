@@ -121,6 +121,24 @@ k_pf_predict(const float* xs, int64_t lds, const int32_t* __restrict__ idx, cons
 #pragma unroll
         for (int j = 0; j < 5; ++j) nz[j] = ld_stream4(noise + j * ldn + row0);
     }
+    // process noise of the four rows: one grouped draw (six Philox calls) when the rows are a whole group of
+    // the global index space -- always, unless a shard starts off a multiple of four
+    float e4[4][5];
+    if (!HOST_NOISE) {
+        const uint64_t r0g = (uint64_t)(index0 + row0);
+        if ((r0g & 3ull) == 0) {
+            draw_mixture5_x4<DIAG, ND>(sp, r0g >> 2, step, k0, k1, e4);
+        } else {
+#pragma unroll 1
+            for (int r = 0; r < 4; ++r) {
+                float g4[4][5];
+                draw_mixture5_x4<DIAG, ND>(sp, (r0g + r) >> 2, step, k0, k1, g4);
+                const int l = (int)((r0g + r) & 3ull);
+#pragma unroll
+                for (int j = 0; j < 5; ++j) e4[r][j] = l == 0 ? g4[0][j] : (l == 1 ? g4[1][j] : (l == 2 ? g4[2][j] : g4[3][j]));
+            }
+        }
+    }
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         float xv[5] = {v[0][r], v[1][r], v[2][r], v[3][r], v[4][r]};
@@ -136,7 +154,8 @@ k_pf_predict(const float* xs, int64_t lds, const int32_t* __restrict__ idx, cons
 #pragma unroll
             for (int j = 0; j < 5; ++j) e[j] = reinterpret_cast<const float*>(&nz[j])[r];
         } else {
-            draw_mixture5<DIAG, ND>(sp, (uint64_t)(index0 + row0 + r), step, 0u, k0, k1, e);
+#pragma unroll
+            for (int j = 0; j < 5; ++j) e[j] = e4[r][j];
         }
 #pragma unroll
         for (int j = 0; j < 5; ++j) v[j][r] = __fadd_rn(xv[j], e[j]);      // particles += draw(N)   (:67)

@@ -56,13 +56,21 @@ from gpu_se_b200.filter.particle import ParallelParticleFilter
 
 
 def shard_bounds(n_total, world):
-    """Contiguous split of [0, n_total): the first n_total % world shards hold one extra row."""
-    base, rem = divmod(int(n_total), int(world))
+    """Contiguous split of [0, n_total) into shards of whole groups of four rows (the predict kernel draws
+    the noise of a group of four global rows together), as even as that allows; the last shard takes
+    the remainder."""
+    n_total, world = int(n_total), int(world)
+    groups = n_total // 4
+    base, rem = divmod(groups, world)
     bounds, lo = [], 0
     for s in range(world):
-        hi = lo + base + (1 if s < rem else 0)
+        hi = lo + 4 * (base + (1 if s < rem else 0))
+        if s == world - 1:
+            hi = n_total
         bounds.append((lo, hi))
         lo = hi
+    if any(b <= a for a, b in bounds):
+        raise ValueError("too few rows (%d) for %d shards" % (n_total, world))
     return bounds
 
 

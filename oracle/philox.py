@@ -9,7 +9,9 @@ kernels' draws can be checked value by value:
 * Philox4x32-10: Salmon, Moraes, Dror, Shaw, "Parallel random numbers: as easy as 1, 2, 3", SC'11;
   pinned by the Random123 known-answer vectors in tests/test_philox.py.
 * uniform: (x + 0.5) * 2^-32 in float32; Box-Muller with the angle folded to (-pi, pi].
-* draw layout for row ``index`` at ``step``, subsequence ``sub``:
+* grouped layout (particle-filter predict): see ``grouped_normals5``.
+* per-row layout (initial draw, GS-UKF sigma points, MultivariateGaussianSum.draw) for row ``index`` at
+  ``step``, subsequence ``sub``:
     A = philox(ctr=(index_lo, index_hi, step, 2*sub),   key=(seed_lo, seed_hi))
     B = philox(ctr=(index_lo, index_hi, step, 2*sub+1), key=(seed_lo, seed_hi))
     (z0, z1) = BM(A0, A1), (z2, z3) = BM(A2, A3), (z4, _) = BM(B0, B1), component from B2.
@@ -66,6 +68,33 @@ def standard_normals5(index, step, sub, seed):
     return numpy.stack([z0, z1, z2, z3, z4], axis=-1), u32_to_unit(B[2])
 
 
+def grouped_normals5(index, step, seed):
+    """(n, 5) float64 standard normals and (n,) float32 component uniforms of the GROUPED layout the
+    particle-filter predict kernel uses (csrc/gse_common.cuh: draw_mixture5_x4): rows 4g..4g+3 share
+    six Philox calls  P_j = philox(ctr=(g_lo, g_hi, step, 0x80000000 + j)),  j = 0..5;  words
+    w[4j..4j+3] = P_j; normals (n[2p], n[2p+1]) = BM(w[2p], w[2p+1]) for p = 0..9; row r of the group
+    takes n[5r..5r+4] and the selector word w[20 + r]."""
+    index = numpy.asarray(index, dtype=numpy.uint64)
+    group, lane = index >> numpy.uint64(2), (index & numpy.uint64(3)).astype(numpy.int64)
+    lo, hi = group & MASK, group >> numpy.uint64(32)
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    words = []
+    for j in range(6):
+        words += list(philox4x32_10(lo, hi, numpy.uint64(step & 0xFFFFFFFF), numpy.uint64(0x80000000 + j), k0, k1))
+    w = numpy.stack(words, axis=-1)                                   # (n, 24)
+    z = numpy.empty((len(index), 20))
+    for p in range(10):
+        z[:, 2 * p], z[:, 2 * p + 1] = box_muller(w[:, 2 * p], w[:, 2 * p + 1])
+    rows = numpy.arange(len(index))
+    normals = numpy.stack([z[rows, 5 * lane + k] for k in range(5)], axis=-1)
+    return normals, u32_to_unit(w[rows, 20 + lane])
+
+
+def draw_mixture5_grouped(means, covariances, weights, index, step, seed):
+    """As draw_mixture5, with the grouped layout of the predict kernel."""
+    return _mix(means, covariances, weights, *grouped_normals5(index, step, seed))
+
+
 def draw_mixture5(means, covariances, weights, index, step, sub, seed):
     """(n, 5) float64 samples the device sampler produces for these rows (up to MUFU rounding)."""
     means = numpy.asarray(means, dtype=numpy.float32).astype(numpy.float64)
@@ -73,7 +102,15 @@ def draw_mixture5(means, covariances, weights, index, step, sub, seed):
     w = numpy.asarray(weights, dtype=numpy.float32).astype(numpy.float64)
     cdf = (numpy.cumsum(w / w.sum())).astype(numpy.float32)
     cdf[-1] = 1.0
-    z, uc = standard_normals5(index, step, sub, seed)
+    return _mix(means, covariances, weights, *standard_normals5(index, step, sub, seed))
+
+
+def _mix(means, covariances, weights, z, uc):
+    means = numpy.asarray(means, dtype=numpy.float32).astype(numpy.float64)
+    covs = numpy.asarray(covariances, dtype=numpy.float32).astype(numpy.float64)
+    w = numpy.asarray(weights, dtype=numpy.float32).astype(numpy.float64)
+    cdf = (numpy.cumsum(w / w.sum())).astype(numpy.float32)
+    cdf[-1] = 1.0
     comp = numpy.zeros(z.shape[0], dtype=numpy.int64)
     for d in range(len(w) - 1):
         comp += (uc > cdf[d]).astype(numpy.int64)

@@ -164,8 +164,8 @@ def test_philox_noise_matches_specification(g):
     pf.predict(u, 0.1)
     x_after = pf.particles.get().astype(numpy.float64)
     stepped = (x_before + bioreactor.increment(x_before.astype(numpy.float32), u, 0.1)).astype(numpy.float32)
-    noise_ref, comp = philox.draw_mixture5(mixture.STATE_MEANS, mixture.STATE_COVS, mixture.STATE_WEIGHTS,
-                                           numpy.arange(N), 0, 0, seed)
+    noise_ref, comp = philox.draw_mixture5_grouped(mixture.STATE_MEANS, mixture.STATE_COVS, mixture.STATE_WEIGHTS,
+                                                   numpy.arange(N), 0, seed)
     err = numpy.abs(x_after - (stepped.astype(numpy.float64) + noise_ref))
     assert (err <= 1e-4 * sd + 6 * numpy.spacing(numpy.float32(30.0))).all()
     assert abs((comp == 0).mean() - 0.75) < 0.03

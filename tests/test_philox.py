@@ -41,3 +41,18 @@ def test_normals_and_mixture_statistics():
     assert abs((comp == 0).mean() - 0.75) < 0.005
     var = 0.75 * numpy.diag(mixture.STATE_COVS[0]) + 0.25 * numpy.diag(mixture.STATE_COVS[1])
     assert numpy.allclose(x.var(axis=0), var, rtol=0.03)
+
+
+def test_grouped_layout_statistics_and_independence():
+    """The predict kernel's grouped layout: rows of one group share Philox calls but no words."""
+    n = 200000
+    z, uc = philox.grouped_normals5(numpy.arange(n), step=5, seed=11)
+    assert numpy.abs(z.mean(axis=0)).max() < 0.01
+    assert numpy.abs(z.std(axis=0) - 1).max() < 0.01
+    assert numpy.abs(numpy.corrcoef(z.T) - numpy.eye(5)).max() < 0.01
+    flat = z.reshape(n // 4, 20)                                # the 20 normals of every group
+    assert numpy.abs(numpy.corrcoef(flat.T) - numpy.eye(20)).max() < 0.02
+    assert abs((uc > 0.75).mean() - 0.25) < 0.005
+    # a row's draw depends on its global index only
+    z2, _ = philox.grouped_normals5(numpy.arange(1001, 1013), step=5, seed=11)
+    assert numpy.array_equal(z2, z[1001:1013])

@@ -133,5 +133,10 @@ def test_sharded_resample_gloo(world, n, case, r):
 
 def test_shard_bounds():
     from gpu_se_b200 import sharded
-    assert sharded.shard_bounds(10, 3) == [(0, 4), (4, 7), (7, 10)]
-    assert sharded.shard_bounds(8, 8) == [(i, i + 1) for i in range(8)]
+    assert sharded.shard_bounds(10, 2) == [(0, 4), (4, 10)]
+    assert sharded.shard_bounds(34, 3) == [(0, 12), (12, 24), (24, 34)]
+    assert sharded.shard_bounds(32, 8) == [(4 * i, 4 * i + 4) for i in range(8)]
+    for n, g in ((1000003, 2), (2 ** 24, 8), (999, 3)):
+        b = sharded.shard_bounds(n, g)
+        assert b[0][0] == 0 and b[-1][1] == n and all(x[1] == y[0] for x, y in zip(b, b[1:]))
+        assert all(lo % 4 == 0 for lo, _ in b)
