@@ -201,7 +201,6 @@ extern "C" int gse_ctx_create(int device, int model_id, int64_t n_max, const gse
     const size_t o_red = off; off = align_up(off + sizeof(double) * 48 * 2048, 256);
     const size_t o_agg = off; off = align_up(off + sizeof(uint64_t) * c->max_tiles, 256);
     const size_t o_inc = off; off = align_up(off + sizeof(uint64_t) * c->max_tiles, 256);
-    const size_t o_flag = off; off = align_up(off + sizeof(unsigned int) * c->max_tiles, 256);
     const size_t o_part = off; off = align_up(off + sizeof(int64_t) * (c->max_tiles + 2), 256);
     const size_t o_range = off; off = align_up(off + sizeof(int64_t) * 8, 256);    // [0..1] range, [4] 1/T
     c->ws_bytes = off;
@@ -225,10 +224,8 @@ extern "C" int gse_ctx_create(int device, int model_id, int64_t n_max, const gse
     c->red_partials = (double*)(base + o_red);
     c->tile_agg = (uint64_t*)(base + o_agg);
     c->tile_inc = (uint64_t*)(base + o_inc);
-    c->tile_flag = (unsigned int*)(base + o_flag);
     c->part = (int64_t*)(base + o_part);
     c->range = (int64_t*)(base + o_range);
-    c->scan_epoch = 0;
     *out = c;
     return GSE_OK;
 }

@@ -97,12 +97,10 @@ struct gse_ctx {
     float* block_sum;         // per-block partial sums of exp(loglik - block max)
     unsigned int* ticket;     // [0]: last-block counter for reductions, [1]: scan tile ticket
     double* red_partials;     // per-block partial moments
-    uint64_t* tile_agg;       // scan: per-tile aggregate
-    uint64_t* tile_inc;       // scan: per-tile inclusive prefix
-    unsigned int* tile_flag;  // scan: (epoch << 2) | state
+    uint64_t* tile_agg;       // scan: sum of every warp's run of tiles
+    uint64_t* tile_inc;       // scan: exclusive offset of every warp's run
     int64_t* part;            // merge-path split points
     int64_t* range;           // [k_lo, k_hi): sources that interleave with a shard's outputs
-    unsigned int scan_epoch;
     const gse_step_params* step_params;   // device block overriding the per-step scalars (CUDA-graph replay), or NULL
     gse_step_params* params_block;        // the context's device block
     gse_step_params* params_ring;         // pinned staging ring (GSE_PARAM_RING slots)

@@ -14,7 +14,8 @@
  *  - every function returns 0 on success, a negative gse_status otherwise; gse_last_error()
  *    returns a thread-local message for the last failure.
  *  - pointers named *_dev are raw DEVICE pointers owned by the caller (the Python side allocates
- *    them as torch tensors); the library allocates nothing but the small per-context workspace.
+ *    them as torch tensors); the library allocates only the per-context workspace, the
+ *    per-context step-parameter block, and what gse_peer_alloc is asked for.
  *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises.
  *  - particle / component state is struct-of-arrays float32: column c of n rows starts at
  *    base + c*ld  (ld = leading dimension in elements, a multiple of 4 so that every column is
@@ -25,7 +26,7 @@
  *    A NULL `loglik` input means "all zero" (the state right after a resample: nothing is read).
  *    `stats_dev` is 4 doubles: [0] = M = max_k loglik_k, [1] = S = sum_k exp(loglik_k - M)
  *    (both written by the update kernels and gse_loglik_max, consumed by scan / moments; the
- *    sharded driver all-reduces them between the two), [2..3] reserved.
+ *    sharded driver merges the shards' pairs in between: gse_peer_allgather_stats), [2..3] reserved.
  *  - resampling is LAZY: gse_resample_search produces the int32 ancestor index `idx` (the
  *    reference's sample_index, particle.py:100 / :314); the kernels that consume the population
  *    next (predict, moments) take `idx_dev` and read row idx[i] of the pre-resample state for
