@@ -37,6 +37,32 @@ def test_struct_layout_matches_header():
         _lib.make_mixture(numpy.zeros((9, 5)), numpy.stack([numpy.eye(5)] * 9), numpy.ones(9))
 
 
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """Compile include/gse.h with gcc and compare every struct's size and field offsets with the ctypes
+    mirrors (the header is plain C: any FFI can consume it)."""
+    import json
+    import shutil
+    import subprocess
+    from gpu_se_b200 import _lib
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    exe = str(tmp_path / "abi_probe")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "abi_probe.c"), "-o", exe], check=True)
+    c = json.loads(subprocess.run([exe], check=True, capture_output=True, text=True).stdout)
+    for name in ("gse_mixture", "gse_shards", "gse_step_params"):
+        cls = getattr(_lib, name)
+        assert ctypes.sizeof(cls) == c["sizeof." + name], name
+        for field, _ in cls._fields_:
+            off, size = c["%s.%s" % (name, field)]
+            f = getattr(cls, field)
+            assert (f.offset, f.size) == (off, size), (name, field)
+    assert c["GSE_ABI_VERSION"] == _lib.GSE_ABI_VERSION
+    assert c["GSE_MAX_SHARDS"] == _lib.GSE_MAX_SHARDS and c["GSE_MAX_ND"] == _lib.GSE_MAX_ND
+    assert c["GSE_MAILBOX_BYTES"] == _lib.GSE_MAILBOX_BYTES and c["GSE_IPC_HANDLE_BYTES"] == _lib.GSE_IPC_HANDLE_BYTES
+
+
 def test_missing_library_fails_loudly(tmp_path, monkeypatch):
     from gpu_se_b200 import _lib
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
