@@ -201,6 +201,7 @@ extern "C" int gse_ctx_create(int device, int model_id, int64_t n_max, const gse
     const size_t o_red = off; off = align_up(off + sizeof(double) * 48 * 2048, 256);
     const size_t o_agg = off; off = align_up(off + sizeof(uint64_t) * c->max_tiles, 256);
     const size_t o_inc = off; off = align_up(off + sizeof(uint64_t) * c->max_tiles, 256);
+    const size_t o_status = off; off = align_up(off + sizeof(uint64_t) * c->max_tiles, 256);
     const size_t o_part = off; off = align_up(off + sizeof(int64_t) * (c->max_tiles + 2), 256);
     const size_t o_range = off; off = align_up(off + sizeof(int64_t) * 8, 256);    // [0..1] range, [4] 1/T
     c->ws_bytes = off;
@@ -224,6 +225,13 @@ extern "C" int gse_ctx_create(int device, int model_id, int64_t n_max, const gse
     c->red_partials = (double*)(base + o_red);
     c->tile_agg = (uint64_t*)(base + o_agg);
     c->tile_inc = (uint64_t*)(base + o_inc);
+    c->tile_status = (uint64_t*)(base + o_status);
+    c->scan_tiles_prev = 0;
+    c->scan_resident_blocks = 0;
+    {
+        const char* mode = getenv("GSE_SCAN");
+        c->scan_single_pass = !(mode && strcmp(mode, "twopass") == 0);
+    }
     c->part = (int64_t*)(base + o_part);
     c->range = (int64_t*)(base + o_range);
     *out = c;

@@ -95,10 +95,14 @@ struct gse_ctx {
     size_t ws_bytes;
     float* block_max;         // per-block partial maxima (update / loglik_max)
     float* block_sum;         // per-block partial sums of exp(loglik - block max)
-    unsigned int* ticket;     // [0]: last-block counter for reductions, [1]: scan tile ticket
+    unsigned int* ticket;     // [0] update reduction, [1] tile sums, [2] moments, [4..6] look-back scan (start ticket, finished, epoch)
     double* red_partials;     // per-block partial moments
     uint64_t* tile_agg;       // scan: sum of every warp's run of tiles
     uint64_t* tile_inc;       // scan: exclusive offset of every warp's run
+    uint64_t* tile_status;    // single-pass scan: one status word per 512-row tile
+    int64_t scan_tiles_prev;  // tiles the previous look-back launch rewrote (0: none yet)
+    int scan_resident_blocks; // co-resident CTAs of the look-back kernel on this device (0: not queried yet)
+    int scan_single_pass;     // use the look-back scan for loglik-only weights (GSE_SCAN=twopass disables)
     int64_t* part;            // merge-path split points
     int64_t* range;           // [k_lo, k_hi): sources that interleave with a shard's outputs
     const gse_step_params* step_params;   // device block overriding the per-step scalars (CUDA-graph replay), or NULL

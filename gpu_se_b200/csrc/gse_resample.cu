@@ -248,6 +248,139 @@ k_weight_scan(const float* __restrict__ loglik, const double* __restrict__ base,
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K3 in one kernel (weights = exp(loglik - M), no float64 base): every block owns one contiguous run of
+// rows; it sums the run (HBM read), chains to the blocks before it with a decoupled look-back, then
+// re-reads the run (L2: a run is ~100 KB) and writes the cumulative weights -- 4 R + 8 W of DRAM
+// traffic, no second launch and no serial last-block pass.  A block publishes ONE 64-bit status word
+// (2 bits state | 8 bits epoch | 54 bits value: the values are < 2^53), so publishing and reading need
+// no fences; warp 0 looks back 32 predecessors at a time (at most gridDim/32 rounds).  Blocks number
+// themselves in the order they start (an atomic ticket), so every block a warp waits for is running.  The epoch
+// lives in device memory and is advanced by the last block to finish, so that the kernel can be
+// replayed from a captured CUDA graph.
+// ------------------------------------------------------------------------------------------------
+#define ST_AGGREGATE 1ull
+#define ST_PREFIX 2ull
+__device__ __forceinline__ uint64_t status_pack(uint64_t state, unsigned int epoch, uint64_t value) {
+    return (state << 62) | ((uint64_t)(epoch & 0xffu) << 54) | value;
+}
+__device__ __forceinline__ uint64_t ld_status(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_status(uint64_t* p, uint64_t v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(TILE_THREADS)
+k_weight_scan_lookback(const float* __restrict__ loglik, const double* __restrict__ stats, int64_t n,
+                       int64_t rows_per_block, uint64_t* status, unsigned int* counters,
+                       uint64_t* __restrict__ cumsum, uint64_t* total_out) {
+    __shared__ unsigned int s_vb, s_epoch;
+    __shared__ uint64_t s_wsum[SCAN_WARPS];
+    __shared__ uint64_t s_excl;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) {
+        s_epoch = *(volatile unsigned int*)(counters + 2);      // advanced only after every block has finished
+        s_vb = atomicAdd(counters, 1u);                         // blocks are numbered in the order they start
+    }
+    __syncthreads();
+    const unsigned int epoch = s_epoch;
+    const int64_t vb = s_vb;
+    const float M = (float)stats[0];
+    const int sexp = quantisation_exponent(stats[1]);
+    const float scale = __int_as_float((127 + sexp) << 23);
+    // this block owns rows [b0, b1), warp w the contiguous sub-run [w0, w1) of it (whole 512-row tiles)
+    const int64_t b0 = vb * rows_per_block, b1 = min(b0 + rows_per_block, n);
+    const int64_t rows_per_warp = rows_per_block / SCAN_WARPS;
+    const int64_t w0 = min(b0 + wid * rows_per_warp, b1), w1 = min(w0 + rows_per_warp, b1);
+    // pass 1: sum of the warp's sub-run (order-free: 128-bit loads)
+    uint64_t sum = 0;
+    {
+        const int64_t full = w0 + ((w1 - w0) & ~(int64_t)127);
+        int64_t row = w0 + 4 * lane;
+#pragma unroll 4
+        for (; row < full; row += 128) {
+            const float4 l = ld_stream4(loglik + row);
+            sum += quantise1<false>(l.x, M, scale) + quantise1<false>(l.y, M, scale) +
+                   quantise1<false>(l.z, M, scale) + quantise1<false>(l.w, M, scale);
+        }
+        for (int r = 0; r < 4; ++r)
+            if (row + r < w1) sum += quantise1<false>(loglik[row + r], M, scale);
+    }
+    sum = warp_sum_u64(sum);
+    if (lane == 0) s_wsum[wid] = sum;
+    __syncthreads();
+    // warp 0: publish the block aggregate, look back over the blocks that started earlier
+    if (wid == 0) {
+        uint64_t agg = 0;
+#pragma unroll
+        for (int w = 0; w < SCAN_WARPS; ++w) agg += s_wsum[w];
+        uint64_t excl = 0;
+        if (vb > 0) {
+            if (lane == 0) st_status(status + vb, status_pack(ST_AGGREGATE, epoch, agg));
+            int64_t pos = vb - 1;                                // lane l looks at block pos - l
+            for (;;) {
+                const int64_t mine = pos - lane;
+                uint64_t word = status_pack(ST_PREFIX, epoch, 0);               // before block 0: prefix 0
+                if (mine >= 0) word = ld_status(status + mine);
+                const bool valid = ((word >> 54) & 0xffull) == (uint64_t)(epoch & 0xffu) && (word >> 62) != 0ull;
+                const unsigned int v_mask = __ballot_sync(0xffffffffu, valid);
+                const unsigned int p_mask = __ballot_sync(0xffffffffu, valid && (word >> 62) == ST_PREFIX);
+                const int first = p_mask ? __ffs(p_mask) - 1 : 32;              // nearest block with a full prefix
+                const unsigned int need = first >= 31 ? 0xffffffffu : ((2u << first) - 1u);
+                if ((v_mask & need) != need) continue;                          // a needed block is not published yet
+                const uint64_t v = (lane <= first) ? (word & ((1ull << 54) - 1ull)) : 0ull;
+                excl += warp_sum_u64(v);
+                if (first < 32) break;
+                pos -= 32;
+            }
+        }
+        if (lane == 0) {
+            st_status(status + vb, status_pack(ST_PREFIX, epoch, excl + agg));
+            s_excl = excl;
+            if (b1 == n && total_out) *total_out = excl + agg;
+        }
+    }
+    __syncthreads();
+    // pass 2: re-read the sub-run (L2), scan inside the warp with a register carry, store
+    uint64_t carry = s_excl;
+#pragma unroll
+    for (int w = 0; w < SCAN_WARPS; ++w) carry += (w < wid) ? s_wsum[w] : 0ull;
+    for (int64_t t0 = w0; t0 < w1; t0 += WTILE_ROWS) {
+        const int64_t row0 = t0 + (int64_t)lane * TILE_ITEMS;
+        uint64_t q[TILE_ITEMS];
+#pragma unroll
+        for (int r = 0; r < TILE_ITEMS; ++r) q[r] = 0;
+        if (row0 < w1) quantise16<true, false>(loglik, NULL, M, sexp, row0, w1, q);
+#pragma unroll
+        for (int r = 1; r < TILE_ITEMS; ++r) q[r] += q[r - 1];
+        const uint64_t incl = warp_inclusive_scan_u64(q[TILE_ITEMS - 1], lane);
+        const uint64_t off = carry + (incl - q[TILE_ITEMS - 1]);
+        if (row0 + TILE_ITEMS <= w1) {
+#pragma unroll
+            for (int v = 0; v < TILE_ITEMS / 4; ++v)
+                st_u64x4(cumsum + row0 + 4 * v, off + q[4 * v], off + q[4 * v + 1], off + q[4 * v + 2], off + q[4 * v + 3]);
+        } else {
+#pragma unroll
+            for (int r = 0; r < TILE_ITEMS; ++r)
+                if (row0 + r < w1) cumsum[row0 + r] = off + q[r];
+        }
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(counters + 1, 1u) == gridDim.x - 1) {      // last block out: reset for the next launch
+            counters[0] = 0u;
+            counters[1] = 0u;
+            counters[2] = epoch + 1u;
+            __threadfence();
+        }
+    }
+}
+
 extern "C" int gse_scan_weights(gse_ctx* ctx, const float* loglik_dev, const double* base_dev,
                                 const double* stats_dev, int64_t n, uint64_t* cumsum_dev,
                                 uint64_t* total_dev, void* stream) {
@@ -259,8 +392,36 @@ extern "C" int gse_scan_weights(gse_ctx* ctx, const float* loglik_dev, const dou
     GSE_REQUIRE(aligned32(cumsum_dev), "cumsum must be 32-byte aligned");
     unsigned g = 0;
     const ScanGeom geo = scan_geometry(n, ctx->num_sms, &g);
-    GSE_REQUIRE(geo.nwarps <= ctx->max_tiles, "workspace too small");
+    GSE_REQUIRE(geo.nwarps <= ctx->max_tiles && geo.ntiles <= ctx->max_tiles, "workspace too small");
     cudaStream_t s = (cudaStream_t)stream;
+    if (loglik_dev && !base_dev && ctx->scan_single_pass) {
+        // status words this context did not rewrite in its previous launch may carry an epoch that has wrapped
+        // around (8 bits) since: clear the ones the tile count grows into
+        if (ctx->scan_resident_blocks == 0) {
+            // every block must be resident at once: warp 0 of a block waits for blocks that have started, and
+            // a block that cannot start while the others spin would never publish its aggregate
+            int per_sm = 0;
+            GSE_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_weight_scan_lookback, TILE_THREADS, 0));
+            GSE_REQUIRE(per_sm >= 1, "look-back scan kernel does not fit an SM");
+            ctx->scan_resident_blocks = per_sm * ctx->num_sms;
+        }
+        // one contiguous run of whole 4096-row groups per block, one wave of blocks
+        const int64_t groups = gse_div_up(n, (int64_t)WTILE_ROWS * SCAN_WARPS);
+        int64_t blocks = groups < ctx->scan_resident_blocks ? groups : ctx->scan_resident_blocks;
+        const int64_t rows_per_block = gse_div_up(groups, blocks) * WTILE_ROWS * SCAN_WARPS;
+        blocks = gse_div_up(n, rows_per_block);
+        // status words this context did not rewrite in its previous launch may carry an epoch that has wrapped
+        // around (8 bits) since: clear the ones the block count grows into
+        if (blocks > ctx->scan_tiles_prev)
+            GSE_CHECK_CUDA(cudaMemsetAsync(ctx->tile_status + ctx->scan_tiles_prev, 0,
+                                           sizeof(uint64_t) * (size_t)(blocks - ctx->scan_tiles_prev), s));
+        ctx->scan_tiles_prev = blocks;
+        k_weight_scan_lookback<<<(unsigned)blocks, TILE_THREADS, 0, s>>>(loglik_dev, stats_dev, n, rows_per_block,
+                                                                          ctx->tile_status, ctx->ticket + 4, cumsum_dev,
+                                                                          total_dev);
+        GSE_CHECK_LAUNCH(ctx);
+        return GSE_OK;
+    }
 #define LAUNCH_SCAN(LL, BASE)                                                                                   \
     do {                                                                                                        \
         k_weight_tile_sums<LL, BASE><<<g, TILE_THREADS, 0, s>>>(loglik_dev, base_dev, stats_dev, n, geo,        \
