@@ -50,9 +50,9 @@ def workload_name(log2n):
 
 # DRAM traffic per launch of each kernel at 2^24 particles (dram__bytes_read.sum + dram__bytes_write.sum of
 # the committed `ncu --set full` capture, profiles/r1_final_pf_step_2p24_ncu_full.csv), in bytes per row
-NCU_TRAFFIC_BYTES_PER_ROW = {"predict": (335.75e6 + 303.09e6) / 2 ** 24, "update": (134.23e6 + 31.21e6) / 2 ** 24,
-                             "scan": (67.13e6 + 0.72e6 + 67.18e6 + 86.73e6) / 2 ** 24,
-                             "search": (72.15e6 + 1.85e6 + 134.33e6 + 43.07e6) / 2 ** 24}
+NCU_TRAFFIC_BYTES_PER_ROW = {"predict": (335.75e6 + 302.81e6) / 2 ** 24, "update": (134.23e6 + 30.44e6) / 2 ** 24,
+                             "scan": (110.59e6 + 84.81e6) / 2 ** 24,
+                             "search": (72.14e6 + 1.71e6 + 134.33e6 + 46.80e6) / 2 ** 24}
 
 
 def parse_args():
