@@ -227,6 +227,10 @@ extern "C" int gse_ctx_create(int device, int model_id, int64_t n_max, const gse
     c->tile_inc = (uint64_t*)(base + o_inc);
     c->tile_status = (uint64_t*)(base + o_status);
     c->scan_tiles_prev = 0;
+    {
+        const char* v = getenv("GSE_UPDATE_CTAS");
+        c->update_ctas_per_sm = (v && atoi(v) >= 1 && atoi(v) <= 32) ? atoi(v) : 8;
+    }
     c->scan_resident_blocks = 0;
     {
         const char* mode = getenv("GSE_SCAN");

@@ -102,6 +102,7 @@ struct gse_ctx {
     uint64_t* tile_status;    // single-pass scan: one status word per 512-row tile
     int64_t scan_tiles_prev;  // tiles the previous look-back launch rewrote (0: none yet)
     int scan_resident_blocks; // co-resident CTAs of the look-back kernel on this device (0: not queried yet)
+    int update_ctas_per_sm;   // persistent grid of the update kernel (8; GSE_UPDATE_CTAS overrides, for tuning)
     int scan_single_pass;     // use the look-back scan for loglik-only weights (GSE_SCAN=twopass disables)
     int64_t* part;            // merge-path split points
     int64_t* range;           // [k_lo, k_hi): sources that interleave with a shard's outputs

@@ -291,7 +291,7 @@ extern "C" int gse_pf_update(gse_ctx* ctx, const float* x_dev, int64_t ld, int64
     (void)u;   // static_outputs ignores u (BioreactorModel.py:250)
     const int64_t groups = gse_div_up(n, ROWS_PER_THREAD);
     int64_t nblk = gse_div_up(groups, PF_THREADS);
-    if (nblk > (int64_t)ctx->num_sms * 8) nblk = (int64_t)ctx->num_sms * 8;      // persistent: 8 CTAs of 256 per SM
+    if (nblk > (int64_t)ctx->num_sms * ctx->update_ctas_per_sm) nblk = (int64_t)ctx->num_sms * ctx->update_ctas_per_sm;   // persistent grid
     const unsigned blocks = (unsigned)nblk;
     GSE_REQUIRE((int64_t)blocks <= ctx->max_blocks, "workspace too small");
     const float z0h = (float)z[0], z1h = (float)z[1];
