@@ -152,7 +152,9 @@ class ShardedParticleFilter:
     """``ParallelParticleFilter`` over all ranks of ``group``: same constructor and
     ``predict / update / resample / point_estimate / point_covariance`` calls, every rank calling
     each method collectively with identical arguments.  ``N_particles`` is the GLOBAL count;
-    ``particles`` / ``weights`` are this rank's shard."""
+    ``particles`` / ``weights`` are this rank's shard.  "Collectively" includes the ``particles``
+    attribute: reading it applies a pending resample, which flips the state buffers every rank's
+    kernels read, so all ranks must do it at the same point of the call sequence."""
 
     def __init__(self, f, g, N_particles, x0, state_pdf, measurement_pdf, *, device=None, seed=0, n_sub=1,
                  group=None, particles=None, exchange="peer"):
