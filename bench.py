@@ -37,10 +37,11 @@ U_NOMINAL = numpy.array([0.06, 0.2])
 # algorithmic bytes per particle and stage (SURVEY.md §8(d) re-cut for the lazy resample --
 # predict reads its rows through the int32 ancestor index, so K5's gather rides inside K1):
 #   predict 4 R idx + 20 R + 20 W, update 8 R + 4 W, scan 4 R + 8 W, search 8 R + 4 W
-STAGE_BYTES = {"predict": 44, "update": 12, "scan": 12, "search": 12}
+#   fused resample: 4 R loglik + 4 W ancestor index (the cumulative weights stay on chip); two-stage (GSE_RESAMPLE=unfused and
+#   the sharded path): scan 4 R + 8 W, search 8 R + 4 W
+STAGE_BYTES = {"predict": 44, "update": 12, "resample": 8, "scan": 12, "search": 12}
 # sharded run: the same, plus the all-gather of the shard totals ("offsets", no HBM traffic to speak of)
 STAGE_BYTES_SHARDED = {"predict": 44, "update": 12, "scan": 12, "offsets": 0, "search": 12}
-STEP_BYTES = sum(STAGE_BYTES.values())          # 80 B per particle-step (SURVEY §8(d) counted 128 B with a materialised gather)
 
 
 def workload_name(log2n):
@@ -291,6 +292,8 @@ def run_ours(args):
         pf = g.ParticleFilter(f, gg, n_total, x0, state, meas, device=dev, seed=1234)
     if args.graphs:
         pf.enable_graphs()
+    from gpu_se_b200.filter import _base
+    two_stage = (world > 1 or args.sharded) or not _base.FUSED_RESAMPLE
 
     K, W = args.steps, max(args.warmup, 3)
     us, zs = trajectory(2 * (K + W), seed=7)
@@ -325,7 +328,7 @@ def run_ours(args):
         pf.resample(r=float(rs[k]))
         pf._stage_hook = None
         if record:
-            hook("search")
+            hook("search" if two_stage else "resample")
 
     for k in range(W):
         step(k, False)
@@ -385,8 +388,8 @@ def run_ours(args):
     peak, peak_src = measured_peak_gbs()
     STAGE_BYTES = globals()["STAGE_BYTES_SHARDED" if world > 1 else "STAGE_BYTES"]
     if args.workload == "gsf":      # 20 floats per component, lazy resample
-        STAGE_BYTES = {"predict": 4 + 80 + 80, "update": 80 + 80 + 4, "scan": 12, "search": 12}
-    STEP_BYTES = sum(STAGE_BYTES.values())
+        STAGE_BYTES = {"predict": 4 + 80 + 80, "update": 80 + 80 + 4, "resample": 8, "scan": 12, "search": 12}
+    STEP_BYTES = sum(v for k, v in STAGE_BYTES.items() if k in stage_avg) if stage_avg else 64
     value = n_total * K / (dev_ms * 1e-3)
     dom = max(stage_avg, key=stage_avg.get) if stage_avg else "predict"
     dom_ms = stage_avg.get(dom, dev_ms / K)

@@ -9,7 +9,7 @@ import os
 
 GSE_NX, GSE_NU, GSE_NY, GSE_NSIGMA, GSE_NCOV, GSE_MAX_ND = 5, 2, 2, 11, 15, 8
 GSE_MODEL_BIOREACTOR = 1
-GSE_ABI_VERSION = 4
+GSE_ABI_VERSION = 5
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgse_b200.so")
 
@@ -29,6 +29,7 @@ class gse_mixture(ctypes.Structure):
                 ("covs", ctypes.c_double * (GSE_MAX_ND * GSE_NX * GSE_NX))]
 
 
+GSE_ERR_CHOLESKY, GSE_ERR_SINGULAR_PYY, GSE_ERR_PEER_TIMEOUT, GSE_ERR_QUEUE_OVERFLOW, GSE_ERR_ZERO_WEIGHTS = 1, 2, 4, 8, 16
 GSE_MAX_SHARDS, GSE_IPC_HANDLE_BYTES = 8, 64
 GSE_MAILBOX_BYTES = 2 * GSE_MAX_SHARDS * 64
 
@@ -64,6 +65,9 @@ SIGNATURES = {
     "gse_weights_linear": (c_int, [c_vp, c_vp, c_vp, c_i64, c_dbl, c_vp, c_vp]),
     "gse_scan_weights": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "gse_resample_search": (c_int, [c_vp, c_vp, c_i64, c_vp, c_dbl, c_i64, c_i64, c_i64, c_vp, c_vp]),
+    "gse_resample_fused": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_dbl, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "gse_resample_search_f64": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_dbl, c_i64, c_i64, c_i64, c_vp, c_vp]),
+    "gse_ctx_errors": (ctypes.c_uint, [c_vp, c_int]),
     "gse_gather_rows": (c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_vp]),
     "gse_peer_alloc": (c_int, [c_int, c_i64, ctypes.POINTER(c_vp), ctypes.c_char_p]),
     "gse_peer_free": (c_int, [c_int, c_vp]),

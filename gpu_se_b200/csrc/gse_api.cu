@@ -165,7 +165,7 @@ extern "C" int gse_ctx_create(int device, int model_id, int64_t n_max, const gse
     int ndev = 0;
     GSE_CHECK_CUDA(cudaGetDeviceCount(&ndev));
     GSE_REQUIRE(device >= 0 && device < ndev, "device index out of range");
-    GSE_CHECK_CUDA(cudaSetDevice(device));
+    gse_device_guard guard(device);
     cudaDeviceProp prop;
     GSE_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) {
@@ -197,13 +197,19 @@ extern "C" int gse_ctx_create(int device, int model_id, int64_t n_max, const gse
     size_t off = 0;
     const size_t o_bmax = off; off = align_up(off + sizeof(float) * c->max_blocks, 256);
     const size_t o_bsum = off; off = align_up(off + sizeof(float) * c->max_blocks, 256);
-    const size_t o_tick = off; off = align_up(off + sizeof(unsigned int) * 8, 256);
+    const size_t o_tick = off; off = align_up(off + sizeof(unsigned int) * 16, 256);
     const size_t o_red = off; off = align_up(off + sizeof(double) * 48 * 2048, 256);
     const size_t o_agg = off; off = align_up(off + sizeof(uint64_t) * c->max_tiles, 256);
     const size_t o_inc = off; off = align_up(off + sizeof(uint64_t) * c->max_tiles, 256);
     const size_t o_status = off; off = align_up(off + sizeof(uint64_t) * c->max_tiles, 256);
     const size_t o_part = off; off = align_up(off + sizeof(int64_t) * (c->max_tiles + 2), 256);
     const size_t o_range = off; off = align_up(off + sizeof(int64_t) * 8, 256);    // [0..1] range, [4] 1/T
+    // fused resample: one status word per co-resident CTA (<= 32 per SM); queue of heavy runs -- every entry covers
+    // more than 4096 outputs of its own, cut into pieces of <= 65536 (gse_resample_fused.cu)
+    const size_t n_fused_status = 32 * 256;
+    c->heavy_queue_cap = (int)(n_max / 4096 + n_max / 65536 + 64);
+    const size_t o_fstatus = off; off = align_up(off + sizeof(uint64_t) * n_fused_status, 256);
+    const size_t o_queue = off; off = align_up(off + sizeof(int4) * (size_t)c->heavy_queue_cap, 256);
     c->ws_bytes = off;
     cudaError_t e = cudaMalloc(&c->ws, c->ws_bytes);
     if (e != cudaSuccess) {
@@ -238,14 +244,34 @@ extern "C" int gse_ctx_create(int device, int model_id, int64_t n_max, const gse
     }
     c->part = (int64_t*)(base + o_part);
     c->range = (int64_t*)(base + o_range);
+    c->fused_status = (uint64_t*)(base + o_fstatus);
+    c->heavy_queue = (int4*)(base + o_queue);
+    {
+        const char* v = getenv("GSE_FUSED_ITEMS");
+        c->fused_items = (v && atoi(v) == 16) ? 16 : 8;
+    }
+    // device-error word: host-mapped so that reading it never needs a copy or a synchronisation of its own
+    e = cudaHostAlloc((void**)&c->err_host, 64, cudaHostAllocMapped);
+    if (e == cudaSuccess) {
+        memset(c->err_host, 0, 64);
+        e = cudaHostGetDevicePointer((void**)&c->err_dev, c->err_host, 0);
+    }
+    if (e != cudaSuccess) {
+        gse_set_error("allocating the device-error word failed: %s", cudaGetErrorString(e));
+        if (c->err_host) cudaFreeHost(c->err_host);
+        cudaFree(c->ws);
+        free(c);
+        return GSE_ECUDA;
+    }
     *out = c;
     return GSE_OK;
 }
 
 extern "C" int gse_ctx_destroy(gse_ctx* ctx) {
     if (!ctx) return GSE_OK;
-    cudaSetDevice(ctx->device);
+    gse_device_guard guard(ctx->device);
     if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->err_host) cudaFreeHost(ctx->err_host);
     if (ctx->params_block) {
         cudaFree(ctx->params_block);
         cudaFreeHost(ctx->params_ring);
@@ -259,7 +285,7 @@ extern "C" int gse_ctx_destroy(gse_ctx* ctx) {
 extern "C" int gse_peer_alloc(int device, int64_t bytes, void** ptr_out, unsigned char handle_out[GSE_IPC_HANDLE_BYTES]) {
     GSE_REQUIRE(ptr_out != NULL && handle_out != NULL && bytes > 0, "bad arguments");
     static_assert(sizeof(cudaIpcMemHandle_t) == GSE_IPC_HANDLE_BYTES, "IPC handle size");
-    GSE_CHECK_CUDA(cudaSetDevice(device));
+    gse_device_guard guard(device);
     void* p = NULL;
     GSE_CHECK_CUDA(cudaMalloc(&p, (size_t)bytes));
     cudaError_t e = cudaMemset(p, 0, (size_t)bytes);
@@ -277,14 +303,14 @@ extern "C" int gse_peer_alloc(int device, int64_t bytes, void** ptr_out, unsigne
 
 extern "C" int gse_peer_free(int device, void* ptr) {
     if (!ptr) return GSE_OK;
-    GSE_CHECK_CUDA(cudaSetDevice(device));
+    gse_device_guard guard(device);
     GSE_CHECK_CUDA(cudaFree(ptr));
     return GSE_OK;
 }
 
 extern "C" int gse_peer_open(int device, const unsigned char handle[GSE_IPC_HANDLE_BYTES], void** ptr_out) {
     GSE_REQUIRE(ptr_out != NULL && handle != NULL, "bad arguments");
-    GSE_CHECK_CUDA(cudaSetDevice(device));
+    gse_device_guard guard(device);
     cudaIpcMemHandle_t h;
     memcpy(&h, handle, GSE_IPC_HANDLE_BYTES);
     GSE_CHECK_CUDA(cudaIpcOpenMemHandle(ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
@@ -293,15 +319,15 @@ extern "C" int gse_peer_open(int device, const unsigned char handle[GSE_IPC_HAND
 
 extern "C" int gse_peer_close(int device, void* ptr) {
     if (!ptr) return GSE_OK;
-    GSE_CHECK_CUDA(cudaSetDevice(device));
+    gse_device_guard guard(device);
     GSE_CHECK_CUDA(cudaIpcCloseMemHandle(ptr));
     return GSE_OK;
 }
 
 extern "C" int gse_ctx_upload_step_params(gse_ctx* ctx, const gse_step_params* values, void* stream) {
     GSE_REQUIRE(ctx != NULL && values != NULL, "ctx / values is NULL");
+    gse_device_guard guard(ctx->device);
     if (!ctx->params_block) {
-        GSE_CHECK_CUDA(cudaSetDevice(ctx->device));
         GSE_CHECK_CUDA(cudaMalloc((void**)&ctx->params_block, sizeof(gse_step_params)));
         GSE_CHECK_CUDA(cudaHostAlloc((void**)&ctx->params_ring, sizeof(gse_step_params) * GSE_PARAM_RING, cudaHostAllocDefault));
         for (int q = 0; q < 4; ++q) GSE_CHECK_CUDA(cudaEventCreateWithFlags(&ctx->params_event[q], cudaEventDisableTiming));
@@ -329,6 +355,21 @@ extern "C" int gse_ctx_use_step_params(gse_ctx* ctx, int enable) {
 }
 
 extern "C" int64_t gse_launch_count(const gse_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" unsigned int gse_ctx_errors(gse_ctx* ctx, int clear) {
+    if (!ctx || !ctx->err_host) return 0u;
+    const unsigned int bits = *(volatile unsigned int*)ctx->err_host;
+    if (bits) {
+        gse_set_error("device-side error(s):%s%s%s%s%s",
+                      (bits & GSE_ERR_CHOLESKY) ? " [covariance not positive definite (Cholesky failed after the +1e-10 I retry)]" : "",
+                      (bits & GSE_ERR_SINGULAR_PYY) ? " [innovation covariance P_yy singular]" : "",
+                      (bits & GSE_ERR_PEER_TIMEOUT) ? " [peer mailbox exchange timed out: a rank died or issued its calls in another order]" : "",
+                      (bits & GSE_ERR_QUEUE_OVERFLOW) ? " [resample heavy-run queue overflow]" : "",
+                      (bits & GSE_ERR_ZERO_WEIGHTS) ? " [resample of all-zero weights]" : "");
+        if (clear) *(volatile unsigned int*)ctx->err_host = 0u;
+    }
+    return bits;
+}
 
 // Host evaluation of the device's output-count predicate (see gse_common.cuh): number of outputs
 // i in [0, n_total) with q*(u_i) <= bound, i.e. those sourced at or below cumulative weight `bound`.

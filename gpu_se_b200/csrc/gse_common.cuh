@@ -95,15 +95,23 @@ struct gse_ctx {
     size_t ws_bytes;
     float* block_max;         // per-block partial maxima (update / loglik_max)
     float* block_sum;         // per-block partial sums of exp(loglik - block max)
-    unsigned int* ticket;     // [0] update reduction, [1] tile sums, [2] moments, [4..6] look-back scan (start ticket, finished, epoch)
+    unsigned int* ticket;     // [0] update reduction, [1] tile sums, [2] moments, [4..6] look-back scan (start ticket, finished,
+                              // epoch), [8..11] fused resample (start ticket, past phase 3, queue length, past the drain)
     double* red_partials;     // per-block partial moments
     uint64_t* tile_agg;       // scan: sum of every warp's run of tiles
     uint64_t* tile_inc;       // scan: exclusive offset of every warp's run
-    uint64_t* tile_status;    // single-pass scan: one status word per 512-row tile
+    uint64_t* tile_status;    // single-pass kernels: one status word per CTA (look-back scan, fused resample)
     int64_t scan_tiles_prev;  // tiles the previous look-back launch rewrote (0: none yet)
     int scan_resident_blocks; // co-resident CTAs of the look-back kernel on this device (0: not queried yet)
     int update_ctas_per_sm;   // persistent grid of the update kernel (8; GSE_UPDATE_CTAS overrides, for tuning)
     int scan_single_pass;     // use the look-back scan for loglik-only weights (GSE_SCAN=twopass disables)
+    uint64_t* fused_status;   // fused resample: one aggregate word per CTA, zero between launches
+    int4* heavy_queue;        // fused resample: runs of one heavy source handed to the whole grid (start, end, ancestor)
+    int heavy_queue_cap;
+    int fused_resident[12];   // co-resident CTAs of each k_resample_fused instantiation (0: not queried yet)
+    int fused_items;          // rows per lane and tile of the fused kernel (8; GSE_FUSED_ITEMS=16 for tuning)
+    unsigned int* err_host;   // device-error word: pinned, mapped host memory the kernels OR their GSE_ERR_* bits into
+    unsigned int* err_dev;    // its device alias
     int64_t* part;            // merge-path split points
     int64_t* range;           // [k_lo, k_hi): sources that interleave with a shard's outputs
     const gse_step_params* step_params;   // device block overriding the per-step scalars (CUDA-graph replay), or NULL
@@ -120,6 +128,19 @@ int gse_build_density2(const gse_mixture* m, MixDensity2* out);
 int gse_build_densityN(const gse_mixture* m, MixDensityN* out);
 
 #define GSE_PARAM_RING 1024
+
+// Every entry point that launches, allocates or frees selects the context's device for the duration of the call and
+// restores the caller's current device on the way out (a filter may live on a device other than the current one).
+struct gse_device_guard {
+    int prev;
+    bool switched;
+    explicit gse_device_guard(int device) : prev(-1), switched(false) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != device) switched = (cudaSetDevice(device) == cudaSuccess);
+    }
+    ~gse_device_guard() {
+        if (switched) cudaSetDevice(prev);
+    }
+};
 
 static inline int64_t gse_div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
@@ -561,6 +582,12 @@ __device__ __forceinline__ void block_max_sumexp_finalize(const float vals[NV], 
     MaxSumExp acc;
     acc.add<NV>(vals, valid);
     block_merge_max_sumexp<THREADS>(acc.m, acc.s, block_max, block_sum, ticket, stats);
+}
+
+__device__ __forceinline__ unsigned int ld_status32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 
 __device__ __forceinline__ int shard_of(const GatherShards& g, int64_t k) {

@@ -81,6 +81,7 @@ k_gsf_sigma_points(const float* __restrict__ mean, const float* __restrict__ cov
 extern "C" int gse_gsf_sigma_points(gse_ctx* ctx, const float* mean_dev, const float* cov_dev, int64_t ld,
                                     int64_t n, float* out_dev, int64_t ld_out, void* stream) {
     GSE_REQUIRE(ctx != NULL && mean_dev != NULL && cov_dev != NULL && out_dev != NULL, "NULL argument");
+    gse_device_guard guard(ctx->device);
     GSE_REQUIRE(n >= 1 && ld >= n && ld_out >= n, "n / ld out of range");
     k_gsf_sigma_points<<<(unsigned)gse_div_up(n, GSF_THREADS), GSF_THREADS, 0, (cudaStream_t)stream>>>(
         mean_dev, cov_dev, ld, n, out_dev, ld_out);
@@ -164,6 +165,7 @@ extern "C" int gse_gsf_predict(gse_ctx* ctx, const float* mean_src_dev, const fl
                                const float* noise_dev, int64_t ld_noise, void* stream) {
     GSE_REQUIRE(ctx != NULL && u != NULL && mean_dev != NULL && cov_dev != NULL && mean_src_dev != NULL &&
                 cov_src_dev != NULL, "NULL argument");
+    gse_device_guard guard(ctx->device);
     GSE_REQUIRE(n >= 1 && n <= ctx->n_max && ld >= n, "n / ld out of range");
     GSE_REQUIRE(idx_dev == NULL || mean_src_dev != mean_dev, "a gathering predict cannot run in place");
     GSE_REQUIRE(idx_dev != NULL || ld_src >= n, "ld_src too small");
@@ -281,6 +283,7 @@ extern "C" int gse_gsf_update(gse_ctx* ctx, float* mean_dev, float* cov_dev, int
                               const float* loglik_in_dev, float* loglik_dev, const double u[GSE_NU], const double z[GSE_NY],
                               double* stats_dev, void* stream) {
     GSE_REQUIRE(ctx != NULL && z != NULL && mean_dev != NULL && cov_dev != NULL && loglik_dev != NULL && stats_dev != NULL, "NULL argument");
+    gse_device_guard guard(ctx->device);
     GSE_REQUIRE(n >= 1 && n <= ctx->n_max && ld >= n, "n / ld out of range");
     (void)u;
     const unsigned blocks = (unsigned)gse_div_up(n, GSF_THREADS);

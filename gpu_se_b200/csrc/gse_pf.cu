@@ -38,6 +38,7 @@ k_mixture_draw(float* __restrict__ x, int64_t ld, int64_t n, const __grid_consta
 extern "C" int gse_mixture_draw(gse_ctx* ctx, const gse_mixture* mix, float* x_dev, int64_t ld, int64_t n,
                                 uint64_t seed, uint64_t step, int64_t index0, void* stream) {
     GSE_REQUIRE(ctx != NULL, "ctx is NULL");
+    gse_device_guard guard(ctx->device);
     GSE_REQUIRE(n >= 0, "n < 0");
     if (n == 0) return GSE_OK;
     CHECK_SOA(x_dev, ld, n);
@@ -170,6 +171,7 @@ static int launch_predict(gse_ctx* ctx, const float* x_src_dev, int64_t ld_src, 
                           const double u[GSE_NU], double dt, int n_sub, uint64_t seed, uint64_t step, int64_t index0,
                           const float* noise_dev, int64_t ld_noise, void* stream) {
     GSE_REQUIRE(ctx != NULL && u != NULL, "ctx / u is NULL");
+    gse_device_guard guard(ctx->device);
     GSE_REQUIRE(n >= 0 && n <= ctx->n_max, "n out of range for this context");
     GSE_REQUIRE(n_sub >= 1, "n_sub must be >= 1");
     if (n == 0) return GSE_OK;
@@ -284,6 +286,7 @@ extern "C" int gse_pf_update(gse_ctx* ctx, const float* x_dev, int64_t ld, int64
                              float* loglik_dev, const double u[GSE_NU], const double z[GSE_NY], double* stats_dev,
                              void* stream) {
     GSE_REQUIRE(ctx != NULL && z != NULL && stats_dev != NULL, "ctx / z / stats is NULL");
+    gse_device_guard guard(ctx->device);
     GSE_REQUIRE(n >= 1 && n <= ctx->n_max, "n out of range for this context");
     CHECK_SOA(x_dev, ld, n);
     GSE_REQUIRE(loglik_dev != NULL && aligned16(loglik_dev), "loglik must be 16-byte aligned");
@@ -334,6 +337,7 @@ k_loglik_max(const float* __restrict__ loglik, int64_t n, float* block_max, floa
 
 extern "C" int gse_loglik_max(gse_ctx* ctx, const float* loglik_dev, int64_t n, double* stats_dev, void* stream) {
     GSE_REQUIRE(ctx != NULL && stats_dev != NULL, "ctx / stats is NULL");
+    gse_device_guard guard(ctx->device);
     GSE_REQUIRE(n >= 1 && n <= ctx->n_max, "n out of range for this context");
     GSE_REQUIRE(loglik_dev != NULL && aligned16(loglik_dev), "loglik must be 16-byte aligned");
     int64_t nblk = gse_div_up(gse_div_up(n, ROWS_PER_THREAD), PF_THREADS);
@@ -426,6 +430,7 @@ static int build_mailboxes(void* const boxes[GSE_MAX_SHARDS], int rank, int nsha
 extern "C" int gse_peer_allgather_stats(gse_ctx* ctx, void* const mailboxes[GSE_MAX_SHARDS], int rank, int nshards,
                                         unsigned int epoch, double* stats_dev, void* stream) {
     GSE_REQUIRE(ctx != NULL && stats_dev != NULL && epoch != 0, "bad arguments");
+    gse_device_guard guard(ctx->device);
     MailboxTable mb;
     int rc = build_mailboxes(mailboxes, rank, nshards, &mb);
     if (rc) return rc;
@@ -438,6 +443,7 @@ extern "C" int gse_peer_allgather_totals(gse_ctx* ctx, void* const mailboxes[GSE
                                          unsigned int epoch, const uint64_t* total_dev, uint64_t* offsets_dev,
                                          void* stream) {
     GSE_REQUIRE(ctx != NULL && total_dev != NULL && offsets_dev != NULL && epoch != 0, "bad arguments");
+    gse_device_guard guard(ctx->device);
     MailboxTable mb;
     int rc = build_mailboxes(mailboxes, rank, nshards, &mb);
     if (rc) return rc;
@@ -461,6 +467,7 @@ __global__ void k_merge_stats(const double* __restrict__ pairs, int nshards, dou
 
 extern "C" int gse_merge_stats(gse_ctx* ctx, const double* pairs_dev, int nshards, double* stats_dev, void* stream) {
     GSE_REQUIRE(ctx != NULL && pairs_dev != NULL && stats_dev != NULL && nshards >= 1, "bad arguments");
+    gse_device_guard guard(ctx->device);
     k_merge_stats<<<1, 32, 0, (cudaStream_t)stream>>>(pairs_dev, nshards, stats_dev);
     GSE_CHECK_LAUNCH(ctx);
     return GSE_OK;
@@ -482,6 +489,7 @@ __global__ void k_weights_linear(const float* __restrict__ loglik, const double*
 extern "C" int gse_weights_linear(gse_ctx* ctx, const float* loglik_dev, const double* base_dev, int64_t n,
                                   double scale, double* out_dev, void* stream) {
     GSE_REQUIRE(ctx != NULL && out_dev != NULL, "ctx / out is NULL");
+    gse_device_guard guard(ctx->device);
     GSE_REQUIRE(n >= 0, "n < 0");
     if (n == 0) return GSE_OK;
     k_weights_linear<<<(unsigned)gse_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(loglik_dev, base_dev, n, scale, out_dev);
@@ -696,6 +704,7 @@ static int launch_moments(gse_ctx* ctx, const float* x, const float* extra, int6
                           const int32_t* idx, const GatherShards* shards, bool mean_only, const float* loglik, const double* base, const double* stats, double* out,
                           void* stream) {
     GSE_REQUIRE(ctx != NULL && stats != NULL && out != NULL, "ctx / stats / out is NULL");
+    gse_device_guard guard(ctx->device);
     GSE_REQUIRE(n >= 1 && n <= ctx->n_max, "n out of range for this context");
     if (idx == NULL) { CHECK_SOA(x, ld, n); }
     GatherShards none;
@@ -787,6 +796,7 @@ __global__ void k_mixture_pdf(const float* __restrict__ x, int64_t ld, int64_t n
 extern "C" int gse_mixture_pdf(gse_ctx* ctx, const gse_mixture* mix, const float* x_dev, int64_t ld, int64_t n,
                                double* out_dev, int log_out, void* stream) {
     GSE_REQUIRE(ctx != NULL && x_dev != NULL && out_dev != NULL, "ctx / x / out is NULL");
+    gse_device_guard guard(ctx->device);
     GSE_REQUIRE(n >= 0 && ld >= n, "n / ld out of range");
     if (n == 0) return GSE_OK;
     MixDensityN md;

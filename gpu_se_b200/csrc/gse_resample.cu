@@ -5,37 +5,15 @@
 // addition is associative, so the cumulative weights are independent of the scan structure, the
 // launch geometry and the number of GPUs, and every comparison below is exact.
 //
-// The scan is reduce-then-scan (per-warp run sums -> offsets -> in-run scan) rather than a single
-// pass with look-back: both kernels are pure streaming kernels with no inter-block waiting.
-#include "gse_common.cuh"
+// Two scans: the single-pass look-back kernel (k_weight_scan_lookback, the default for weights without a float64
+// base) and reduce-then-scan (k_weight_tile_sums + k_weight_scan: per-warp run sums -> offsets -> in-run scan).
+// The filters' resample() itself runs the fused kernel of gse_resample_fused.cu; the kernels here serve the
+// stand-alone ABI entry points (gse_scan_weights, gse_resample_search), the slab exchange and the sharded search.
+#include "gse_resample_common.cuh"
 
 #define TILE_THREADS 256
 #define TILE_ITEMS 16
 #define TILE_ROWS (TILE_THREADS * TILE_ITEMS)      // 4096 rows per tile
-
-static inline bool aligned32(const void* p) { return ((uintptr_t)p & 31u) == 0; }
-
-__device__ __forceinline__ void ld_f32x8(const float* p, float v[8]) {
-    asm volatile("ld.global.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
-                 : "l"(p));
-}
-__device__ __forceinline__ void ld_f64x4(const double* p, double v[4]) {
-    asm volatile("ld.global.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
-                 : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
-}
-__device__ __forceinline__ void st_u64x4(uint64_t* p, uint64_t a, uint64_t b, uint64_t c, uint64_t d) {
-    asm volatile("st.global.L1::no_allocate.v4.u64 [%0], {%1,%2,%3,%4};"
-                 :: "l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
-}
-
-// scale = 2^(52 - e) with S <= 2^e: the quantised weights sum to at most 2^52 + n/2 < 2^53
-__device__ __forceinline__ int quantisation_exponent(double S) {
-    if (!(S > 0.0) || !isfinite(S)) return 0;
-    int e;
-    frexp(S, &e);
-    return GSE_TOTAL_BITS - e;
-}
 
 // q = rint(exp(l - M) * 2^sexp): the one expression both passes (K3a, K3b) evaluate, with explicit
 // round-to-nearest operations so that no contraction can make them differ
@@ -90,20 +68,6 @@ __device__ __forceinline__ void quantise16(const float* __restrict__ loglik, con
             q[r] = __double2ull_rn(w * scale);
         }
     }
-}
-
-__device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-__device__ __forceinline__ uint64_t warp_inclusive_scan_u64(uint64_t v, int lane) {
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint64_t t = __shfl_up_sync(0xffffffffu, v, o);
-        if (lane >= o) v += t;
-    }
-    return v;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -259,20 +223,6 @@ k_weight_scan(const float* __restrict__ loglik, const double* __restrict__ base,
 // lives in device memory and is advanced by the last block to finish, so that the kernel can be
 // replayed from a captured CUDA graph.
 // ------------------------------------------------------------------------------------------------
-#define ST_AGGREGATE 1ull
-#define ST_PREFIX 2ull
-__device__ __forceinline__ uint64_t status_pack(uint64_t state, unsigned int epoch, uint64_t value) {
-    return (state << 62) | ((uint64_t)(epoch & 0xffu) << 54) | value;
-}
-__device__ __forceinline__ uint64_t ld_status(const uint64_t* p) {
-    uint64_t v;
-    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_status(uint64_t* p, uint64_t v) {
-    asm volatile("st.volatile.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
-}
-
 __global__ void __launch_bounds__(TILE_THREADS)
 k_weight_scan_lookback(const float* __restrict__ loglik, const double* __restrict__ stats, int64_t n,
                        int64_t rows_per_block, uint64_t* status, unsigned int* counters,
@@ -385,6 +335,7 @@ extern "C" int gse_scan_weights(gse_ctx* ctx, const float* loglik_dev, const dou
                                 const double* stats_dev, int64_t n, uint64_t* cumsum_dev,
                                 uint64_t* total_dev, void* stream) {
     GSE_REQUIRE(ctx != NULL && stats_dev != NULL && cumsum_dev != NULL, "ctx / stats / cumsum is NULL");
+    gse_device_guard guard(ctx->device);
     GSE_REQUIRE(n >= 1 && n <= ctx->n_max, "n out of range for this context");
     GSE_REQUIRE(loglik_dev != NULL || base_dev != NULL, "need loglik or base weights");
     GSE_REQUIRE(loglik_dev == NULL || aligned32(loglik_dev), "loglik must be 32-byte aligned");
@@ -625,18 +576,6 @@ __device__ __forceinline__ double sample_pos(const ResampleArgs& a, double di) {
     return gse_sample_position(di, offset_r(a), a.n_total, a.inv_n, POW2);
 }
 
-// first global output index i in [dbase, dend] with u_i > g = fl(cd / Td), starting from a guess.
-// Out of line and fed with scalars only: passing the argument struct would make every thread spill it.
-template <bool POW2>
-__device__ __noinline__ double rank_exact(double r, double n_total, double inv_n, double cd, double Td, double di,
-                                          double dbase, double dend) {
-    const double g = __ddiv_rn(cd, Td);                            // cumsum / cumsum[-1]   (:90)
-    di = fmin(fmax(di, dbase), dend);
-    while (di > dbase && gse_sample_position(di - 1.0, r, n_total, inv_n, POW2) > g) di -= 1.0;
-    while (di < dend && !(gse_sample_position(di, r, n_total, inv_n, POW2) > g)) di += 1.0;
-    return di;
-}
-
 template <bool POW2, bool SEG>
 __global__ void __launch_bounds__(RS_THREADS, 6)
 k_resample_search(const ResampleArgs a, const int64_t* __restrict__ part, int32_t* __restrict__ idx_out) {
@@ -832,6 +771,7 @@ static void fill_common(gse_ctx* ctx, ResampleArgs& a, double r, int64_t n_total
 extern "C" int gse_resample_search_sharded(gse_ctx* ctx, const gse_shards* sh, double r, int64_t out0, int64_t n_out,
                                            int32_t* idx_out_dev, void* stream) {
     GSE_REQUIRE(ctx != NULL && sh != NULL && idx_out_dev != NULL, "ctx / shards / idx is NULL");
+    gse_device_guard guard(ctx->device);
     GSE_REQUIRE(sh->nshards >= 1 && sh->nshards <= GSE_MAX_SHARDS && sh->offsets_dev != NULL, "bad shard table");
     const int64_t n_total = sh->rows[sh->nshards];
     GSE_REQUIRE(sh->rows[0] == 0 && n_total >= 1 && n_total <= 0x7fffffff, "global row count out of range (int32 index)");
@@ -860,6 +800,7 @@ extern "C" int gse_resample_search(gse_ctx* ctx, const uint64_t* cumsum_dev, int
                                    int64_t n_out, int32_t* idx_out_dev, void* stream) {
     GSE_REQUIRE(ctx != NULL && cumsum_dev != NULL && offtot_dev != NULL && idx_out_dev != NULL,
                 "ctx / cumsum / offtot / idx is NULL");
+    gse_device_guard guard(ctx->device);
     GSE_REQUIRE(n_src >= 1 && n_src <= ctx->n_max && n_src <= 0x7fffffff, "n_src out of range for this context");
     GSE_REQUIRE(n_out >= 0 && n_out <= ctx->n_max, "n_out out of range for this context");
     GSE_REQUIRE(n_total >= 1 && out0 >= 0 && out0 + n_out <= n_total, "output range outside [0, n_total)");
@@ -876,8 +817,6 @@ extern "C" int gse_resample_search(gse_ctx* ctx, const uint64_t* cumsum_dev, int
     GSE_REQUIRE(nparts + 1 <= ctx->max_tiles + 2, "workspace too small");
     cudaStream_t s = (cudaStream_t)stream;
     return launch_search(ctx, a, nparts, idx_out_dev, false, s);
-    GSE_CHECK_LAUNCH(ctx);
-    return GSE_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -955,6 +894,7 @@ k_gather_rows_sharded(const __grid_constant__ GatherShards g, const int32_t* __r
 extern "C" int gse_gather_rows_sharded(gse_ctx* ctx, const gse_shards* sh, const int32_t* idx_dev, int64_t n_out,
                                        float* dst_dev, int64_t ld_dst, int ncols, void* stream) {
     GSE_REQUIRE(ctx != NULL && sh != NULL && idx_dev != NULL && dst_dev != NULL, "NULL argument");
+    gse_device_guard guard(ctx->device);
     GSE_REQUIRE(sh->nshards >= 1 && sh->nshards <= GSE_MAX_SHARDS, "bad shard table");
     GSE_REQUIRE(n_out >= 0 && ncols >= 1 && ld_dst >= n_out, "n_out / ncols / ld out of range");
     if (n_out == 0) return GSE_OK;
@@ -976,6 +916,7 @@ extern "C" int gse_gather_rows(gse_ctx* ctx, const int32_t* idx_dev, int64_t n_o
                                int64_t ld_src, float* dst_dev, int64_t ld_dst, int ncols,
                                float* loglik_out_dev, void* stream) {
     GSE_REQUIRE(ctx != NULL && idx_dev != NULL && src_dev != NULL && dst_dev != NULL, "NULL argument");
+    gse_device_guard guard(ctx->device);
     GSE_REQUIRE(n_out >= 0 && ncols >= 1 && ld_dst >= n_out, "n_out / ncols / ld out of range");
     GSE_REQUIRE(src_dev != dst_dev, "gather cannot be done in place");
     if (n_out == 0) return GSE_OK;

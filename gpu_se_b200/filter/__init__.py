@@ -5,6 +5,8 @@ from gpu_se_b200.filter.particle import ParticleFilter
 from gpu_se_b200.filter.particle import ParallelParticleFilter
 from gpu_se_b200.filter.gs_ukf import GaussianSumUnscentedKalmanFilter
 from gpu_se_b200.filter.gs_ukf import ParallelGaussianSumUnscentedKalmanFilter
+from gpu_se_b200.filter.resample import resample_from_cumsum
 
 __all__ = ['ParticleFilter', 'ParallelParticleFilter',
-           'GaussianSumUnscentedKalmanFilter', 'ParallelGaussianSumUnscentedKalmanFilter']
+           'GaussianSumUnscentedKalmanFilter', 'ParallelGaussianSumUnscentedKalmanFilter',
+           'resample_from_cumsum']

@@ -35,7 +35,12 @@ import ctypes
 import numpy
 import torch
 
+import os
+
 from gpu_se_b200 import _device, _lib
+
+# GSE_RESAMPLE=unfused: scan + merge-path search as two stages (A/B measurements, the sharded path's kernels)
+FUSED_RESAMPLE = os.environ.get("GSE_RESAMPLE", "fused") != "unfused"
 
 
 class Context:
@@ -57,6 +62,18 @@ class Context:
     @property
     def launches(self):
         return int(_lib.lib.gse_launch_count(self.handle))
+
+    def check_device_errors(self):
+        """Raise if a kernel of this context flagged an error since the last check (include/gse.h GSE_ERR_*).
+        Call after a synchronisation: the word lives in host-mapped memory and is read without one."""
+        bits = int(_lib.lib.gse_ctx_errors(self.handle, 1))
+        if bits:
+            msg = _lib.lib.gse_last_error().decode()
+            if bits & (_lib.GSE_ERR_CHOLESKY | _lib.GSE_ERR_SINGULAR_PYY):
+                raise numpy.linalg.LinAlgError(msg)          # what the reference raises (gs_ukf.py:72-75)
+            if bits & _lib.GSE_ERR_ZERO_WEIGHTS:
+                raise FloatingPointError(msg)
+            raise _lib.GseError(msg)
 
     def close(self):
         if getattr(self, "handle", None):
@@ -292,16 +309,9 @@ class WeightedEnsemble:
     def _scan(self):
         """cumsum of the fixed-point weights -> self._cumsum, total -> self._offtot[1]."""
         n = self.N_particles
-        use_loglik = self._base is None or self._loglik_dirty
-        stats = self._stats
-        if self._base is not None and self._loglik_dirty:
-            # S bounds sum exp(loglik - M); the scale must bound sum base * exp(loglik - M)
-            stats = self._stats.clone()
-            stats[1] = stats[1] * self._base_max
-        _lib.check(_lib.lib.gse_scan_weights(
-            self._ctx.handle, self._ensure_loglik_buffer() if use_loglik else None,
-            self._base.data_ptr() if self._base is not None else None, stats.data_ptr(), n,
-            self._cumsum.data_ptr(), self._offtot.data_ptr() + 8, self._stream()))
+        ll, base, stats = self._weight_sources()
+        _lib.check(_lib.lib.gse_scan_weights(self._ctx.handle, ll, base, stats.data_ptr(), n, self._cumsum.data_ptr(),
+                                             self._offtot.data_ptr() + 8, self._stream()))
 
     def resample(self, r=None, return_index=False):
         """Systematic resample (particle.py:85-103 / gs_ukf.py:151-171).  ``r`` defaults to
@@ -320,15 +330,33 @@ class WeightedEnsemble:
         self._flush()
         return self._resample_now(r, return_index)
 
+    def _weight_sources(self):
+        """(loglik pointer or None, base pointer or None, stats tensor) the scan kernels quantise."""
+        use_loglik = self._base is None or self._loglik_dirty
+        stats = self._stats
+        if self._base is not None and self._loglik_dirty:
+            # S bounds sum exp(loglik - M); the scale must bound sum base * exp(loglik - M)
+            stats = self._stats.clone()
+            stats[1] = stats[1] * self._base_max
+        return (self._ensure_loglik_buffer() if use_loglik else None,
+                self._base.data_ptr() if self._base is not None else None, stats)
+
     def _resample_now(self, r, return_index):
         n = self.N_particles
         self._materialise()                       # a second resample without a predict in between
-        self._scan()
-        if self._stage_hook is not None:
-            self._stage_hook("scan")
-        _lib.check(_lib.lib.gse_resample_search(
-            self._ctx.handle, self._cumsum.data_ptr(), n, self._offtot.data_ptr(), r, n, 0, n,
-            self._idx.data_ptr(), self._stream()))
+        if FUSED_RESAMPLE:
+            # scan + rank + fill in one launch: the cumulative weights never reach HBM (csrc/gse_resample_fused.cu)
+            ll, base, stats = self._weight_sources()
+            _lib.check(_lib.lib.gse_resample_fused(
+                self._ctx.handle, ll, base, stats.data_ptr(), n, r, n, 0, n, 0, self._idx.data_ptr(),
+                self._offtot.data_ptr() + 8, self._stream()))
+        else:
+            self._scan()
+            if self._stage_hook is not None:
+                self._stage_hook("scan")
+            _lib.check(_lib.lib.gse_resample_search(
+                self._ctx.handle, self._cumsum.data_ptr(), n, self._offtot.data_ptr(), r, n, 0, n,
+                self._idx.data_ptr(), self._stream()))
         self._pending = True
         self._loglik_zero = True                  # weights = 1/N  (:103 / :316)
         self._reset_uniform()
@@ -364,6 +392,7 @@ class WeightedEnsemble:
             self._mom[41:43].copy_(self._stats[0:2])        # M, S ride along in the same read-back
             self._mom_host.copy_(self._mom, non_blocking=True)
             torch.cuda.current_stream(self.device).synchronize()
+            self._ctx.check_device_errors()
             self._mom_np = self._mom_host.numpy().copy()
             self._mom_valid = True
         return self._mom_np

@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define GSE_ABI_VERSION 4
+#define GSE_ABI_VERSION 5
 
 #define GSE_NX 5        /* states  (Cg, Cx, Cfa, Ce, Ch)   model/BioreactorModel.py:191 */
 #define GSE_NU 2        /* inputs  (Fg_in, Fm_in)          model/BioreactorModel.py:195 */
@@ -80,6 +80,16 @@ typedef struct gse_mixture {
 
 typedef struct gse_ctx gse_ctx;
 
+/* Conditions detected INSIDE kernels cannot fail the call that launched them (nothing synchronises).  The kernels OR
+ * these bits into a per-context error word in host-mapped memory; gse_ctx_errors() returns it (and sets
+ * gse_last_error() to a description) whenever the caller is at a synchronisation point anyway -- the Python classes
+ * poll it after every moments read-back and raise. */
+#define GSE_ERR_CHOLESKY 1u        /* GS-UKF: covariance not positive definite even with the +1e-10 I retry (gs_ukf.py:72-75 raises LinAlgError) */
+#define GSE_ERR_SINGULAR_PYY 2u    /* GS-UKF update: innovation covariance P_yy singular / not positive (gs_ukf.py:132) */
+#define GSE_ERR_PEER_TIMEOUT 4u    /* sharded run: a peer's mailbox flag did not arrive within the spin bound */
+#define GSE_ERR_QUEUE_OVERFLOW 8u  /* fused resample: heavy-run queue full (workspace sized for fewer outputs) */
+#define GSE_ERR_ZERO_WEIGHTS 16u   /* resample of weights that are all zero (the reference divides by zero, particle.py:90) */
+
 int gse_abi_version(void);
 const char* gse_last_error(void);
 
@@ -91,6 +101,10 @@ const char* gse_last_error(void);
 int gse_ctx_create(int device, int model_id, int64_t n_max, const gse_mixture* state,
                    const gse_mixture* meas, gse_ctx** out);
 int gse_ctx_destroy(gse_ctx* ctx);
+
+/* The context's device-error word (GSE_ERR_* bits, 0 = none); clear != 0 resets it.  Does not synchronise: call it
+ * after the stream the kernels ran on has been synchronised. */
+unsigned int gse_ctx_errors(gse_ctx* ctx, int clear);
 
 /* Per-step scalars in DEVICE memory.  While a context has a parameter block attached
  * (gse_ctx_set_step_params), every launch made through it reads u, dt, z, r and the Philox step
@@ -193,6 +207,32 @@ int gse_scan_weights(gse_ctx* ctx, const float* loglik_dev, const double* base_d
 int gse_resample_search(gse_ctx* ctx, const uint64_t* cumsum_dev, int64_t n_src,
                         const uint64_t* offtot_dev, double r, int64_t n_total, int64_t out0,
                         int64_t n_out, int32_t* idx_out_dev, void* stream);
+
+/* resample() in ONE launch (particle.py:85-100 / :296-314): scan of the fixed-point weights (as gse_scan_weights:
+ * q_i = rint(base_i * exp(loglik_i - stats_dev[0]) * 2^s), either array may be NULL), global total, and for every
+ * local source row k the outputs it owns,
+ *     idx_j = src_row0 + k   for   e_{k-1} <= j < e_k,    e_k = #{ j : (j + r) / n_total <= cumsum_k / total }
+ * -- the same indices as gse_scan_weights + gse_resample_search, bit for bit, without the cumulative weights ever
+ * reaching HBM.  Outputs j in [out0, out0 + n_out) are written to idx_out_dev[j - out0] (int32 global ancestor row);
+ * a single-GPU population passes out0 = 0, n_out = n_total = n_src, src_row0 = 0.  total_dev receives the integer
+ * total (NULL to skip).  The kernel's CTAs wait on one another: the grid is one wave of co-resident CTAs. */
+int gse_resample_fused(gse_ctx* ctx, const float* loglik_dev, const double* base_dev, const double* stats_dev,
+                       int64_t n_src, double r, int64_t n_total, int64_t out0, int64_t n_out, int64_t src_row0,
+                       int32_t* idx_out_dev, uint64_t* total_dev, void* stream);
+
+/* `resample_from_cumsum` (contract (ii)): systematic resample fed the CALLER'S float64
+ * cumulative sum -- e.g. the reference's own numpy.cumsum / torch.cumsum array (particle.py:89-90 / :301-304).
+ *     normalise == 0: cumsum_dev is already normalised (`cumsum /= cumsum[-1]` done by the caller)
+ *     normalise != 0: every element is divided by cumsum_dev[n_src - 1] on the fly (div.rn.f64, as numpy)
+ *     ties_right == 0: idx_j = #{ k : cumsum[k] <  u_j }  the reference CPU loop (:96-100), searchsorted 'left'
+ *     ties_right != 0: idx_j = min(#{ k : cumsum[k] <= u_j }, n_src - 1)  the reference GPU kernel _parallel_resample
+ *                      (:223-263; searchsorted 'right' -- the two differ only where a sample position ties with a
+ *                      DUPLICATED cumsum value, and the kernel indexes one past the end for u = 1.0)
+ * with u_j = (j + r) / n_total in float64.  Outputs [out0, out0 + n_out) -> idx_out_dev[j - out0] (int32).
+ * Bit-exact for any non-decreasing cumsum. */
+int gse_resample_search_f64(gse_ctx* ctx, const double* cumsum_dev, int64_t n_src, int normalise, int ties_right,
+                            double r, int64_t n_total, int64_t out0, int64_t n_out, int32_t* idx_out_dev,
+                            void* stream);
 
 /* dst[:, i] = src[:, idx[i]] for ncols SoA columns, i in [0, n_out) (particles[sample_index],
  * particle.py:102 / :315); loglik_out_dev (NULL to skip) is zeroed (weights reset, :103 / :316). */

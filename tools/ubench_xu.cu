@@ -33,6 +33,12 @@ __global__ void k(float* out, float seed, unsigned long long useed) {
             if (OP == 13) asm volatile("fma.rn.f64 %0, %0, %0, %0;" : "+d"(d[i]));
             if (OP == 14) { asm volatile("cvt.rn.f32.u32 %0, %1;" : "=f"(x[i]) : "r"(__float_as_uint(x[i]))); }
             if (OP == 15) asm volatile("div.rn.f64 %0, %0, %1;" : "+d"(d[i]) : "d"(d[(i + 1) % ILP]));
+            if (OP == 16) { asm volatile("cvt.f64.f32 %0, %1;" : "=d"(d[i]) : "f"(x[i])); x[i] += __int_as_float(__double2loint(d[i]) & 1); }
+            if (OP == 17) asm volatile("add.rn.f64 %0, %0, %0;" : "+d"(d[i]));
+            if (OP == 18) asm volatile("cvt.rni.f32.f32 %0, %0;" : "+f"(x[i]));
+            if (OP == 19) { asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(x[i]) : "d"(d[i])); d[i] += __longlong_as_double((long long)(__float_as_uint(x[i]) & 1)); }
+            if (OP == 20) { unsigned long long r; asm volatile("cvt.rni.u64.f64 %0, %1;" : "=l"(r) : "d"(d[i])); d[i] += __longlong_as_double((long long)(r & 1)); }
+            if (OP == 21) { int r; asm volatile("cvt.rni.s32.f32 %0, %1;" : "=r"(r) : "f"(x[i])); x[i] += __int_as_float(r & 1); }
         }
     }
     float s = 0;
@@ -77,5 +83,11 @@ int main() {
     run<13>("dfma", p.multiProcessorCount, ghz, out);
     run<14>("cvt f32<-u32", p.multiProcessorCount, ghz, out);
     run<15>("div.rn.f64", p.multiProcessorCount, ghz, out);
+    run<16>("cvt f64<-f32", p.multiProcessorCount, ghz, out);
+    run<17>("dadd", p.multiProcessorCount, ghz, out);
+    run<18>("rint f32", p.multiProcessorCount, ghz, out);
+    run<19>("cvt f32<-f64", p.multiProcessorCount, ghz, out);
+    run<20>("cvt u64<-f64", p.multiProcessorCount, ghz, out);
+    run<21>("cvt s32<-f32", p.multiProcessorCount, ghz, out);
     return 0;
 }
