@@ -235,7 +235,7 @@ extern "C" int gse_ctx_create(int device, int model_id, int64_t n_max, const gse
     c->scan_tiles_prev = 0;
     {
         const char* v = getenv("GSE_UPDATE_CTAS");
-        c->update_ctas_per_sm = (v && atoi(v) >= 1 && atoi(v) <= 32) ? atoi(v) : 8;
+        c->update_ctas_per_sm = (v && atoi(v) >= 1 && atoi(v) <= 32) ? atoi(v) : 5;
     }
     c->scan_resident_blocks = 0;
     {
@@ -247,8 +247,12 @@ extern "C" int gse_ctx_create(int device, int model_id, int64_t n_max, const gse
     c->fused_status = (uint64_t*)(base + o_fstatus);
     c->heavy_queue = (int4*)(base + o_queue);
     {
-        const char* v = getenv("GSE_FUSED_ITEMS");
-        c->fused_items = (v && atoi(v) == 16) ? 16 : 8;
+        const char* v = getenv("GSE_PREDICT_MINB");               // tuning knob: CTAs per SM of the predict kernel
+        c->predict_minb = (v && (atoi(v) == 4 || atoi(v) == 6)) ? atoi(v) : 5;
+    }
+    {
+        const char* v = getenv("GSE_FUSED_MINB");                 // tuning knob: 3 = 85 registers, 24 warps per SM
+        c->fused_minb = (v && atoi(v) == 3) ? 3 : 4;
     }
     // device-error word: host-mapped so that reading it never needs a copy or a synchronisation of its own
     e = cudaHostAlloc((void**)&c->err_host, 64, cudaHostAllocMapped);

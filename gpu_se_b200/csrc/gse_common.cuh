@@ -109,7 +109,8 @@ struct gse_ctx {
     int4* heavy_queue;        // fused resample: runs of one heavy source handed to the whole grid (start, end, ancestor)
     int heavy_queue_cap;
     int fused_resident[12];   // co-resident CTAs of each k_resample_fused instantiation (0: not queried yet)
-    int fused_items;          // rows per lane and tile of the fused kernel (8; GSE_FUSED_ITEMS=16 for tuning)
+    int predict_minb;         // CTAs per SM of the benchmark's predict specialisation (5; GSE_PREDICT_MINB = 4 / 6 for tuning)
+    int fused_minb;           // CTAs per SM the fused kernel is compiled for (4; GSE_FUSED_MINB=3 for tuning)
     unsigned int* err_host;   // device-error word: pinned, mapped host memory the kernels OR their GSE_ERR_* bits into
     unsigned int* err_dev;    // its device alias
     int64_t* part;            // merge-path split points
@@ -224,6 +225,13 @@ __device__ __forceinline__ float mufu_rcp(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+// exp(x) for x <= ~0 as one multiply and one MUFU: ex2.approx.ftz (results below 2^-126 flush to zero; __expf spends
+// three more instructions per call on that range)
+__device__ __forceinline__ float fast_exp(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+    return r;
+}
 __device__ __forceinline__ float box_muller_radius(uint32_t a) {
     // sqrt(-2 ln u1) = sqrt(lg2(u1) * (-2 ln 2))
     return mufu_sqrt(mufu_lg2(u32_to_unit(a)) * -1.3862943611198906f);
@@ -306,19 +314,20 @@ __device__ __forceinline__ void draw_mixture5(const MixSampler5& sp, uint64_t in
 template <bool DIAG, int ND>
 __device__ __forceinline__ void draw_mixture5_x4(const MixSampler5& sp, uint64_t group, uint32_t step, uint32_t k0,
                                                  uint32_t k1, float out[4][5]) {
-    uint32_t w[24];
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-        const Philox4 P = philox4x32_10((uint32_t)group, (uint32_t)(group >> 32), step, 0x80000000u + j, k0, k1);
-        w[4 * j] = P.x; w[4 * j + 1] = P.y; w[4 * j + 2] = P.z; w[4 * j + 3] = P.w;
-    }
+    // every Philox call is turned into its four normals at once (its words die there): 20 normals + 4 selectors live
     float z[20];
 #pragma unroll
-    for (int p = 0; p < 10; ++p) box_muller(w[2 * p], w[2 * p + 1], z[2 * p], z[2 * p + 1]);
+    for (int j = 0; j < 5; ++j) {
+        const Philox4 P = philox4x32_10((uint32_t)group, (uint32_t)(group >> 32), step, 0x80000000u + j, k0, k1);
+        box_muller(P.x, P.y, z[4 * j], z[4 * j + 1]);
+        box_muller(P.z, P.w, z[4 * j + 2], z[4 * j + 3]);
+    }
+    const Philox4 S = philox4x32_10((uint32_t)group, (uint32_t)(group >> 32), step, 0x80000005u, k0, k1);
+    const uint32_t sel[4] = {S.x, S.y, S.z, S.w};
     const int dg[5] = {0, 2, 5, 9, 14};
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-        const float uc = u32_to_unit(w[20 + r]);
+        const float uc = u32_to_unit(sel[r]);
         int comp = 0;
         if (ND != 1) {
 #pragma unroll
@@ -417,8 +426,8 @@ __device__ __forceinline__ double meas_logpdf(const MixDensity2& md, double e0, 
     float s = 0.0f;
 #pragma unroll
     for (int d = 0; d < GSE_MAX_ND; ++d)
-        if (d < md.nd) s += __expf((float)(a[d] - m));
-    return m + (double)__logf(s);
+        if (d < md.nd) s += fast_exp((float)(a[d] - m));
+    return m + (double)(mufu_lg2(s) * 0.69314718055994531f);
 }
 
 // float32 variant for the particle-filter update (K2).  e = z - y is formed from a float32 hi/lo
@@ -441,7 +450,7 @@ __device__ __forceinline__ float meas_logpdf32(const MixDensity2f& md, float e0,
         if (ND == 1) return a[0];
         float s = 0.0f;
 #pragma unroll
-        for (int d = 0; d < ND; ++d) s += __expf(a[d] - m);
+        for (int d = 0; d < ND; ++d) s += fast_exp(a[d] - m);
         return fmaf(mufu_lg2(s), 0.69314718055994531f, m);
     }
     float a[GSE_MAX_ND];
@@ -458,7 +467,7 @@ __device__ __forceinline__ float meas_logpdf32(const MixDensity2f& md, float e0,
     float s = 0.0f;
 #pragma unroll
     for (int d = 0; d < GSE_MAX_ND; ++d)
-        if (d < md.nd) s += __expf(a[d] - m);
+        if (d < md.nd) s += fast_exp(a[d] - m);
     return fmaf(mufu_lg2(s), 0.69314718055994531f, m);
 }
 
@@ -492,15 +501,29 @@ struct MaxSumExp {
     float m, s;
     __device__ __forceinline__ MaxSumExp() : m(-INFINITY), s(0.0f) {}
     template <int NV>
+    __device__ __forceinline__ void add_all(const float vals[NV]) {
+        float g = vals[0];
+#pragma unroll
+        for (int r = 1; r < NV; ++r) g = fmaxf(g, vals[r]);
+        const float mn = fmaxf(m, g);
+        if (mn > -INFINITY) {
+            float t = s * fast_exp(m - mn);          // m = -inf: exp(-inf) = 0, s = 0
+#pragma unroll
+            for (int r = 0; r < NV; ++r) t += fast_exp(vals[r] - mn);
+            s = t;
+            m = mn;
+        }
+    }
+    template <int NV>
     __device__ __forceinline__ void add(const float vals[NV], const bool valid[NV]) {
         float g = -INFINITY;
 #pragma unroll
         for (int r = 0; r < NV; ++r) if (valid[r]) g = fmaxf(g, vals[r]);
         const float mn = fmaxf(m, g);
         if (mn > -INFINITY) {
-            float t = s * __expf(m - mn);          // m = -inf: exp(-inf) = 0, s = 0
+            float t = s * fast_exp(m - mn);          // m = -inf: exp(-inf) = 0, s = 0
 #pragma unroll
-            for (int r = 0; r < NV; ++r) if (valid[r]) t += __expf(vals[r] - mn);
+            for (int r = 0; r < NV; ++r) if (valid[r]) t += fast_exp(vals[r] - mn);
             s = t;
             m = mn;
         }
@@ -524,7 +547,7 @@ __device__ __forceinline__ void block_merge_max_sumexp(float m_t, float s_t, flo
     }
     __syncthreads();
     const float bm = s_bcast;
-    float sum = (m_t > -INFINITY) ? s_t * __expf(m_t - bm) : 0.0f;
+    float sum = (m_t > -INFINITY) ? s_t * fast_exp(m_t - bm) : 0.0f;
     sum = warp_sum(sum);
     __syncthreads();
     if (lane == 0) s_red[wid] = sum;
@@ -560,7 +583,7 @@ __device__ __forceinline__ void block_merge_max_sumexp(float m_t, float s_t, flo
     double acc = 0.0;
     for (unsigned int b = threadIdx.x; b < gridDim.x; b += THREADS) {
         const float bmx = __ldcg(block_max + b);
-        if (bmx > -INFINITY) acc += (double)__ldcg(block_sum + b) * (double)__expf(bmx - M);
+        if (bmx > -INFINITY) acc += (double)__ldcg(block_sum + b) * (double)fast_exp(bmx - M);
     }
     acc = warp_sum(acc);
     if (lane == 0) s_dred[wid] = acc;

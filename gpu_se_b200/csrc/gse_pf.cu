@@ -4,6 +4,9 @@
 #include "gse_common.cuh"
 
 #define PF_THREADS 256
+#ifndef PREDICT_MINB
+#define PREDICT_MINB 5       // CTAs per SM the predict kernel is compiled for (48 registers)
+#endif
 #define ROWS_PER_THREAD 4
 
 static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
@@ -61,8 +64,10 @@ extern "C" int gse_mixture_draw(gse_ctx* ctx, const gse_mixture* mix, float* x_d
 // ------------------------------------------------------------------------------------------------
 // GMODE: 0 rows in place, 1 rows through a local ancestor index, 2 rows through a GLOBAL ancestor
 // index into the shards of a multi-GPU population (peer memory)
-template <bool DIAG, bool HOST_NOISE, bool ONE_STEP, int ND, int GMODE>
-__global__ void __launch_bounds__(PF_THREADS, 5)
+// ALIGNED: global row index0 + row0 of every thread is a multiple of four (one grouped draw serves the thread's rows);
+// always the case except for a shard that starts off a multiple of four
+template <bool DIAG, bool HOST_NOISE, bool ONE_STEP, int ND, int GMODE, bool ALIGNED, int MINB>
+__global__ void __launch_bounds__(PF_THREADS, MINB)
 k_pf_predict(const float* xs, int64_t lds, const int32_t* __restrict__ idx, const __grid_constant__ GatherShards shards,
              float* xd, int64_t ldd, int64_t n,
              ModelInputs in_arg, int n_sub, const __grid_constant__ MixSampler5 sp, uint32_t k0, uint32_t k1,
@@ -127,10 +132,11 @@ k_pf_predict(const float* xs, int64_t lds, const int32_t* __restrict__ idx, cons
     float e4[4][5];
     if (!HOST_NOISE) {
         const uint64_t r0g = (uint64_t)(index0 + row0);
-        if ((r0g & 3ull) == 0) {
+        if (ALIGNED) {
             draw_mixture5_x4<DIAG, ND>(sp, r0g >> 2, step, k0, k1, e4);
         } else {
-#pragma unroll 1
+            // (fully unrolled: a loop over r would index e4 dynamically and push it into local memory)
+#pragma unroll
             for (int r = 0; r < 4; ++r) {
                 float g4[4][5];
                 draw_mixture5_x4<DIAG, ND>(sp, (r0g + r) >> 2, step, k0, k1, g4);
@@ -193,10 +199,23 @@ static int launch_predict(gse_ctx* ctx, const float* x_src_dev, int64_t ld_src, 
     const unsigned blocks = (unsigned)gse_div_up(groups, PF_THREADS);
     cudaStream_t s = (cudaStream_t)stream;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-#define LAUNCH_PREDICT_G(DIAG, HOST, ONE, ND, GMODE)                                                             \
-    k_pf_predict<DIAG, HOST, ONE, ND, GMODE><<<blocks, PF_THREADS, 0, s>>>(                                      \
+#define LAUNCH_PREDICT_GAM(DIAG, HOST, ONE, ND, GMODE, AL, MB)                                                   \
+    k_pf_predict<DIAG, HOST, ONE, ND, GMODE, AL, MB><<<blocks, PF_THREADS, 0, s>>>(                              \
         x_src_dev, ld_src, idx_dev, *shards, x_dst_dev, ld_dst, n, in, n_sub, ctx->state_sampler, k0, k1,        \
         (uint32_t)step, index0, noise_dev, ld_noise, ctx->step_params)
+// (the benchmark's specialisation -- diagonal two-component noise, one Euler step, aligned rows -- is also compiled for
+//  4 and 6 CTAs per SM: GSE_PREDICT_MINB, a tuning knob)
+#define LAUNCH_PREDICT_GA(DIAG, HOST, ONE, ND, GMODE, AL)                                                        \
+    do {                                                                                                         \
+        if ((ND) == 2 && (AL) && ctx->predict_minb == 4) LAUNCH_PREDICT_GAM(DIAG, HOST, ONE, ND, GMODE, AL, ((ND) == 2 && (AL)) ? 4 : PREDICT_MINB); \
+        else if ((ND) == 2 && (AL) && ctx->predict_minb == 6) LAUNCH_PREDICT_GAM(DIAG, HOST, ONE, ND, GMODE, AL, ((ND) == 2 && (AL)) ? 6 : PREDICT_MINB); \
+        else LAUNCH_PREDICT_GAM(DIAG, HOST, ONE, ND, GMODE, AL, PREDICT_MINB);                                   \
+    } while (0)
+#define LAUNCH_PREDICT_G(DIAG, HOST, ONE, ND, GMODE)                                                             \
+    do {                                                                                                         \
+        if ((index0 & 3) == 0 || (HOST)) LAUNCH_PREDICT_GA(DIAG, HOST, ONE, ND, GMODE, true);                    \
+        else LAUNCH_PREDICT_GA(DIAG, HOST, ONE, ND, GMODE, false);                                               \
+    } while (0)
 #define LAUNCH_PREDICT(DIAG, HOST, ONE, ND)                                                                      \
     do {                                                                                                         \
         if (sharded) LAUNCH_PREDICT_G(DIAG, HOST, ONE, ND, 2);                                                   \
@@ -212,6 +231,8 @@ static int launch_predict(gse_ctx* ctx, const float* x_src_dev, int64_t ld_src, 
     else { if (one) LAUNCH_PREDICT(false, false, true, 0); else LAUNCH_PREDICT(false, false, false, 0); }
 #undef LAUNCH_PREDICT
 #undef LAUNCH_PREDICT_G
+#undef LAUNCH_PREDICT_GA
+#undef LAUNCH_PREDICT_GAM
     GSE_CHECK_LAUNCH(ctx);
     return GSE_OK;
 }
@@ -244,7 +265,7 @@ extern "C" int gse_pf_predict_sharded(gse_ctx* ctx, const gse_shards* shards, co
 // keeps a running (max, sum exp) pair, so the block-level reduction and its barriers run once per
 // CTA instead of once per 1024 rows.
 template <int ND, bool LL_ZERO>      // LL_ZERO: the accumulated log-likelihood is all zero (fresh resample)
-__global__ void __launch_bounds__(PF_THREADS)
+__global__ void __launch_bounds__(PF_THREADS, 5)
 k_pf_update(const float* __restrict__ xg, const float* __restrict__ xfa, const float* loglik_in,
             float* loglik, int64_t n, float z0h, float z0l, float z1h, float z1l,
             const __grid_constant__ MixDensity2f md, float* block_max, float* block_sum, unsigned int* ticket,
@@ -255,29 +276,46 @@ k_pf_update(const float* __restrict__ xg, const float* __restrict__ xfa, const f
         z0l = (float)(params->z[0] - (double)z0h);
         z1l = (float)(params->z[1] - (double)z1h);
     }
-    const int64_t groups = (n + 3) >> 2;
+    const int64_t groups = n >> 2;                          // whole groups of four rows; a ragged tail is handled below
     const int64_t stride = (int64_t)gridDim.x * PF_THREADS;
     MaxSumExp acc;
-    for (int64_t g = (int64_t)blockIdx.x * PF_THREADS + threadIdx.x; g < groups; g += stride) {
-        const int64_t row0 = g * ROWS_PER_THREAD;
-        const float4 cg = ld_stream4(xg + row0);
-        const float4 cf = ld_stream4(xfa + row0);
-        float4 lw = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!LL_ZERO) lw = ld_stream4(loglik_in + row0);
-        const float a[4] = {cg.x, cg.y, cg.z, cg.w};
-        const float b[4] = {cf.x, cf.y, cf.z, cf.w};
-        const float l[4] = {lw.x, lw.y, lw.z, lw.w};
-        float vals[4];
-        bool valid[4];
+    // two groups per iteration, all six loads issued before the first use
+    for (int64_t g = (int64_t)blockIdx.x * PF_THREADS + threadIdx.x; g < groups; g += 2 * stride) {
+        const int64_t rowA = g * ROWS_PER_THREAD, rowB = (g + stride) * ROWS_PER_THREAD;
+        const bool hasB = g + stride < groups;
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 cg[2], cf[2], lw[2];
+        cg[0] = ld_stream4(xg + rowA);
+        cf[0] = ld_stream4(xfa + rowA);
+        lw[0] = LL_ZERO ? zero4 : ld_stream4(loglik_in + rowA);
+        cg[1] = hasB ? ld_stream4(xg + rowB) : zero4;
+        cf[1] = hasB ? ld_stream4(xfa + rowB) : zero4;
+        lw[1] = (hasB && !LL_ZERO) ? ld_stream4(loglik_in + rowB) : zero4;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const float e0 = __fadd_rn(__fsub_rn(z0h, output_glucose(a[r])), z0l);   // e = z - y   (:82)
-            const float e1 = __fadd_rn(__fsub_rn(z1h, output_fa(b[r])), z1l);
-            vals[r] = l[r] + meas_logpdf32<ND>(md, e0, e1);                 // weights[i] *= pdf(e)  (:83)
-            valid[r] = (row0 + r) < n;
+        for (int h = 0; h < 2; ++h) {
+            if (h == 1 && !hasB) break;
+            const float a[4] = {cg[h].x, cg[h].y, cg[h].z, cg[h].w};
+            const float b[4] = {cf[h].x, cf[h].y, cf[h].z, cf[h].w};
+            const float l[4] = {lw[h].x, lw[h].y, lw[h].z, lw[h].w};
+            float vals[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float e0 = __fadd_rn(__fsub_rn(z0h, output_glucose(a[r])), z0l);   // e = z - y   (:82)
+                const float e1 = __fadd_rn(__fsub_rn(z1h, output_fa(b[r])), z1l);
+                vals[r] = l[r] + meas_logpdf32<ND>(md, e0, e1);                 // weights[i] *= pdf(e)  (:83)
+            }
+            st_stream4(loglik + (h ? rowB : rowA), make_float4(vals[0], vals[1], vals[2], vals[3]));
+            acc.add_all<4>(vals);
         }
-        st_stream4(loglik + row0, make_float4(vals[0], vals[1], vals[2], vals[3]));
-        acc.add<4>(vals, valid);
+    }
+    if ((n & 3) && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {      // the last one to three rows
+        for (int64_t i = groups * ROWS_PER_THREAD; i < n; ++i) {
+            const float e0 = __fadd_rn(__fsub_rn(z0h, output_glucose(xg[i])), z0l);
+            const float e1 = __fadd_rn(__fsub_rn(z1h, output_fa(xfa[i])), z1l);
+            const float v[1] = {(LL_ZERO ? 0.0f : loglik_in[i]) + meas_logpdf32<ND>(md, e0, e1)};
+            loglik[i] = v[0];
+            acc.add_all<1>(v);
+        }
     }
     block_merge_max_sumexp<PF_THREADS>(acc.m, acc.s, block_max, block_sum, ticket, stats);
 }
@@ -292,7 +330,7 @@ extern "C" int gse_pf_update(gse_ctx* ctx, const float* x_dev, int64_t ld, int64
     GSE_REQUIRE(loglik_dev != NULL && aligned16(loglik_dev), "loglik must be 16-byte aligned");
     GSE_REQUIRE(loglik_in_dev == NULL || aligned16(loglik_in_dev), "loglik_in must be 16-byte aligned");
     (void)u;   // static_outputs ignores u (BioreactorModel.py:250)
-    const int64_t groups = gse_div_up(n, ROWS_PER_THREAD);
+    const int64_t groups = gse_div_up(n, 2 * ROWS_PER_THREAD);          // a thread takes two groups of four rows per iteration
     int64_t nblk = gse_div_up(groups, PF_THREADS);
     if (nblk > (int64_t)ctx->num_sms * ctx->update_ctas_per_sm) nblk = (int64_t)ctx->num_sms * ctx->update_ctas_per_sm;   // persistent grid
     const unsigned blocks = (unsigned)nblk;
@@ -559,7 +597,7 @@ k_moments(const float* __restrict__ x, const float* __restrict__ extra, int64_t 
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             if (row0 + r < n) {
-                double w = loglik ? (double)__expf(l[r] - M) : 1.0;
+                double w = loglik ? (double)fast_exp(l[r] - M) : 1.0;
                 if (base) w *= base[row0 + r];
                 double d[5];
 #pragma unroll
@@ -661,7 +699,7 @@ k_means(const float* __restrict__ x, int64_t ld, int64_t n, const int32_t* __res
         float w[4] = {1.f, 1.f, 1.f, 1.f};
         if (loglik) {
             const float4 lw = ld_stream4(loglik + row0);
-            w[0] = __expf(lw.x - M); w[1] = __expf(lw.y - M); w[2] = __expf(lw.z - M); w[3] = __expf(lw.w - M);
+            w[0] = fast_exp(lw.x - M); w[1] = fast_exp(lw.y - M); w[2] = fast_exp(lw.z - M); w[3] = fast_exp(lw.w - M);
         }
 #pragma unroll
         for (int r = 1; r < 4; ++r) if (row0 + r >= n) w[r] = 0.f;

@@ -15,13 +15,13 @@
 #define TILE_ITEMS 16
 #define TILE_ROWS (TILE_THREADS * TILE_ITEMS)      // 4096 rows per tile
 
-// q = rint(exp(l - M) * 2^sexp): the one expression both passes (K3a, K3b) evaluate, with explicit
-// round-to-nearest operations so that no contraction can make them differ
+// q = rint(exp(l - M) * 2^sexp): the one expression both passes (K3a, K3b) and the fused kernel evaluate (weight_exp();
+// the argument named M is -M log2(e)), with explicit round-to-nearest operations so that no contraction can make them differ
 // (SMALL = convert through cvt.rni.u32.f32 when the scale is <= 2^31: measured slower than the plain
 // 64-bit conversion, kept only as the documented experiment)
 template <bool SMALL>
 __device__ __forceinline__ uint64_t quantise1(float l, float M, float scale) {
-    const float v = __fmul_rn(__expf(__fsub_rn(l, M)), scale);
+    const float v = __fmul_rn(weight_exp(l, M), scale);
     return SMALL ? (uint64_t)__float2uint_rn(v) : __float2ull_rn(v);
 }
 
@@ -41,7 +41,7 @@ __device__ __forceinline__ void quantise16(const float* __restrict__ loglik, con
             for (int r = 0; r < TILE_ITEMS; ++r) l[r] = (row0 + r < n) ? loglik[row0 + r] : -INFINITY;
         }
 #pragma unroll
-        for (int r = 0; r < TILE_ITEMS; ++r) e[r] = __expf(__fsub_rn(l[r], M));
+        for (int r = 0; r < TILE_ITEMS; ++r) e[r] = weight_exp(l[r], M);
     }
     if (!HAS_BASE) {
         const float scale = __int_as_float((127 + sexp) << 23);       // 2^sexp, 0 <= sexp <= 52
@@ -104,7 +104,7 @@ k_weight_tile_sums(const float* __restrict__ loglik, const double* __restrict__ 
     __shared__ uint64_t s_scan[TILE_THREADS];
     __shared__ bool s_last;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const float M = HAS_LL ? (float)stats[0] : 0.0f;
+    const float M = HAS_LL ? weight_exp_offset((float)stats[0]) : 0.0f;    // -M log2(e), see weight_exp()
     const int sexp = quantisation_exponent(stats[1]);
     const int w = blockIdx.x * SCAN_WARPS + wid;
     if (w < geo.nwarps) {
@@ -184,7 +184,7 @@ k_weight_scan(const float* __restrict__ loglik, const double* __restrict__ base,
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int w = blockIdx.x * SCAN_WARPS + wid;
     if (w >= geo.nwarps) return;
-    const float M = HAS_LL ? (float)stats[0] : 0.0f;
+    const float M = HAS_LL ? weight_exp_offset((float)stats[0]) : 0.0f;    // -M log2(e), see weight_exp()
     const int sexp = quantisation_exponent(stats[1]);
     const int64_t t0 = (int64_t)w * geo.tiles_per_warp;
     const int64_t t1 = min(t0 + geo.tiles_per_warp, geo.ntiles);
@@ -238,7 +238,7 @@ k_weight_scan_lookback(const float* __restrict__ loglik, const double* __restric
     __syncthreads();
     const unsigned int epoch = s_epoch;
     const int64_t vb = s_vb;
-    const float M = (float)stats[0];
+    const float M = weight_exp_offset((float)stats[0]);          // -M log2(e), see weight_exp()
     const int sexp = quantisation_exponent(stats[1]);
     const float scale = __int_as_float((127 + sexp) << 23);
     // this block owns rows [b0, b1), warp w the contiguous sub-run [w0, w1) of it (whole 512-row tiles)

@@ -17,8 +17,8 @@
 // The cumulative weights are exact integers (< 2^53) carried in float64 -- the same values the uint64 scan of
 // gse_resample.cu produces -- so the ancestor indices are bit-identical to searchsorted(cumsum / cumsum[-1], u, 'left')
 // on those integers.  Everything on the per-row path avoids the XU pipe except the one ex2: integer <-> float64
-// conversions, floor and cvt.u64.f32 (7-14 lanes/clk/SM, profiles/r1_ubench_xu_pipe.txt) are replaced by float64
-// adds of 2^52-type constants.
+// conversions, floor and cvt.u64.f32 (7-14 lanes/clk/SM, profiles/r2_ubench_xu_pipe.txt) are replaced by adding
+// 2^23 / 2^52-type constants and reading the mantissa.
 //
 // gse_resample_search_f64 feeds the same rank + fill code with a caller's own float64 cumulative sum
 // (`resample_from_cumsum`, SURVEY.md section 7 contract (ii)).
@@ -26,10 +26,13 @@
 
 #define RF_THREADS 256
 #define RF_WARPS (RF_THREADS / 32)
-#define RF_HEAVY_MIN 4096        // a warp fills at most this many outputs of one source beyond the current window itself
+#define RF_ITEMS 8               // consecutive source rows per lane and tile
+#define RF_TILE (32 * RF_ITEMS)  // source rows per warp tile
+#define RF_WIN 256               // outputs per window (one flush: 8 per lane)
+#define RF_RING (2 * RF_WIN)     // per-warp marker ring: the window being completed and the one after it
+#define RF_HEAVY_MIN 4096        // whole windows inside a longer run of one source are queued, not filled by the warp
 #define RF_PIECE 65536           // queued runs are cut into pieces of at most this many outputs (one warp each)
 
-#define RF_MAGIC 6755399441055744.0      // 1.5 * 2^52: (t + MAGIC) - MAGIC = rint(t), low word of (t + MAGIC) = (int)rint(t)
 #define RF_TWO52 4503599627370496.0
 
 struct FusedArgs {
@@ -38,13 +41,14 @@ struct FusedArgs {
     const double* stats;       // [0] M, [1] S
     const double* cumsum;      // f64 entry: the caller's cumulative sum (normalised unless `normalise`)
     int64_t n_src;
-    int64_t rows_per_block;    // multiple of RF_WARPS * 32 * ITEMS
+    int64_t rows_per_block;    // multiple of RF_WARPS * RF_TILE
     uint64_t* status;          // one word per CTA, zero between launches
     unsigned int* counters;    // [0] start ticket, [1] CTAs past phase 3, [2] queue length, [3] CTAs past the drain
     int4* queue;
     int queue_cap;
     unsigned int* err;         // device error word of the context (host-mapped)
     double r;
+    double magic_minus_r;      // RF_MAGIC16 - r (see rank_of)
     const double* r_dev;       // device override of r (parameter block of a captured graph), or NULL
     double n_total;
     double inv_n;
@@ -68,167 +72,238 @@ __device__ __forceinline__ int warp_sum_i32(int v) {
     return v;
 }
 
-// rint for 0 <= x (already an integer from 2^52 on), without the conversion pipe
-__device__ __forceinline__ double rint_nonneg(double x) {
-    const double y = __dadd_rn(__dadd_rn(x, RF_TWO52), -RF_TWO52);
-    return x >= RF_TWO52 ? x : y;
+// ring[slot] = val where `take` (a predicated store: the compiler otherwise branches around every one of them)
+__device__ __forceinline__ void sts_if(unsigned int saddr, int val, bool take) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.shared.b32 [%0], %1;\n\t}"
+                 :: "r"(saddr), "r"(val), "r"((int)take) : "memory");
 }
 
-// Fixed-point weights of ITEMS consecutive rows as float64 integers: the values of quantise16() in gse_resample.cu
-// (rint(fl32(exp(l - M)) * 2^s), or rint(base * fl32(exp(l - M)) * 2^s) in float64 with a base), rows >= n_end are 0.
-template <int ITEMS, bool HAS_LL, bool HAS_BASE>
-__device__ __forceinline__ void quantise_rows(const float* __restrict__ loglik, const double* __restrict__ base, float M,
-                                              float scale_f, double scale_d, int64_t row0, int64_t n_end,
-                                              double q[ITEMS]) {
-    static_assert(ITEMS == 8 || ITEMS == 16, "ITEMS");
-    const bool full = row0 + ITEMS <= n_end;
-    float e[ITEMS];
-    if (HAS_LL) {
-        float l[ITEMS];
-        if (full) {
-#pragma unroll
-            for (int v = 0; v < ITEMS / 8; ++v) ld_f32x8(loglik + row0 + 8 * v, l + 8 * v);
-        } else {
-#pragma unroll
-            for (int k = 0; k < ITEMS; ++k) l[k] = (row0 + k < n_end) ? loglik[row0 + k] : -INFINITY;
-        }
-#pragma unroll
-        for (int k = 0; k < ITEMS; ++k) e[k] = __expf(__fsub_rn(l[k], M));
-    }
-    if (!HAS_BASE) {
-#pragma unroll
-        for (int k = 0; k < ITEMS; ++k) q[k] = rint_nonneg((double)__fmul_rn(e[k], scale_f));
+// rint for 0 <= x <= 2^52 without the conversion pipe
+__device__ __forceinline__ double rint_to_2p52(double x) { return __dadd_rn(__dadd_rn(x, RF_TWO52), -RF_TWO52); }
+__device__ __forceinline__ double rint_nonneg(double x) { return x >= RF_TWO52 ? x : rint_to_2p52(x); }
+
+// raw log-likelihoods of the lane's RF_ITEMS rows (rows >= n_end: -inf, weight 0)
+__device__ __forceinline__ void load_loglik(const float* __restrict__ loglik, int64_t row0, int64_t n_end, float l[RF_ITEMS]) {
+    if (row0 + RF_ITEMS <= n_end) {
+        ld_f32x8(loglik + row0, l);
     } else {
-        double b[ITEMS];
-        if (full) {
 #pragma unroll
-            for (int v = 0; v < ITEMS / 4; ++v) ld_f64x4(base + row0 + 4 * v, b + 4 * v);
-        } else {
-#pragma unroll
-            for (int k = 0; k < ITEMS; ++k) b[k] = (row0 + k < n_end) ? base[row0 + k] : 0.0;
-        }
-#pragma unroll
-        for (int k = 0; k < ITEMS; ++k) {
-            double w = b[k];
-            if (HAS_LL) w = __dmul_rn(w, (double)e[k]);
-            q[k] = rint_nonneg(fmax(__dmul_rn(w, scale_d), 0.0));
-        }
+        for (int k = 0; k < RF_ITEMS; ++k) l[k] = (row0 + k < n_end) ? loglik[row0 + k] : -INFINITY;
     }
-    if (HAS_LL && !HAS_BASE && !full) {
+}
+
+// Fixed-point weights as float64 integers: the values of quantise16() in gse_resample.cu, rint(fl32(exp(l - M)) 2^s)
+// (the float32 product is at most 2^52, so adding and subtracting 2^52 rounds it to an integer exactly as cvt.rni does)
+__device__ __forceinline__ void quantise_loglik(const float l[RF_ITEMS], float nm, float scale_f, double q[RF_ITEMS]) {
 #pragma unroll
-        for (int k = 0; k < ITEMS; ++k) if (row0 + k >= n_end) q[k] = 0.0;
+    for (int k = 0; k < RF_ITEMS; ++k) q[k] = rint_to_2p52((double)__fmul_rn(weight_exp(l[k], nm), scale_f));
+}
+
+// ... and with float64 base weights: rint(base * fl32(exp(l - M)) * 2^s) in float64; rows >= n_end are 0
+template <bool HAS_LL>
+__device__ __forceinline__ void quantise_base(const float* __restrict__ loglik, const double* __restrict__ base, float nm,
+                                              double scale_d, int64_t row0, int64_t n_end, double q[RF_ITEMS]) {
+    const bool full = row0 + RF_ITEMS <= n_end;
+    float l[RF_ITEMS];
+    if (HAS_LL) load_loglik(loglik, row0, n_end, l);
+    double b[RF_ITEMS];
+    if (full) {
+#pragma unroll
+        for (int v = 0; v < RF_ITEMS / 4; ++v) ld_f64x4(base + row0 + 4 * v, b + 4 * v);
+    } else {
+#pragma unroll
+        for (int k = 0; k < RF_ITEMS; ++k) b[k] = (row0 + k < n_end) ? base[row0 + k] : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < RF_ITEMS; ++k) {
+        double w = b[k];
+        if (HAS_LL) w = __dmul_rn(w, (double)weight_exp(l[k], nm));
+        q[k] = rint_nonneg(fmax(__dmul_rn(w, scale_d), 0.0));
     }
 }
 
 struct RankConsts {
-    double inv_T, Td, n_total, inv_n, r, eps;
+    double inv_T, Td, n_total, inv_n, r, magic_minus_r;
     int n_total_i;
 };
 
+// 1.5 * 2^36: y = t + RF_MAGIC16 has ulp 2^-16, so the mantissa of y holds rint(t * 2^16) + 2^51: its low 16 bits are the
+// fraction of t in units of 2^-16 and bits 16..47 are floor(t) (two's complement, modulo 2^32)
+#define RF_MAGIC16 103079215104.0
+__device__ __forceinline__ void rank_consts(RankConsts& k, double Td, const FusedArgs& a) {
+    k.Td = Td;
+    k.inv_T = 1.0 / Td;
+    k.n_total = a.n_total;
+    k.inv_n = a.inv_n;
+    k.r = a.r_dev ? __ldg(a.r_dev) : a.r;
+    k.magic_minus_r = a.r_dev ? RF_MAGIC16 - k.r : a.magic_minus_r;   // rounds r to a multiple of 2^-16: error <= 2^-17
+    k.n_total_i = a.n_total_i;
+}
+
 // e = #{ outputs j in [0, N) : u_j <= g }  (TIES_RIGHT: u_j < g), g = fl(C / T) for the integer weights, g = C for a
-// caller's normalised cumulative sum (Td = 1).  Fast path: with t* = g N - r in real arithmetic, u_j <= g  <=>
-// j <= t* up to the rounding of u_j and g, which moves the boundary by less than 3 N 2^-53; t below is within another
-// 3 N 2^-53 of t*.  So when t is further than eps = N 2^-48 from an integer the rank is floor(t) + 1; otherwise
-// (exact ties -- dyadic weights, r = 0 -- and ~2 eps of random sources) the comparison is evaluated as the reference does.
+// caller's normalised cumulative sum.  Fast path: with t* = g N - r in real arithmetic, u_j <= g  <=>  j <= t* up to
+// the rounding of u_j and g, which moves the boundary by less than 6 N 2^-53 <= 0.19 * 2^-17 (N < 2^31).  One FMA
+// gives y = fl(g N + (MAGIC - r)), i.e. t* in 2^-16 fixed point with an error below 2^-17 (rounding of r) + 2^-17
+// (rounding of y) + 0.19 * 2^-17: when the 16-bit fraction is in [2, 65533] t* is further than that from an integer
+// and the rank is floor(t) + 1 (in [0, N]: t* >= -r > -1 and t* <= N - r).  Otherwise (exact ties -- dyadic weights,
+// r = 0 -- and 2^-14 of random sources) the comparison is evaluated exactly as the reference does.
 template <bool POW2, bool TIES_RIGHT, bool NORMALISED>
 __device__ __forceinline__ int rank_of(double C, const RankConsts& k) {
     const double g_fast = NORMALISED ? C : __dmul_rn(C, k.inv_T);
-    const double t = __fma_rn(g_fast, k.n_total, -k.r);
-    const double y = __dadd_rn(t, RF_MAGIC);
-    const double rn = __dadd_rn(y, -RF_MAGIC);
-    const double diff = __dadd_rn(t, -rn);                        // t - rint(t), exact
-    int e = __double2loint(y) + (diff >= 0.0 ? 1 : 0);            // floor(t) + 1
-    if (!(fabs(diff) > k.eps)) {
+    const double y = __fma_rn(g_fast, k.n_total, k.magic_minus_r);
+    const unsigned int lo = (unsigned int)__double2loint(y), hi = (unsigned int)__double2hiint(y);
+    int e = (int)__funnelshift_r(lo, hi, 16) + 1;                 // floor(t) + 1
+    if ((lo & 0xffffu) - 2u > 65531u) {                           // fraction in {0, 1, 65534, 65535}
         const double g = NORMALISED ? C : __ddiv_rn(C, k.Td);
-        e = __double2int_rz(rank_exact_g<POW2, TIES_RIGHT>(k.r, k.n_total, k.inv_n, g, rn + 1.0, 0.0, k.n_total));
+        e = __double2int_rz(rank_exact_g<POW2, TIES_RIGHT>(k.r, k.n_total, k.inv_n, g, (double)e, 0.0, k.n_total));
+        e = min(max(e, 0), k.n_total_i);
     }
-    if (t >= k.n_total) e = k.n_total_i;
-    return min(max(e, 0), k.n_total_i);
+    return e;
 }
 
-// Outputs [max(E0, out_lo), min(E1, out_hi)) of the warp's tile: source (lane, k) of the tile owns the outputs
-// [start, e[k]) with start = e[k - 1] (ep for the lane's first row).  s_mark / s_end: 32 * ITEMS ints each, this warp's.
-template <int ITEMS>
-__device__ __forceinline__ void warp_fill(const int (&e)[ITEMS], int ep, int E0, int E1, int src_base, const FusedArgs& a,
-                                          int* s_mark, int* s_end, int lane) {
-    constexpr int TILE = 32 * ITEMS;
-    const int lo = max(E0, a.out_lo), hi = min(E1, a.out_hi);
-    if (lo >= hi) return;                                         // warp-uniform
-    int* my_end = s_end + lane * ITEMS;
-    int* my_mark = s_mark + lane * ITEMS;
+// ------------------------------------------------------------------------------------------------
+// Streaming fill of one warp's contiguous sub-run of sources.  Source s of the sub-run owns the outputs
+// [start_s, e_s), start_s = e_{s-1}.  The warp keeps a ring of two 256-output windows in shared memory, aligned to 256
+// outputs globally: every source WITH offspring drops the marker (its 1-based index in the sub-run) at its first output;
+// once the ranks of a tile reach past the end of the oldest window, that window is complete: a prefix maximum spreads
+// the markers over the runs (carry = the source covering the window's first output) and the window leaves as two
+// coalesced 128-bit stores per lane.  Only the first and the last window of a sub-run are partial (masked scalar stores).
+// ------------------------------------------------------------------------------------------------
+struct WarpFill {
+    int wb;            // first output of the oldest window not yet flushed (multiple of RF_WIN)
+    int carry_m;       // marker of the source that covers output wb (0: none yet -- only below the sub-run's first output)
+    int mlo;           // outputs below mlo are not this sub-run's (or not this launch's)
+    int hi_al;         // no window at or beyond this output is needed (out_hi rounded up to a window)
+    int vbase;         // stored ancestor = vbase + marker
+    int* ring;
+    int32_t* out;      // idx_out - out_lo
+    bool vec_ok;       // out + (multiple of 4) is 16-byte aligned
+
+    __device__ __forceinline__ void begin(int E0, const FusedArgs& a, int vbase_, int* ring_, int lane) {
+        ring = ring_;
+        vbase = vbase_;
+        out = a.idx_out - a.out_lo;
+        vec_ok = (((uintptr_t)out) & 15u) == 0;
+        mlo = max(E0, a.out_lo);
+        wb = mlo & ~(RF_WIN - 1);
+        hi_al = (a.out_hi + RF_WIN - 1) & ~(RF_WIN - 1);
+        carry_m = 0;
 #pragma unroll
-    for (int v = 0; v < ITEMS / 4; ++v)
-        *reinterpret_cast<int4*>(my_end + 4 * v) = make_int4(e[4 * v], e[4 * v + 1], e[4 * v + 2], e[4 * v + 3]);
-    // the source that covers output lo: 1 + #{ sources of the tile with e <= lo }  (1-based index into the tile)
-    int cnt = 0;
-#pragma unroll
-    for (int k = 0; k < ITEMS; ++k) cnt += (e[k] <= lo) ? 1 : 0;
-    int carry_m = warp_sum_i32(cnt) + 1;
-    int wb = lo;
-    while (wb < hi) {
-#pragma unroll
-        for (int v = 0; v < ITEMS / 4; ++v) *reinterpret_cast<int4*>(my_mark + 4 * v) = make_int4(0, 0, 0, 0);
-        __syncwarp();
-#pragma unroll
-        for (int k = 0; k < ITEMS; ++k) {
-            const int start = k ? e[k - 1] : ep;
-            const unsigned int p = (unsigned int)(start - wb);   // start < wb wraps to a huge value
-            if (e[k] > start && p < (unsigned int)TILE) s_mark[p] = lane * ITEMS + k + 1;
-        }
-        __syncwarp();
-        int v[ITEMS];
-#pragma unroll
-        for (int m = 0; m < ITEMS / 4; ++m) {
-            const int4 x = *reinterpret_cast<const int4*>(my_mark + 4 * m);
-            v[4 * m] = x.x; v[4 * m + 1] = x.y; v[4 * m + 2] = x.z; v[4 * m + 3] = x.w;
-        }
-#pragma unroll
-        for (int k = 1; k < ITEMS; ++k) v[k] = max(v[k], v[k - 1]);
-        int incl = v[ITEMS - 1];
+        for (int v = 0; v < RF_RING / 128; ++v) reinterpret_cast<int4*>(ring)[32 * v + lane] = make_int4(0, 0, 0, 0);
+    }
+
+    // complete window [wb, wb + RF_WIN): prefix maximum of its markers, store, clear, advance.  Lane l owns the outputs
+    // wb + 4 l + {0..3} and wb + 128 + 4 l + {0..3}: both 128-bit stores of the warp are fully coalesced.
+    __device__ __forceinline__ void flush(int lane, int mhi) {
+        int4* r4 = reinterpret_cast<int4*>(ring + (wb & (RF_RING - 1)));
+        int4 a = r4[lane], b = r4[32 + lane];
+        r4[lane] = make_int4(0, 0, 0, 0);
+        r4[32 + lane] = make_int4(0, 0, 0, 0);
+        a.y = max(a.x, a.y); a.z = max(a.y, a.z); a.w = max(a.z, a.w);
+        b.y = max(b.x, b.y); b.z = max(b.y, b.z); b.w = max(b.z, b.w);
+        int ia = a.w, ib = b.w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl = max(incl, t);
+            const int ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
+            if (lane >= o) { ia = max(ia, ta); ib = max(ib, tb); }
         }
-        int excl = __shfl_up_sync(0xffffffffu, incl, 1);
-        if (lane == 0) excl = 0;
-        excl = max(excl, carry_m);
-#pragma unroll
-        for (int m = 0; m < ITEMS / 4; ++m)
-            *reinterpret_cast<int4*>(my_mark + 4 * m) = make_int4(max(v[4 * m], excl), max(v[4 * m + 1], excl),
-                                                                  max(v[4 * m + 2], excl), max(v[4 * m + 3], excl));
-        __syncwarp();
-        const int cntw = min(hi - wb, TILE);
-        int32_t* out = a.idx_out + (wb - a.out_lo);
-        const int vbase = src_base - 1;
-#pragma unroll
-        for (int i = 0; i < ITEMS; ++i) {
-            const int pos = i * 32 + lane;
-            if (pos < cntw) out[pos] = vbase + s_mark[pos];
+        const int tot_a = max(__shfl_sync(0xffffffffu, ia, 31), carry_m);
+        int ea = __shfl_up_sync(0xffffffffu, ia, 1), eb = __shfl_up_sync(0xffffffffu, ib, 1);
+        if (lane == 0) { ea = 0; eb = 0; }
+        ea = max(ea, carry_m);
+        eb = max(eb, tot_a);
+        const int va = vbase;
+        a = make_int4(max(a.x, ea) + va, max(a.y, ea) + va, max(a.z, ea) + va, max(a.w, ea) + va);
+        b = make_int4(max(b.x, eb) + va, max(b.y, eb) + va, max(b.z, eb) + va, max(b.w, eb) + va);
+        carry_m = max(tot_a, __shfl_sync(0xffffffffu, ib, 31));
+        int32_t* o = out + wb + 4 * lane;
+        if (vec_ok && wb >= mlo && wb + RF_WIN <= mhi) {
+            *reinterpret_cast<int4*>(o) = a;
+            *reinterpret_cast<int4*>(o + 128) = b;
+        } else {
+            const int p = wb + 4 * lane;
+            if (p + 0 >= mlo && p + 0 < mhi) o[0] = a.x;
+            if (p + 1 >= mlo && p + 1 < mhi) o[1] = a.y;
+            if (p + 2 >= mlo && p + 2 < mhi) o[2] = a.z;
+            if (p + 3 >= mlo && p + 3 < mhi) o[3] = a.w;
+            if (p + 128 >= mlo && p + 128 < mhi) o[128] = b.x;
+            if (p + 129 >= mlo && p + 129 < mhi) o[129] = b.y;
+            if (p + 130 >= mlo && p + 130 < mhi) o[130] = b.z;
+            if (p + 131 >= mlo && p + 131 < mhi) o[131] = b.w;
         }
-        carry_m = max(__shfl_sync(0xffffffffu, incl, 31), carry_m);
-        wb += TILE;
-        if (wb < hi) {
-            const int end_c = s_end[carry_m - 1];                // where the covering source's run ends
-            if (end_c - wb > RF_HEAVY_MIN) {                     // a heavy source: queue the rest of its run
-                const int target = min(end_c, hi);
-                if (lane == 0) {
-                    const int pieces = (target - wb + RF_PIECE - 1) / RF_PIECE;
-                    const int slot = (int)atomicAdd(a.counters + 2, (unsigned int)pieces);
-                    for (int p = 0; p < pieces; ++p) {
-                        if (slot + p < a.queue_cap)
-                            a.queue[slot + p] = make_int4(wb + p * RF_PIECE, min(wb + (p + 1) * RF_PIECE, target),
-                                                          vbase + carry_m, 0);
-                        else
-                            atomicOr(a.err, GSE_ERR_QUEUE_OVERFLOW);
+        wb += RF_WIN;
+    }
+
+    // one tile: lane's sources have ranks e[0..7], the source before the lane's first has rank ep; the tile's outputs are
+    // [E0, E1); mbase = marker of the tile's first source
+    __device__ __forceinline__ void tile(const int (&e)[RF_ITEMS], int ep, int E0, int E1, int mbase, const FusedArgs& a,
+                                         int lane) {
+        const int E1c = min(E1, hi_al);
+        if (E1c <= max(E0, wb)) return;                           // no outputs of this launch in the tile (warp-uniform)
+        if (E0 < wb && carry_m == 0) {
+            // the launch's outputs start inside this tile's range: the source covering output wb started below it
+            int cnt = 0;
+#pragma unroll
+            for (int k = 0; k < RF_ITEMS; ++k) cnt += (e[k] <= wb) ? 1 : 0;
+            carry_m = mbase + warp_sum_i32(cnt);
+        }
+        const bool maybe_heavy = (E1 - E0) > RF_HEAVY_MIN;
+        for (;;) {
+            __syncwarp();
+            const int limit = wb + RF_RING;
+            const unsigned int ring_s = (unsigned int)__cvta_generic_to_shared(ring);
+            const int m0 = mbase + lane * RF_ITEMS;
+#pragma unroll
+            for (int k = 0; k < RF_ITEMS; ++k) {
+                const int start = k ? e[k - 1] : ep;
+                const bool take = e[k] > start && (unsigned int)(start - wb) < (unsigned int)RF_RING;   // start < wb wraps around
+                sts_if(ring_s + 4u * (unsigned int)(start & (RF_RING - 1)), m0 + k, take);
+            }
+            __syncwarp();
+            bool again = E1c > limit;
+            while (wb + RF_WIN <= min(E1c, limit)) {
+                flush(lane, a.out_hi);
+                if (maybe_heavy && carry_m >= mbase) {
+                    // the source covering the new window is one of this tile's: does its run go on for long?
+                    // (one shuffle per k, then a uniform select: indexing e[] with li would push the array into local memory)
+                    const int li = carry_m - mbase;
+                    int end_c = 0;
+#pragma unroll
+                    for (int k = 0; k < RF_ITEMS; ++k) {
+                        const int v = __shfl_sync(0xffffffffu, e[k], li >> 3);
+                        if ((li & (RF_ITEMS - 1)) == k) end_c = v;
+                    }
+                    const int skip_to = min(end_c, hi_al) & ~(RF_WIN - 1);
+                    if (skip_to - wb > RF_HEAVY_MIN) {            // hand [wb, skip_to) to the whole grid
+                        if (lane == 0) {
+                            const int lo_q = max(wb, a.out_lo), hi_q = min(skip_to, a.out_hi);
+                            const int pieces = hi_q > lo_q ? (hi_q - lo_q + RF_PIECE - 1) / RF_PIECE : 0;
+                            const int slot = pieces ? (int)atomicAdd(a.counters + 2, (unsigned int)pieces) : 0;
+                            for (int p = 0; p < pieces; ++p) {
+                                if (slot + p < a.queue_cap)
+                                    a.queue[slot + p] = make_int4(lo_q + p * RF_PIECE, min(lo_q + (p + 1) * RF_PIECE, hi_q),
+                                                                  vbase + carry_m, 0);
+                                else
+                                    atomicOr(a.err, GSE_ERR_QUEUE_OVERFLOW);
+                            }
+                        }
+                        wb = skip_to;                             // the ring is all zero here: no source starts inside a run
+                        again = E1c > wb;
+                        break;
                     }
                 }
-                wb = target;
             }
+            if (!again) break;
         }
-        __syncwarp();
     }
-}
+
+    // end of the sub-run: its last outputs sit in a partial window
+    __device__ __forceinline__ void finish(int E1, const FusedArgs& a, int lane) {
+        const int mhi = min(E1, a.out_hi);
+        __syncwarp();
+        if (wb < mhi) flush(lane, mhi);
+    }
+};
 
 // drain of the heavy-run queue by every warp of the grid (after all CTAs have finished phase 3)
 __device__ __forceinline__ void drain_queue(const FusedArgs& a, int vb, int nblocks, int lane, int wid) {
@@ -249,21 +324,19 @@ __device__ __forceinline__ void drain_queue(const FusedArgs& a, int vb, int nblo
     }
 }
 
-template <int ITEMS, bool HAS_LL, bool HAS_BASE, bool POW2>
-__global__ void __launch_bounds__(RF_THREADS, ITEMS == 8 ? 4 : 3)
+template <bool HAS_LL, bool HAS_BASE, bool POW2, int MINB>
+__global__ void __launch_bounds__(RF_THREADS, MINB)
 k_resample_fused(const __grid_constant__ FusedArgs a) {
-    constexpr int TILE = 32 * ITEMS;
-    __shared__ __align__(16) int s_mark[RF_WARPS][TILE];
-    __shared__ __align__(16) int s_end[RF_WARPS][TILE];
+    __shared__ __align__(16) int s_ring[RF_WARPS][RF_RING];
     __shared__ double s_wsum[RF_WARPS];
-    __shared__ double s_excl, s_total;
+    __shared__ uint64_t s_part[RF_WARPS][2];
     __shared__ unsigned int s_vb;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int nblocks = gridDim.x;
     if (tid == 0) s_vb = atomicAdd(a.counters, 1u);               // CTAs are numbered in the order they start
     __syncthreads();
     const int vb = (int)s_vb;
-    const float M = HAS_LL ? (float)a.stats[0] : 0.0f;
+    const float nm = HAS_LL ? weight_exp_offset((float)a.stats[0]) : 0.0f;       // -M log2(e), see weight_exp()
     const int sexp = quantisation_exponent(a.stats[1]);
     const float scale_f = __int_as_float((127 + sexp) << 23);     // 2^sexp, 0 <= sexp <= 52
     const double scale_d = ldexp(1.0, sexp);
@@ -272,98 +345,108 @@ k_resample_fused(const __grid_constant__ FusedArgs a) {
     const int64_t rows_per_warp = a.rows_per_block / RF_WARPS;
     const int64_t w0 = min(b0 + wid * rows_per_warp, b1), w1 = min(w0 + rows_per_warp, b1);
 
-    // ---- phase 1: sum of the warp's sub-run -------------------------------------------------------------------
+    // ---- phase 1: sum of the warp's sub-run (four tiles of loads in flight per lane) --------------------------
     double sum = 0.0;
-    for (int64_t t0 = w0; t0 < w1; t0 += TILE) {
-        const int64_t row0 = t0 + (int64_t)lane * ITEMS;
-        if (row0 < w1) {
-            double q[ITEMS];
-            quantise_rows<ITEMS, HAS_LL, HAS_BASE>(a.loglik, a.base, M, scale_f, scale_d, row0, w1, q);
+    if (HAS_LL && !HAS_BASE) {
+        for (int64_t t0 = w0; t0 < w1; t0 += 4 * RF_TILE) {
+            float l[4][RF_ITEMS];
 #pragma unroll
-            for (int k = 0; k < ITEMS; k += 2) sum += q[k] + q[k + 1];
+            for (int u = 0; u < 4; ++u) load_loglik(a.loglik, t0 + u * RF_TILE + (int64_t)lane * RF_ITEMS, w1, l[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                double q[RF_ITEMS];
+                quantise_loglik(l[u], nm, scale_f, q);
+                sum += ((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + q[7]));
+            }
+        }
+    } else {
+        for (int64_t t0 = w0; t0 < w1; t0 += RF_TILE) {
+            double q[RF_ITEMS];
+            quantise_base<HAS_LL>(a.loglik, a.base, nm, scale_d, t0 + (int64_t)lane * RF_ITEMS, w1, q);
+            sum += ((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + q[7]));
         }
     }
     sum = warp_sum_f64(sum);
     if (lane == 0) s_wsum[wid] = sum;
     __syncthreads();
 
-    // ---- phase 2: publish the CTA aggregate, read all of them -------------------------------------------------
-    if (wid == 0) {
+    // ---- phase 2: publish the CTA aggregate; every thread collects a few of the other CTAs' -------------------
+    if (tid == 0) {
         double agg = 0.0;
 #pragma unroll
         for (int w = 0; w < RF_WARPS; ++w) agg += s_wsum[w];
-        if (lane == 0) st_status(a.status + vb, status_pack(ST_AGGREGATE, 0u, (uint64_t)__double2ll_rn(agg)));
+        st_status(a.status + vb, status_pack(ST_AGGREGATE, 0u, (uint64_t)__double2ll_rn(agg)));
+    }
+    {
         uint64_t excl = 0, tot = 0;
-        for (int base = 0; base < nblocks; base += 32) {
-            const int i = base + lane;
-            if (i < nblocks) {
-                uint64_t word = ld_status(a.status + i);
-                while ((word >> 62) == 0ull) { __nanosleep(64); word = ld_status(a.status + i); }
-                const uint64_t v = word & ((1ull << 54) - 1ull);
-                tot += v;
-                if (i < vb) excl += v;
-            }
+        for (int i = tid; i < nblocks; i += RF_THREADS) {
+            uint64_t word = ld_status(a.status + i);
+            while ((word >> 62) == 0ull) { __nanosleep(32); word = ld_status(a.status + i); }
+            const uint64_t v = word & ((1ull << 54) - 1ull);
+            tot += v;
+            if (i < vb) excl += v;
         }
         excl = warp_sum_u64(excl);
         tot = warp_sum_u64(tot);
-        if (lane == 0) {
-            s_excl = __ull2double_rn(excl);
-            s_total = __ull2double_rn(tot);
-            if (vb == 0 && a.total_out) *a.total_out = tot;
-        }
+        if (lane == 0) { s_part[wid][0] = excl; s_part[wid][1] = tot; }
     }
     __syncthreads();
+    uint64_t excl_u = 0, tot_u = 0;
+#pragma unroll
+    for (int w = 0; w < RF_WARPS; ++w) { excl_u += s_part[w][0]; tot_u += s_part[w][1]; }
+    if (tid == 0 && vb == 0 && a.total_out) *a.total_out = tot_u;
 
-    // ---- phase 3: scan + rank + fill, one warp per tile, no block barrier -------------------------------------
+    // ---- phase 3: scan + rank + fill, warp-autonomous ---------------------------------------------------------
     RankConsts rc;
-    rc.Td = s_total;
-    rc.inv_T = 1.0 / rc.Td;
-    rc.n_total = a.n_total;
-    rc.inv_n = a.inv_n;
-    rc.r = a.r_dev ? __ldg(a.r_dev) : a.r;
-    rc.eps = a.n_total * 3.5527136788005009e-15;                  // N * 2^-48
-    rc.n_total_i = a.n_total_i;
-    const bool degenerate = !(rc.Td > 0.0);                       // all weights zero: everything descends from the last row
-    double carry = s_excl;
+    rank_consts(rc, __ull2double_rn(tot_u), a);
+    const bool degenerate = (tot_u == 0ull);                      // all weights zero: everything descends from the last row
+    double carry = __ull2double_rn(excl_u);
 #pragma unroll
     for (int w = 0; w < RF_WARPS; ++w) carry += (w < wid) ? s_wsum[w] : 0.0;
-    int carry_rank = 0;
     if (w0 < w1) {
+        int carry_rank = 0;
         if (!(a.first_shard && w0 == 0) && !degenerate) carry_rank = rank_of<POW2, false, false>(carry, rc);
-        if (degenerate) {
-            if (lane == 0 && vb == 0 && wid == 0) atomicOr(a.err, GSE_ERR_ZERO_WEIGHTS);
+        if (degenerate && lane == 0 && vb == 0 && wid == 0) atomicOr(a.err, GSE_ERR_ZERO_WEIGHTS);
+        WarpFill wf;
+        wf.begin(carry_rank, a, a.src_row0 + (int)w0 - 1, s_ring[wid], lane);
+        float lcur[RF_ITEMS];
+        if (HAS_LL && !HAS_BASE) load_loglik(a.loglik, w0 + (int64_t)lane * RF_ITEMS, w1, lcur);
+        const int ntiles = (int)((w1 - w0 + RF_TILE - 1) / RF_TILE);
+        for (int t = 0; t < ntiles; ++t) {
+            const int64_t row0 = w0 + (int64_t)t * RF_TILE + (int64_t)lane * RF_ITEMS;
+            double q[RF_ITEMS];
+            if (HAS_LL && !HAS_BASE) quantise_loglik(lcur, nm, scale_f, q);
+            else quantise_base<HAS_LL>(a.loglik, a.base, nm, scale_d, row0, w1, q);
+            const double lane_sum = ((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + q[7]));
+            double incl = lane_sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            double C = carry + (incl - lane_sum);                // cumulative weight before the lane's first row
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+            int e[RF_ITEMS];
+            if (!degenerate) {
+#pragma unroll
+                for (int k = 0; k < RF_ITEMS; ++k) {
+                    C += q[k];
+                    e[k] = rank_of<POW2, false, false>(C, rc);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < RF_ITEMS; ++k)          // only the last row of the whole population has offspring
+                    e[k] = (row0 + k >= a.n_src - 1 && a.src_row0 + a.n_src >= (int64_t)a.n_total_i) ? a.n_total_i : 0;
+            }
+            // next tile's rows: in flight while this tile's outputs are filled
+            if (HAS_LL && !HAS_BASE && t + 1 < ntiles) load_loglik(a.loglik, row0 + RF_TILE, w1, lcur);
+            int ep = __shfl_up_sync(0xffffffffu, e[RF_ITEMS - 1], 1);
+            if (lane == 0) ep = carry_rank;
+            const int E1 = __shfl_sync(0xffffffffu, e[RF_ITEMS - 1], 31);
+            wf.tile(e, ep, carry_rank, E1, t * RF_TILE + 1, a, lane);
+            carry_rank = E1;
         }
-    }
-    for (int64_t t0 = w0; t0 < w1; t0 += TILE) {
-        const int64_t row0 = t0 + (int64_t)lane * ITEMS;
-        double q[ITEMS];
-#pragma unroll
-        for (int k = 0; k < ITEMS; ++k) q[k] = 0.0;
-        if (row0 < w1) quantise_rows<ITEMS, HAS_LL, HAS_BASE>(a.loglik, a.base, M, scale_f, scale_d, row0, w1, q);
-#pragma unroll
-        for (int k = 1; k < ITEMS; ++k) q[k] += q[k - 1];
-        double incl = q[ITEMS - 1];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const double t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        const double off = carry + (incl - q[ITEMS - 1]);
-        int e[ITEMS];
-        if (!degenerate) {
-#pragma unroll
-            for (int k = 0; k < ITEMS; ++k) e[k] = rank_of<POW2, false, false>(off + q[k], rc);
-        } else {
-#pragma unroll
-            for (int k = 0; k < ITEMS; ++k)          // only the last row of the whole population has offspring
-                e[k] = (row0 + k >= a.n_src - 1 && a.src_row0 + a.n_src >= (int64_t)a.n_total_i) ? a.n_total_i : 0;
-        }
-        int ep = __shfl_up_sync(0xffffffffu, e[ITEMS - 1], 1);
-        if (lane == 0) ep = carry_rank;
-        const int E1 = __shfl_sync(0xffffffffu, e[ITEMS - 1], 31);
-        warp_fill<ITEMS>(e, ep, carry_rank, E1, a.src_row0 + (int)t0, a, s_mark[wid], s_end[wid], lane);
-        carry += __shfl_sync(0xffffffffu, incl, 31);
-        carry_rank = E1;
+        wf.finish(carry_rank, a, lane);
     }
 
     // ---- tail: wait for every CTA, drain the heavy-run queue, reset the launch state --------------------------
@@ -386,61 +469,59 @@ k_resample_fused(const __grid_constant__ FusedArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// rank + fill on a caller's float64 cumulative sum: no scan, no inter-CTA dependency (every tile reads the element
-// before it for e_{k-1}), any grid.  TIES_RIGHT = the reference's GPU kernel (`cumsum[k] > u` walk,
-// particle.py:223-263, searchsorted side='right'); otherwise the CPU loop (`cumsum[k] < u`, :96-100, side='left').
+// rank + fill on a caller's float64 cumulative sum: no scan, no inter-CTA dependency (every warp reads the element
+// before its chunk for e_{k-1}).  TIES_RIGHT = the reference's GPU kernel (`cumsum[k] > u` walk, particle.py:223-263,
+// searchsorted side='right'); otherwise the CPU loop (`cumsum[k] < u`, :96-100, side='left').
 // ------------------------------------------------------------------------------------------------
-template <int ITEMS, bool POW2, bool TIES_RIGHT>
+template <bool POW2, bool TIES_RIGHT>
 __global__ void __launch_bounds__(RF_THREADS, 4)
-k_resample_search_f64(const __grid_constant__ FusedArgs a, int64_t ntiles) {
-    constexpr int TILE = 32 * ITEMS;
-    __shared__ __align__(16) int s_mark[RF_WARPS][TILE];
-    __shared__ __align__(16) int s_end[RF_WARPS][TILE];
+k_resample_search_f64(const __grid_constant__ FusedArgs a, int64_t tiles_per_warp) {
+    __shared__ __align__(16) int s_ring[RF_WARPS][RF_RING];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     RankConsts rc;
-    rc.Td = a.normalise ? a.cumsum[a.n_src - 1] : 1.0;
-    rc.inv_T = 1.0;
-    rc.n_total = a.n_total;
-    rc.inv_n = a.inv_n;
-    rc.r = a.r_dev ? __ldg(a.r_dev) : a.r;
-    rc.eps = a.n_total * 3.5527136788005009e-15;
-    rc.n_total_i = a.n_total_i;
-    const int64_t warps = (int64_t)gridDim.x * RF_WARPS;
-    for (int64_t tile = (int64_t)blockIdx.x * RF_WARPS + wid; tile < ntiles; tile += warps) {
-        const int64_t t0 = tile * TILE, row0 = t0 + (int64_t)lane * ITEMS;
-        double c[ITEMS];
-        if (row0 + ITEMS <= a.n_src) {
+    rank_consts(rc, a.normalise ? a.cumsum[a.n_src - 1] : 1.0, a);
+    const int64_t w0 = ((int64_t)blockIdx.x * RF_WARPS + wid) * tiles_per_warp * RF_TILE;
+    const int64_t w1 = min(w0 + tiles_per_warp * RF_TILE, a.n_src);
+    if (w0 >= w1) return;
+    int carry_rank = 0;
+    if (w0 > 0) {
+        double cp = a.cumsum[w0 - 1];
+        if (a.normalise) cp = __ddiv_rn(cp, rc.Td);
+        carry_rank = rank_of<POW2, TIES_RIGHT, true>(cp, rc);
+    }
+    WarpFill wf;
+    wf.begin(carry_rank, a, a.src_row0 + (int)w0 - 1, s_ring[wid], lane);
+    for (int64_t t0 = w0; t0 < w1; t0 += RF_TILE) {
+        const int64_t row0 = t0 + (int64_t)lane * RF_ITEMS;
+        double c[RF_ITEMS];
+        if (row0 + RF_ITEMS <= a.n_src) {
 #pragma unroll
-            for (int v = 0; v < ITEMS / 4; ++v) ld_f64x4(a.cumsum + row0 + 4 * v, c + 4 * v);
+            for (int v = 0; v < RF_ITEMS / 4; ++v) ld_f64x4(a.cumsum + row0 + 4 * v, c + 4 * v);
         } else {
             const double last = a.cumsum[a.n_src - 1];           // padding rows repeat the last value: no outputs
 #pragma unroll
-            for (int k = 0; k < ITEMS; ++k) c[k] = (row0 + k < a.n_src) ? a.cumsum[row0 + k] : last;
+            for (int k = 0; k < RF_ITEMS; ++k) c[k] = (row0 + k < a.n_src) ? a.cumsum[row0 + k] : last;
         }
         if (a.normalise) {
 #pragma unroll
-            for (int k = 0; k < ITEMS; ++k) c[k] = __ddiv_rn(c[k], rc.Td);        // cumsum /= cumsum[-1]  (:90)
+            for (int k = 0; k < RF_ITEMS; ++k) c[k] = __ddiv_rn(c[k], rc.Td);        // cumsum /= cumsum[-1]  (:90)
         }
-        int e[ITEMS];
+        int e[RF_ITEMS];
 #pragma unroll
-        for (int k = 0; k < ITEMS; ++k) e[k] = rank_of<POW2, TIES_RIGHT, true>(c[k], rc);
-        if (row0 + ITEMS >= a.n_src) {
+        for (int k = 0; k < RF_ITEMS; ++k) e[k] = rank_of<POW2, TIES_RIGHT, true>(c[k], rc);
+        if (row0 + RF_ITEMS >= a.n_src) {
             // the last row takes whatever is left (TIES_RIGHT with u = 1.0: the reference kernel would index one past
             // the end, particle.py:259-263; a cumsum that does not end at 1.0)
 #pragma unroll
-            for (int k = 0; k < ITEMS; ++k) if (row0 + k >= a.n_src - 1) e[k] = a.n_total_i;
+            for (int k = 0; k < RF_ITEMS; ++k) if (row0 + k >= a.n_src - 1) e[k] = a.n_total_i;
         }
-        int E0 = 0;
-        if (t0 > 0) {
-            double cp = a.cumsum[t0 - 1];
-            if (a.normalise) cp = __ddiv_rn(cp, rc.Td);
-            E0 = rank_of<POW2, TIES_RIGHT, true>(cp, rc);
-        }
-        int ep = __shfl_up_sync(0xffffffffu, e[ITEMS - 1], 1);
-        if (lane == 0) ep = E0;
-        const int E1 = __shfl_sync(0xffffffffu, e[ITEMS - 1], 31);
-        warp_fill<ITEMS>(e, ep, E0, E1, a.src_row0 + (int)t0, a, s_mark[wid], s_end[wid], lane);
+        int ep = __shfl_up_sync(0xffffffffu, e[RF_ITEMS - 1], 1);
+        if (lane == 0) ep = carry_rank;
+        const int E1 = __shfl_sync(0xffffffffu, e[RF_ITEMS - 1], 31);
+        wf.tile(e, ep, carry_rank, E1, (int)(t0 - w0) + 1, a, lane);
+        carry_rank = E1;
     }
+    wf.finish(carry_rank, a, lane);
 }
 
 // queued heavy runs of k_resample_search_f64 (its CTAs do not wait for one another): a second, tiny launch
@@ -462,6 +543,7 @@ static void fill_common(gse_ctx* ctx, FusedArgs& a, double r, int64_t n_total, i
     a.queue_cap = ctx->heavy_queue_cap;
     a.err = ctx->err_dev;
     a.r = r;
+    a.magic_minus_r = RF_MAGIC16 - r;
     a.r_dev = ctx->step_params ? &ctx->step_params->r : NULL;
     a.n_total = (double)n_total;
     a.inv_n = 1.0 / (double)n_total;
@@ -472,24 +554,23 @@ static void fill_common(gse_ctx* ctx, FusedArgs& a, double r, int64_t n_total, i
     a.src_row0 = (int)src_row0;
 }
 
-#define GSE_FUSED_VARIANTS 12
-template <int ITEMS, bool LL, bool BASE, bool POW2>
+template <bool LL, bool BASE, bool POW2, int MINB>
 static int launch_fused(gse_ctx* ctx, FusedArgs& a, int variant, cudaStream_t s) {
     // every CTA must be resident at once (phase 2 and the tail wait on the other CTAs)
     if (ctx->fused_resident[variant] == 0) {
         int per_sm = 0;
-        GSE_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_resample_fused<ITEMS, LL, BASE, POW2>,
+        GSE_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_resample_fused<LL, BASE, POW2, MINB>,
                                                                      RF_THREADS, 0));
         GSE_REQUIRE(per_sm >= 1, "fused resample kernel does not fit an SM");
         ctx->fused_resident[variant] = per_sm * ctx->num_sms;
     }
-    const int64_t group = (int64_t)RF_WARPS * 32 * ITEMS;           // rows of one tile per warp
+    const int64_t group = (int64_t)RF_WARPS * RF_TILE;               // rows of one tile per warp
     const int64_t groups = gse_div_up(a.n_src, group);
     int64_t blocks = groups < ctx->fused_resident[variant] ? groups : ctx->fused_resident[variant];
     a.rows_per_block = gse_div_up(groups, blocks) * group;
     blocks = gse_div_up(a.n_src, a.rows_per_block);
     GSE_REQUIRE(blocks <= ctx->max_tiles, "workspace too small");
-    k_resample_fused<ITEMS, LL, BASE, POW2><<<(unsigned)blocks, RF_THREADS, 0, s>>>(a);
+    k_resample_fused<LL, BASE, POW2, MINB><<<(unsigned)blocks, RF_THREADS, 0, s>>>(a);
     GSE_CHECK_LAUNCH(ctx);
     return GSE_OK;
 }
@@ -519,21 +600,15 @@ extern "C" int gse_resample_fused(gse_ctx* ctx, const float* loglik_dev, const d
     fill_common(ctx, a, r, n_total, out0, n_out, idx_out_dev, src_row0);
     cudaStream_t s = (cudaStream_t)stream;
     const bool pow2 = (n_total & (n_total - 1)) == 0;
-    const int items = ctx->fused_items;
-#define FUSED_CASE(IT, LL, BASE, V)                                                       \
+#define FUSED_CASE(LL, BASE, V)                                                           \
     do {                                                                                  \
-        if (pow2) return launch_fused<IT, LL, BASE, true>(ctx, a, 2 * (V), s);            \
-        return launch_fused<IT, LL, BASE, false>(ctx, a, 2 * (V) + 1, s);                 \
+        if (pow2 && ctx->fused_minb == 3) return launch_fused<LL, BASE, true, 3>(ctx, a, 6 + (V), s);   \
+        if (pow2) return launch_fused<LL, BASE, true, 4>(ctx, a, 2 * (V), s);             \
+        return launch_fused<LL, BASE, false, 4>(ctx, a, 2 * (V) + 1, s);                  \
     } while (0)
-    if (items == 16) {
-        if (loglik_dev && base_dev) FUSED_CASE(16, true, true, 0);
-        else if (loglik_dev) FUSED_CASE(16, true, false, 1);
-        else FUSED_CASE(16, false, true, 2);
-    } else {
-        if (loglik_dev && base_dev) FUSED_CASE(8, true, true, 3);
-        else if (loglik_dev) FUSED_CASE(8, true, false, 4);
-        else FUSED_CASE(8, false, true, 5);
-    }
+    if (loglik_dev && base_dev) FUSED_CASE(true, true, 0);
+    else if (loglik_dev) FUSED_CASE(true, false, 1);
+    else FUSED_CASE(false, true, 2);
 #undef FUSED_CASE
     return GSE_OK;
 }
@@ -557,13 +632,12 @@ extern "C" int gse_resample_search_f64(gse_ctx* ctx, const double* cumsum_dev, i
     a.first_shard = 1;
     fill_common(ctx, a, r, n_total, out0, n_out, idx_out_dev, 0);
     cudaStream_t s = (cudaStream_t)stream;
-    constexpr int ITEMS = 8;
-    const int64_t ntiles = gse_div_up(n_src, 32 * ITEMS);
-    int64_t blocks = gse_div_up(ntiles, RF_WARPS);
-    const int64_t cap = (int64_t)ctx->num_sms * 8;
-    if (blocks > cap) blocks = cap;
+    const int64_t ntiles = gse_div_up(n_src, RF_TILE);
+    const int64_t max_warps = (int64_t)ctx->num_sms * 8 * RF_WARPS;
+    const int64_t tiles_per_warp = gse_div_up(ntiles, max_warps);
+    const int64_t blocks = gse_div_up(gse_div_up(ntiles, tiles_per_warp), RF_WARPS);
     const bool pow2 = (n_total & (n_total - 1)) == 0;
-#define F64_CASE(P, T) k_resample_search_f64<ITEMS, P, T><<<(unsigned)blocks, RF_THREADS, 0, s>>>(a, ntiles)
+#define F64_CASE(P, T) k_resample_search_f64<P, T><<<(unsigned)blocks, RF_THREADS, 0, s>>>(a, tiles_per_warp)
     if (pow2) { if (ties_right) F64_CASE(true, true); else F64_CASE(true, false); }
     else { if (ties_right) F64_CASE(false, true); else F64_CASE(false, false); }
 #undef F64_CASE

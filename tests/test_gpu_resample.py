@@ -205,3 +205,28 @@ def test_all_zero_weights_raise_at_the_next_synchronisation(g):
     pf.resample(r=0.5)
     with pytest.raises(FloatingPointError):
         pf.point_estimate()
+
+
+@pytest.mark.parametrize("N,out0,n_out", [(5000, 0, 5000), (5000, 123, 517), (100003, 4096, 50000), (100003, 99999, 4),
+                                          (1 << 20, 777, 300001)])
+def test_fused_abi_output_subrange(g, N, out0, n_out):
+    """gse_resample_fused called directly with a clipped output range [out0, out0 + n_out) (what a shard of a
+    multi-GPU population asks for) and an unaligned destination."""
+    import ctypes
+    import torch
+    from gpu_se_b200 import _lib
+    rng = numpy.random.default_rng(N + out0)
+    w = rng.random(N) ** 8                     # skewed
+    w[rng.random(N) < 0.5] = 0.0
+    pf = make_pf(g, N, particles=numpy.zeros((N, 5), dtype=numpy.float32))
+    pf.weights = w
+    c, total = pf.cumulative_weights()
+    r = 0.618
+    expect = expected_indices_from_cumsum(c, r)[out0:out0 + n_out]
+    idx = torch.full((n_out + 64,), -7, dtype=torch.int32, device=pf.device)
+    ll, base, stats = pf._weight_sources()
+    _lib.check(_lib.lib.gse_resample_fused(pf._ctx.handle, ll, base, stats.data_ptr(), N, r, N, out0, n_out, 0,
+                                           idx.data_ptr(), None, pf._stream()))
+    got = idx.cpu().numpy()
+    assert numpy.array_equal(got[:n_out], expect)
+    assert (got[n_out:] == -7).all()           # nothing written past the range
