@@ -86,15 +86,20 @@ def measured_peak_gbs():
 # synthetic open-loop trajectory: inputs as sim_base.get_random_io draws them (sim_base.py:196-199),
 # measurements physically consistent with a host plant following the same model
 # ----------------------------------------------------------------------------------------------
-def trajectory(n_steps, seed=0):
-    from gpu_se_b200.model.BioreactorModel import Bioreactor, X_STEADY
+def trajectory(n_steps, seed=0, model=None):
+    """`model` = (f, g, x_steady): host evaluations of the plant.  Our arm uses gpu_se_b200.model.Bioreactor's plain-Python
+    static methods; the reference arm uses the reference's own (or the oracle's) so that it never loads libgse_b200.so."""
+    if model is None:
+        from gpu_se_b200.model.BioreactorModel import Bioreactor, X_STEADY
+        model = (Bioreactor.homeostatic_DEs, Bioreactor.static_outputs, X_STEADY)
+    f, g, x_steady = model
     rng = numpy.random.default_rng(seed)
-    x = numpy.array(X_STEADY, dtype=numpy.float64)
+    x = numpy.array(x_steady, dtype=numpy.float64)
     us, zs = [], []
     for _ in range(n_steps):
         u = numpy.array([rng.uniform(0.03, 0.09), rng.uniform(0.1, 0.3)])
-        x = x + numpy.array(Bioreactor.homeostatic_DEs(x, u, DT))
-        z = numpy.array(Bioreactor.static_outputs(x, u)) + rng.normal(size=2) * numpy.array([0.2, 0.25])
+        x = x + numpy.array(f(x, u, DT), dtype=numpy.float64)
+        z = numpy.array(g(x, u), dtype=numpy.float64) + rng.normal(size=2) * numpy.array([0.2, 0.25])
         us.append(u)
         zs.append(z)
     return us, zs
@@ -163,15 +168,65 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------
-# CPU arm: the loop-faithful oracle port (the reference's per-particle algorithm, particle.py:54-103)
+# CPU arm.  The reference's OWN classes (filter.ParticleFilter / GaussianSumUnscentedKalmanFilter, numpy code path,
+# filter/particle.py:9-114, filter/gs_ukf.py:9-183) imported unmodified from /root/reference or from the git-ignored copy
+# oracle/_ref that oracle/make_ref.py makes and gpurun ships; only when neither is present, the loop-faithful oracle port
+# of the same per-particle algorithm.  Single-threaded Python either way: 1 core.
 # ----------------------------------------------------------------------------------------------
+def _oracle_model():
+    from oracle import bioreactor
+    return (bioreactor.increment_scalar, bioreactor.outputs_scalar, bioreactor.X_STEADY)
+
+
+def _reference_parts():
+    """(R, f, g, state, meas, x0) built from the reference's own classes, or None when it is not available."""
+    import warnings
+    from oracle import mixture, ref_loader
+    if not ref_loader.available():
+        return None
+    warnings.simplefilter("ignore")
+    R = ref_loader.load()
+    MGS = R.gaussian_sum_dist.MultivariateGaussianSum
+    f, g = R.model.Bioreactor.homeostatic_DEs, R.model.Bioreactor.static_outputs
+    from oracle import bioreactor
+    x_ss = numpy.asarray(bioreactor.X_STEADY)      # = Bioreactor.find_SS(...) (sim_base.py:46-53; tests pin the equality)
+    state = MGS(numpy.zeros((2, 5)), mixture.STATE_COVS, numpy.array([0.75, 0.25]), library=numpy)
+    meas = MGS(mixture.MEAS_MEANS, mixture.MEAS_COVS, numpy.array([0.85, 0.15]), library=numpy)
+    x0 = MGS(numpy.zeros((2, 5)) + x_ss[None, :], mixture.STATE_COVS, numpy.array([0.75, 0.25]), library=numpy)
+    return R, f, g, state, meas, x0, ("reference copy oracle/_ref" if ref_loader.is_copy() else "/root/reference")
+
+
+def cpu_reference_run(log2n, steps, warmup, gsf=False):
+    """predict(u, 1.) -> update(u, z) -> resample() of the reference's own CPU class; returns None if unavailable."""
+    parts = _reference_parts()
+    if parts is None:
+        return None
+    R, f, g, state, meas, x0, where = parts
+    n = 1 << log2n
+    numpy.random.seed(0)
+    cls = R.filter.GaussianSumUnscentedKalmanFilter if gsf else R.filter.ParticleFilter
+    flt = cls(f, g, n, x0, state, meas)
+    us, zs = trajectory(steps + warmup, seed=1, model=(f, g, numpy.asarray(x0.means[0], dtype=numpy.float64)))
+    times = []
+    for k in range(steps + warmup):
+        t = time.perf_counter()
+        flt.predict(us[k], DT)
+        flt.update(us[k], zs[k])
+        flt.resample()
+        dtm = time.perf_counter() - t
+        if k >= warmup:
+            times.append(dtm)
+    total = sum(times)
+    return n * len(times) / total, 1e3 * total / len(times), n, where
+
+
 def cpu_port_run(log2n, steps, warmup, vectorised=False):
     from oracle import bioreactor, mixture, particle
     n = 1 << log2n
     state, meas = mixture.benchmark_noise()
     numpy.random.seed(0)
     pf = particle.ParticleFilterOracle(n, mixture.benchmark_x0(bioreactor.X_STEADY), state, meas)
-    us, zs = trajectory(steps + warmup, seed=1)
+    us, zs = trajectory(steps + warmup, seed=1, model=_oracle_model())
     times = []
     for k in range(steps + warmup):
         t = time.perf_counter()
@@ -194,28 +249,43 @@ def cpu_port_run(log2n, steps, warmup, vectorised=False):
     return n * len(times) / total, 1e3 * total / len(times), n
 
 
-def cpu_baseline(log2n):
-    value, ms, n = cpu_port_run(log2n, steps=4, warmup=1)
+def cpu_baseline(log2n, steps=10):
+    """~10 s of the reference's own ParticleFilter on one host core (rank 0, N = 1 only)."""
+    ref = cpu_reference_run(log2n, steps=steps, warmup=1)
+    if ref is not None:
+        value, ms, n, where = ref
+        out = {"value": value, "unit": UNIT, "cores": 1, "kind": "reference",
+               "sample": "the reference's own filter.ParticleFilter (numpy path, filter/particle.py:9-114; %s), 2^%d particles "
+                         "x %d steps, %.1f ms/step; host has %d cores, the reference is single-threaded Python"
+                         % (where, log2n, steps, ms, os.cpu_count())}
+    else:
+        value, ms, n = cpu_port_run(log2n - 1, steps=4, warmup=1)
+        out = {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": "oracle loop port (per-particle Python loops as filter/particle.py:54-103; the reference copy oracle/_ref "
+                         "is absent), 2^%d particles x 4 steps, %.1f ms/step; host has %d cores" % (log2n - 1, ms, os.cpu_count())}
     vec_value, vec_ms, vec_n = cpu_port_run(20, steps=2, warmup=1, vectorised=True)
-    return {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": "oracle loop port (per-particle Python loops as filter/particle.py:54-103), "
-                      "2^%d particles x 4 steps, %.1f ms/step; host has %d cores, the reference is single-threaded"
-                      % (log2n, ms, os.cpu_count()),
-            "vectorised_numpy_value": vec_value,
-            "vectorised_numpy_sample": "oracle vectorised float64 numpy port, 2^20 particles x 2 steps, %.1f ms/step" % vec_ms}
+    out["vectorised_numpy_value"] = vec_value
+    out["vectorised_numpy_sample"] = "oracle vectorised float64 numpy port, 2^20 particles x 2 steps, %.1f ms/step" % vec_ms
+    return out
 
 
-def cpu_baseline_gsf(log2n=10, steps=5):
-    """GS-UKF on the host: the vectorised float64 oracle port of filter/gs_ukf.py:45-171 (the reference's own
-    CPU class loops over N x 11 Python calls of f and is ~30x slower than this)."""
+def cpu_baseline_gsf(log2n=9, steps=8):
+    """GS-UKF on the host: the reference's own GaussianSumUnscentedKalmanFilter (N x 11 Python calls of f per predict,
+    gs_ukf.py:82-103); the vectorised float64 oracle port when the reference is not available."""
+    ref = cpu_reference_run(log2n, steps=steps, warmup=1, gsf=True)
+    if ref is not None:
+        value, ms, n, where = ref
+        return {"value": value, "unit": "components/s", "cores": 1, "kind": "reference",
+                "sample": "the reference's own filter.GaussianSumUnscentedKalmanFilter (numpy path, filter/gs_ukf.py:9-183; %s), "
+                          "2^%d components x %d steps, %.1f ms/step" % (where, log2n, steps, ms)}
     from oracle import bioreactor, gs_ukf, mixture
-    n = 1 << log2n
+    n = 1 << 10
     state, meas = mixture.benchmark_noise()
     numpy.random.seed(0)
     f = gs_ukf.GSUKFOracle(n, mixture.benchmark_x0(bioreactor.X_STEADY), state, meas)
-    us, zs = trajectory(steps + 1, seed=1)
+    us, zs = trajectory(6, seed=1, model=_oracle_model())
     times = []
-    for k in range(steps + 1):
+    for k in range(6):
         t = time.perf_counter()
         f.predict(us[k], DT)
         f.update(us[k], zs[k])
@@ -224,8 +294,8 @@ def cpu_baseline_gsf(log2n=10, steps=5):
             times.append(time.perf_counter() - t)
     total = sum(times)
     return {"value": n * len(times) / total, "unit": "components/s", "cores": 1, "kind": "port",
-            "sample": "oracle vectorised float64 numpy port of filter/gs_ukf.py:45-171, 2^%d components x %d steps, "
-                      "%.1f ms/step" % (log2n, len(times), 1e3 * total / len(times))}
+            "sample": "oracle vectorised float64 numpy port of filter/gs_ukf.py:45-171, 2^10 components x %d steps, "
+                      "%.1f ms/step" % (len(times), 1e3 * total / len(times))}
 
 
 def run_reference(args):
@@ -234,16 +304,24 @@ def run_reference(args):
         return
     log2n = args.cpu_log2n
     t0 = time.perf_counter()
-    value, ms, n = cpu_port_run(log2n, args.steps, max(args.warmup, 1))
+    ref = cpu_reference_run(log2n, args.steps, max(args.warmup, 1))
+    if ref is not None:
+        value, ms, n, where = ref
+        kind = "reference"
+        sample = ("the reference's own filter.ParticleFilter (numpy path, filter/particle.py:9-114; %s): predict(u, 1.) -> "
+                  "update(u, z) -> resample(), 2^%d particles x %d steps" % (where, log2n, args.steps))
+    else:
+        value, ms, n = cpu_port_run(log2n, args.steps, max(args.warmup, 1))
+        kind = "port"
+        sample = ("oracle loop port of filter/particle.py:54-103 (reference copy oracle/_ref absent), 2^%d particles x %d steps"
+                  % (log2n, args.steps))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.log2n),
-                       "sample": "bounded CPU sample of 2^%d particles per step (cost is linear in N)" % log2n,
+                       "sample": "bounded CPU sample of 2^%d particles per step (per-particle Python loops: cost is linear in N)" % log2n,
                        "particles_per_step": n},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
-                             "sample": "oracle loop port of filter/particle.py:54-103 (the Python reference cannot "
-                                       "travel to the GPU box), 2^%d particles x %d steps" % (log2n, args.steps)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.perf_counter() - t0}
     emit(line)
@@ -429,7 +507,7 @@ def run_ours(args):
         "last_estimate": [float(v) for v in est],
     }
     if not args.no_cpu_baseline and world == 1:
-        line["cpu_baseline"] = cpu_baseline(args.cpu_log2n) if args.workload == "pf" else cpu_baseline_gsf()
+        line["cpu_baseline"] = cpu_baseline(args.cpu_log2n + 1) if args.workload == "pf" else cpu_baseline_gsf()
     emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -90,6 +90,7 @@ SIGNATURES = {
     "gse_gsf_update": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_dbl_p, c_dbl_p, c_vp, c_vp]),
     "gse_gsf_sigma_points": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp]),
     "gse_gsf_moments": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "gse_ctx_read_trace": (c_i64, [c_vp, c_vp, c_i64]),
     "gse_launch_count": (c_i64, [c_vp]),
 }
 

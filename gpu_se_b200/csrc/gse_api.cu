@@ -75,9 +75,13 @@ static int check_mixture(const gse_mixture* m, int nx) {
 // parameters are stored float32 by the reference (MultivariateGaussianSum.py:29-31)
 static double f32(double v) { return (double)(float)v; }
 
-int gse_build_sampler5(const gse_mixture* m, MixSampler5* out) {
-    int rc = check_mixture(m, GSE_NX);
-    if (rc) return rc;
+// Sampler of an nx-dimensional mixture, nx <= 5: mean and Cholesky factor are padded to five dimensions (zero mean, zero
+// factor rows), the kernels write the first nx columns.
+int gse_build_sampler(const gse_mixture* m, MixSampler5* out, int* nx_out) {
+    GSE_REQUIRE(m != NULL, "mixture is NULL");
+    GSE_REQUIRE(m->nd >= 1 && m->nd <= GSE_MAX_ND, "mixture nd out of range");
+    GSE_REQUIRE(m->nx >= 1 && m->nx <= GSE_NX, "mixture nx out of range");
+    const int nx = m->nx;
     memset(out, 0, sizeof(*out));
     out->nd = m->nd;
     double wsum = 0.0;
@@ -89,24 +93,32 @@ int gse_build_sampler5(const gse_mixture* m, MixSampler5* out) {
         acc += f32(m->weights[d]) / wsum;
         out->cdf[d] = (float)acc;
         double C[25], L[25];
-        for (int i = 0; i < 25; ++i) C[i] = f32(m->covs[d * 25 + i]);
-        if (chol_lower(C, 5, L) != 0) {
-            gse_set_error("state mixture component %d covariance is not positive definite", d);
+        for (int i = 0; i < nx * nx; ++i) C[i] = f32(m->covs[d * nx * nx + i]);
+        if (chol_lower(C, nx, L) != 0) {
+            gse_set_error("mixture component %d covariance is not positive definite", d);
             return GSE_ELINALG;
         }
         int t = 0;
         for (int i = 0; i < 5; ++i) {
-            out->mean[d][i] = (float)m->means[d * 5 + i];
+            out->mean[d][i] = i < nx ? (float)m->means[d * nx + i] : 0.0f;
             for (int j = 0; j <= i; ++j) {
-                out->L[d][t++] = (float)L[i * 5 + j];
-                if (i != j && L[i * 5 + j] != 0.0) diag = 0;
+                const double v = (i < nx) ? L[i * nx + j] : 0.0;
+                out->L[d][t++] = (float)v;
+                if (i != j && v != 0.0) diag = 0;
             }
         }
     }
     out->cdf[m->nd - 1] = 1.0f;
     for (int d = m->nd; d < GSE_MAX_ND; ++d) out->cdf[d] = 2.0f;
     out->diag = diag;
+    if (nx_out) *nx_out = nx;
     return GSE_OK;
+}
+
+int gse_build_sampler5(const gse_mixture* m, MixSampler5* out) {
+    int rc = check_mixture(m, GSE_NX);
+    if (rc) return rc;
+    return gse_build_sampler(m, out, NULL);
 }
 
 int gse_build_densityN(const gse_mixture* m, MixDensityN* out) {
@@ -206,7 +218,7 @@ extern "C" int gse_ctx_create(int device, int model_id, int64_t n_max, const gse
     const size_t o_range = off; off = align_up(off + sizeof(int64_t) * 8, 256);    // [0..1] range, [4] 1/T
     // fused resample: one status word per co-resident CTA (<= 32 per SM); queue of heavy runs -- every entry covers
     // more than 4096 outputs of its own, cut into pieces of <= 65536 (gse_resample_fused.cu)
-    const size_t n_fused_status = 32 * 256;
+    const size_t n_fused_status = 2 * 4096 + 8;       // aggregates + prefixes (gse_resample_fused.cu: RF_MAX_BLOCKS)
     c->heavy_queue_cap = (int)(n_max / 4096 + n_max / 65536 + 64);
     const size_t o_fstatus = off; off = align_up(off + sizeof(uint64_t) * n_fused_status, 256);
     const size_t o_queue = off; off = align_up(off + sizeof(int4) * (size_t)c->heavy_queue_cap, 256);
@@ -254,6 +266,10 @@ extern "C" int gse_ctx_create(int device, int model_id, int64_t n_max, const gse
         const char* v = getenv("GSE_FUSED_MINB");                 // tuning knob: 3 = 85 registers, 24 warps per SM
         c->fused_minb = (v && atoi(v) == 3) ? 3 : 4;
     }
+    if (getenv("GSE_FUSED_TRACE")) {
+        if (cudaMalloc((void**)&c->fused_trace, sizeof(unsigned long long) * 8 * 4096) != cudaSuccess) c->fused_trace = NULL;
+        else cudaMemset(c->fused_trace, 0, sizeof(unsigned long long) * 8 * 4096);
+    }
     // device-error word: host-mapped so that reading it never needs a copy or a synchronisation of its own
     e = cudaHostAlloc((void**)&c->err_host, 64, cudaHostAllocMapped);
     if (e == cudaSuccess) {
@@ -276,6 +292,7 @@ extern "C" int gse_ctx_destroy(gse_ctx* ctx) {
     gse_device_guard guard(ctx->device);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->err_host) cudaFreeHost(ctx->err_host);
+    if (ctx->fused_trace) cudaFree(ctx->fused_trace);
     if (ctx->params_block) {
         cudaFree(ctx->params_block);
         cudaFreeHost(ctx->params_ring);
@@ -359,6 +376,14 @@ extern "C" int gse_ctx_use_step_params(gse_ctx* ctx, int enable) {
 }
 
 extern "C" int64_t gse_launch_count(const gse_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int64_t gse_ctx_read_trace(gse_ctx* ctx, uint64_t* host_out, int64_t max_words) {
+    if (!ctx || !ctx->fused_trace || !host_out || max_words <= 0) return 0;
+    gse_device_guard guard(ctx->device);
+    const int64_t n = max_words < 8 * 4096 ? max_words : 8 * 4096;
+    if (cudaMemcpy(host_out, ctx->fused_trace, sizeof(uint64_t) * (size_t)n, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return n;
+}
 
 extern "C" unsigned int gse_ctx_errors(gse_ctx* ctx, int clear) {
     if (!ctx || !ctx->err_host) return 0u;

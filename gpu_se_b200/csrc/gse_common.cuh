@@ -110,6 +110,7 @@ struct gse_ctx {
     int heavy_queue_cap;
     int fused_resident[12];   // co-resident CTAs of each k_resample_fused instantiation (0: not queried yet)
     int predict_minb;         // CTAs per SM of the benchmark's predict specialisation (5; GSE_PREDICT_MINB = 4 / 6 for tuning)
+    unsigned long long* fused_trace;   // GSE_FUSED_TRACE=1: per-CTA phase time stamps of the last fused resample (debugging)
     int fused_minb;           // CTAs per SM the fused kernel is compiled for (4; GSE_FUSED_MINB=3 for tuning)
     unsigned int* err_host;   // device-error word: pinned, mapped host memory the kernels OR their GSE_ERR_* bits into
     unsigned int* err_dev;    // its device alias
@@ -125,6 +126,7 @@ struct gse_ctx {
 };
 
 int gse_build_sampler5(const gse_mixture* m, MixSampler5* out);
+int gse_build_sampler(const gse_mixture* m, MixSampler5* out, int* nx_out);
 int gse_build_density2(const gse_mixture* m, MixDensity2* out);
 int gse_build_densityN(const gse_mixture* m, MixDensityN* out);
 

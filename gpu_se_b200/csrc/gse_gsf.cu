@@ -39,8 +39,40 @@ __device__ __forceinline__ bool cholesky5(const float P[15], float jitter, float
     return ok;
 }
 
-__device__ __forceinline__ void cholesky5_retry(const float P[15], float L[15]) {
-    if (!cholesky5(P, 0.0f, L)) cholesky5(P, 1e-10f, L);     // + 1e-10 * I  (gs_ukf.py:75)
+// float64 Cholesky of P + jitter * I (the reference's retry: `covariances + 1e-10 * numpy.eye(Nx)` is a float64 array,
+// gs_ukf.py:75), result rounded to float32 as `sigmas[:, 1:Nx+1, :] += stds` rounds it (:77)
+__device__ __noinline__ bool cholesky5_f64(const float P[15], double jitter, float L[15]) {
+    double Ld[15];
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        double d = (double)P[tri(j, j)] + jitter;
+#pragma unroll
+        for (int k = 0; k < j; ++k) d -= Ld[tri(j, k)] * Ld[tri(j, k)];
+        ok = ok && (d > 0.0);
+        const double sd = sqrt(d);
+        Ld[tri(j, j)] = sd;
+#pragma unroll
+        for (int i = j + 1; i < 5; ++i) {
+            double v = (double)P[tri(i, j)];
+#pragma unroll
+            for (int k = 0; k < j; ++k) v -= Ld[tri(i, k)] * Ld[tri(j, k)];
+            Ld[tri(i, j)] = v / sd;
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 15; ++t) L[t] = (float)Ld[t];
+    return ok;
+}
+
+// numpy.linalg.cholesky(covariances), and on LinAlgError the retry with + 1e-10 I (gs_ukf.py:72-75).  The reference
+// retries the WHOLE batch when any component fails; here every component decides for itself (a batch-wide retry
+// cannot be reproduced by a population that is streamed and sharded).  A component that still fails -- the reference
+// raises LinAlgError -- sets GSE_ERR_CHOLESKY in the context's error word.
+__device__ __forceinline__ void cholesky5_retry(const float P[15], float L[15], unsigned int* err) {
+    if (!cholesky5(P, 0.0f, L)) {
+        if (!cholesky5_f64(P, 1e-10, L)) atomicOr(err, GSE_ERR_CHOLESKY);
+    }
 }
 
 // sigma point s of (m, L): m, m + L[:, j], m - L[:, j]   (gs_ukf.py:76-78), float32 adds
@@ -60,7 +92,7 @@ __device__ __forceinline__ void sigma_point(const float m[5], const float L[15],
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GSF_THREADS)
 k_gsf_sigma_points(const float* __restrict__ mean, const float* __restrict__ cov, int64_t ld, int64_t n,
-                   float* __restrict__ out, int64_t ldo) {
+                   float* __restrict__ out, int64_t ldo, unsigned int* err) {
     const int64_t i = (int64_t)blockIdx.x * GSF_THREADS + threadIdx.x;
     if (i >= n) return;
     float m[5], P[15], L[15];
@@ -68,7 +100,7 @@ k_gsf_sigma_points(const float* __restrict__ mean, const float* __restrict__ cov
     for (int j = 0; j < 5; ++j) m[j] = mean[j * ld + i];
 #pragma unroll
     for (int j = 0; j < 15; ++j) P[j] = cov[j * ld + i];
-    cholesky5_retry(P, L);
+    cholesky5_retry(P, L, err);
 #pragma unroll
     for (int s = 0; s < GSE_NSIGMA; ++s) {
         float x[5];
@@ -84,7 +116,7 @@ extern "C" int gse_gsf_sigma_points(gse_ctx* ctx, const float* mean_dev, const f
     gse_device_guard guard(ctx->device);
     GSE_REQUIRE(n >= 1 && ld >= n && ld_out >= n, "n / ld out of range");
     k_gsf_sigma_points<<<(unsigned)gse_div_up(n, GSF_THREADS), GSF_THREADS, 0, (cudaStream_t)stream>>>(
-        mean_dev, cov_dev, ld, n, out_dev, ld_out);
+        mean_dev, cov_dev, ld, n, out_dev, ld_out, ctx->err_dev);
     GSE_CHECK_LAUNCH(ctx);
     return GSE_OK;
 }
@@ -97,7 +129,8 @@ __global__ void __launch_bounds__(GSF_THREADS)
 k_gsf_predict(const float* mean_src, const float* cov_src, int64_t lds, const int32_t* __restrict__ idx,
               float* mean, float* cov, int64_t ld, int64_t n, ModelInputs in_arg,
               const __grid_constant__ MixSampler5 sp, uint32_t k0, uint32_t k1, uint32_t step, int64_t index0,
-              const float* __restrict__ noise, int64_t ldn, const gse_step_params* __restrict__ params) {
+              const float* __restrict__ noise, int64_t ldn, const gse_step_params* __restrict__ params,
+              unsigned int* err) {
     const int64_t i = (int64_t)blockIdx.x * GSF_THREADS + threadIdx.x;
     if (i >= n) return;
     const ModelInputs in = model_inputs(in_arg, params, 1);
@@ -108,7 +141,7 @@ k_gsf_predict(const float* mean_src, const float* cov_src, int64_t lds, const in
     for (int j = 0; j < 5; ++j) m[j] = mean_src[j * lds + is];
 #pragma unroll
     for (int j = 0; j < 15; ++j) P[j] = cov_src[j * lds + is];
-    cholesky5_retry(P, L);
+    cholesky5_retry(P, L, err);
 
     float sg[GSE_NSIGMA][5];
     double msum[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
@@ -178,11 +211,11 @@ extern "C" int gse_gsf_predict(gse_ctx* ctx, const float* mean_src_dev, const fl
     cudaStream_t s = (cudaStream_t)stream;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     if (noise_dev)
-        k_gsf_predict<true, true><<<blocks, GSF_THREADS, 0, s>>>(mean_src_dev, cov_src_dev, ld_src, idx_dev, mean_dev, cov_dev, ld, n, in, ctx->state_sampler, k0, k1, (uint32_t)step, index0, noise_dev, ld_noise, ctx->step_params);
+        k_gsf_predict<true, true><<<blocks, GSF_THREADS, 0, s>>>(mean_src_dev, cov_src_dev, ld_src, idx_dev, mean_dev, cov_dev, ld, n, in, ctx->state_sampler, k0, k1, (uint32_t)step, index0, noise_dev, ld_noise, ctx->step_params, ctx->err_dev);
     else if (ctx->state_sampler.diag)
-        k_gsf_predict<true, false><<<blocks, GSF_THREADS, 0, s>>>(mean_src_dev, cov_src_dev, ld_src, idx_dev, mean_dev, cov_dev, ld, n, in, ctx->state_sampler, k0, k1, (uint32_t)step, index0, NULL, 0, ctx->step_params);
+        k_gsf_predict<true, false><<<blocks, GSF_THREADS, 0, s>>>(mean_src_dev, cov_src_dev, ld_src, idx_dev, mean_dev, cov_dev, ld, n, in, ctx->state_sampler, k0, k1, (uint32_t)step, index0, NULL, 0, ctx->step_params, ctx->err_dev);
     else
-        k_gsf_predict<false, false><<<blocks, GSF_THREADS, 0, s>>>(mean_src_dev, cov_src_dev, ld_src, idx_dev, mean_dev, cov_dev, ld, n, in, ctx->state_sampler, k0, k1, (uint32_t)step, index0, NULL, 0, ctx->step_params);
+        k_gsf_predict<false, false><<<blocks, GSF_THREADS, 0, s>>>(mean_src_dev, cov_src_dev, ld_src, idx_dev, mean_dev, cov_dev, ld, n, in, ctx->state_sampler, k0, k1, (uint32_t)step, index0, NULL, 0, ctx->step_params, ctx->err_dev);
     GSE_CHECK_LAUNCH(ctx);
     return GSE_OK;
 }
@@ -194,7 +227,7 @@ extern "C" int gse_gsf_predict(gse_ctx* ctx, const float* mean_src_dev, const fl
 __global__ void __launch_bounds__(GSF_THREADS)
 k_gsf_update(float* __restrict__ mean, float* __restrict__ cov, int64_t ld, int64_t n, const float* loglik_in,
              float* loglik, double z0, double z1, const __grid_constant__ MixDensity2 md, float* block_max, float* block_sum,
-             unsigned int* ticket, double* stats, const gse_step_params* __restrict__ params) {
+             unsigned int* ticket, double* stats, const gse_step_params* __restrict__ params, unsigned int* err) {
     if (params) { z0 = params->z[0]; z1 = params->z[1]; }
     const int64_t i = (int64_t)blockIdx.x * GSF_THREADS + threadIdx.x;
     float vals[1] = {0.0f};
@@ -205,7 +238,7 @@ k_gsf_update(float* __restrict__ mean, float* __restrict__ cov, int64_t ld, int6
         for (int j = 0; j < 5; ++j) m[j] = mean[j * ld + i];
 #pragma unroll
         for (int j = 0; j < 15; ++j) P[j] = cov[j * ld + i];
-        cholesky5_retry(P, L);
+        cholesky5_retry(P, L, err);
         constexpr double inv_wsum = 1.0 / ((double)W_SIGMA_0 + 10.0 * (double)W_SIGMA_I);
         // pass 1: eta mean (:126)
         double eta[GSE_NSIGMA][2];
@@ -242,10 +275,21 @@ k_gsf_update(float* __restrict__ mean, float* __restrict__ cov, int64_t ld, int6
                 pxy[a][1] = fma(w * ds, d1, pxy[a][1]);
             }
         }
-        // K = P_xy P_yy^-1 (:132-133): closed-form 2x2 inverse
+        // K = P_xy pinv(P_yy) (:132-133).  P_yy is symmetric positive semi-definite 2x2: closed-form inverse; when its
+        // smaller eigenvalue is below numpy.linalg.pinv's cut-off (1e-15 of the larger) the pseudo-inverse of the
+        // rank-one matrix, P_yy / trace^2 (zero for the zero matrix).  Anything else -- NaN, negative determinant: not
+        // a covariance -- is flagged in the error word.
         const double det = pyy00 * pyy11 - pyy01 * pyy01;
-        const double inv_det = 1.0 / det;                               // one division, three products
-        const double i00 = pyy11 * inv_det, i01 = -pyy01 * inv_det, i11 = pyy00 * inv_det;
+        const double tr = pyy00 + pyy11;
+        double i00, i01, i11;
+        if (det > 1e-15 * tr * tr) {                                    // lambda_min / lambda_max ~ det / tr^2
+            const double inv_det = 1.0 / det;                           // one division, three products
+            i00 = pyy11 * inv_det; i01 = -pyy01 * inv_det; i11 = pyy00 * inv_det;
+        } else {
+            if (!(det >= -1e-12 * tr * tr) || !(tr >= 0.0)) atomicOr(err, GSE_ERR_SINGULAR_PYY);
+            const double s2 = tr > 0.0 ? 1.0 / (tr * tr) : 0.0;
+            i00 = pyy00 * s2; i01 = pyy01 * s2; i11 = pyy11 * s2;
+        }
         double K[5][2];
 #pragma unroll
         for (int a = 0; a < 5; ++a) {
@@ -290,7 +334,7 @@ extern "C" int gse_gsf_update(gse_ctx* ctx, float* mean_dev, float* cov_dev, int
     GSE_REQUIRE((int64_t)blocks <= ctx->max_blocks, "workspace too small");
     k_gsf_update<<<blocks, GSF_THREADS, 0, (cudaStream_t)stream>>>(mean_dev, cov_dev, ld, n, loglik_in_dev, loglik_dev, z[0], z[1],
                                                                    ctx->meas_density, ctx->block_max, ctx->block_sum,
-                                                                   ctx->ticket, stats_dev, ctx->step_params);
+                                                                   ctx->ticket, stats_dev, ctx->step_params, ctx->err_dev);
     GSE_CHECK_LAUNCH(ctx);
     return GSE_OK;
 }

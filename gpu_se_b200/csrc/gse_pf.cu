@@ -20,7 +20,7 @@ static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; 
 // ------------------------------------------------------------------------------------------------
 template <bool DIAG>
 __global__ void __launch_bounds__(PF_THREADS)
-k_mixture_draw(float* __restrict__ x, int64_t ld, int64_t n, const __grid_constant__ MixSampler5 sp,
+k_mixture_draw(float* __restrict__ x, int64_t ld, int64_t n, int ncols, const __grid_constant__ MixSampler5 sp,
                uint32_t k0, uint32_t k1, uint32_t step, int64_t index0) {
     const int64_t g = (int64_t)blockIdx.x * PF_THREADS + threadIdx.x;
     const int64_t row0 = g * ROWS_PER_THREAD;
@@ -35,7 +35,7 @@ k_mixture_draw(float* __restrict__ x, int64_t ld, int64_t n, const __grid_consta
     }
 #pragma unroll
     for (int j = 0; j < 5; ++j)
-        st_stream4(x + j * ld + row0, make_float4(v[j][0], v[j][1], v[j][2], v[j][3]));
+        if (j < ncols) st_stream4(x + j * ld + row0, make_float4(v[j][0], v[j][1], v[j][2], v[j][3]));
 }
 
 extern "C" int gse_mixture_draw(gse_ctx* ctx, const gse_mixture* mix, float* x_dev, int64_t ld, int64_t n,
@@ -46,15 +46,16 @@ extern "C" int gse_mixture_draw(gse_ctx* ctx, const gse_mixture* mix, float* x_d
     if (n == 0) return GSE_OK;
     CHECK_SOA(x_dev, ld, n);
     MixSampler5 sp;
-    int rc = gse_build_sampler5(mix, &sp);
+    int nx = 0;
+    int rc = gse_build_sampler(mix, &sp, &nx);
     if (rc) return rc;
     const int64_t groups = gse_div_up(n, ROWS_PER_THREAD);
     const unsigned blocks = (unsigned)gse_div_up(groups, PF_THREADS);
     cudaStream_t s = (cudaStream_t)stream;
     if (sp.diag)
-        k_mixture_draw<true><<<blocks, PF_THREADS, 0, s>>>(x_dev, ld, n, sp, (uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)step, index0);
+        k_mixture_draw<true><<<blocks, PF_THREADS, 0, s>>>(x_dev, ld, n, nx, sp, (uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)step, index0);
     else
-        k_mixture_draw<false><<<blocks, PF_THREADS, 0, s>>>(x_dev, ld, n, sp, (uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)step, index0);
+        k_mixture_draw<false><<<blocks, PF_THREADS, 0, s>>>(x_dev, ld, n, nx, sp, (uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)step, index0);
     GSE_CHECK_LAUNCH(ctx);
     return GSE_OK;
 }

@@ -34,6 +34,7 @@
 #define RF_PIECE 65536           // queued runs are cut into pieces of at most this many outputs (one warp each)
 
 #define RF_TWO52 4503599627370496.0
+#define RF_MAX_BLOCKS 4096       // status words: [0, 4096) CTA aggregates, [4096, 8192] exclusive prefixes + total
 
 struct FusedArgs {
     const float* loglik;       // NULL: weights = base
@@ -43,7 +44,7 @@ struct FusedArgs {
     int64_t n_src;
     int64_t rows_per_block;    // multiple of RF_WARPS * RF_TILE
     uint64_t* status;          // one word per CTA, zero between launches
-    unsigned int* counters;    // [0] start ticket, [1] CTAs past phase 3, [2] queue length, [3] CTAs past the drain
+    unsigned int* counters;    // [0] start ticket, [1] CTAs past phase 3, [2] queue length, [3] CTAs past the drain, [4] aggregates published
     int4* queue;
     int queue_cap;
     unsigned int* err;         // device error word of the context (host-mapped)
@@ -59,7 +60,14 @@ struct FusedArgs {
     int first_shard;           // local row 0 is the first row of the whole population (e_{-1} = 0)
     int normalise;             // f64 entry: divide by cumsum[n_src - 1] on the fly (`cumsum /= cumsum[-1]`, :90)
     uint64_t* total_out;       // receives the integer total (NULL to skip)
+    unsigned long long* trace; // GSE_FUSED_TRACE: 8 words per CTA (globaltimer at start / phase 1 / 2 / 3 done, SM id, ...), or NULL
 };
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 __device__ __forceinline__ double warp_sum_f64(double v) {
 #pragma unroll
@@ -147,18 +155,51 @@ __device__ __forceinline__ void rank_consts(RankConsts& k, double Td, const Fuse
 // (rounding of y) + 0.19 * 2^-17: when the 16-bit fraction is in [2, 65533] t* is further than that from an integer
 // and the rank is floor(t) + 1 (in [0, N]: t* >= -r > -1 and t* <= N - r).  Otherwise (exact ties -- dyadic weights,
 // r = 0 -- and 2^-14 of random sources) the comparison is evaluated exactly as the reference does.
-template <bool POW2, bool TIES_RIGHT, bool NORMALISED>
-__device__ __forceinline__ int rank_of(double C, const RankConsts& k) {
+// branch-free part: floor(t) + 1 and whether the fraction is too close to an integer to trust it
+template <bool NORMALISED>
+__device__ __forceinline__ int rank_fast(double C, const RankConsts& k, bool& near_integer) {
     const double g_fast = NORMALISED ? C : __dmul_rn(C, k.inv_T);
     const double y = __fma_rn(g_fast, k.n_total, k.magic_minus_r);
     const unsigned int lo = (unsigned int)__double2loint(y), hi = (unsigned int)__double2hiint(y);
-    int e = (int)__funnelshift_r(lo, hi, 16) + 1;                 // floor(t) + 1
-    if ((lo & 0xffffu) - 2u > 65531u) {                           // fraction in {0, 1, 65534, 65535}
-        const double g = NORMALISED ? C : __ddiv_rn(C, k.Td);
-        e = __double2int_rz(rank_exact_g<POW2, TIES_RIGHT>(k.r, k.n_total, k.inv_n, g, (double)e, 0.0, k.n_total));
-        e = min(max(e, 0), k.n_total_i);
-    }
+    near_integer = ((lo & 0xffffu) - 2u) > 65531u;                // fraction in {0, 1, 65534, 65535}
+    return (int)__funnelshift_r(lo, hi, 16) + 1;
+}
+template <bool POW2, bool TIES_RIGHT, bool NORMALISED>
+__device__ __forceinline__ int rank_slow(double C, int guess, const RankConsts& k) {
+    const double g = NORMALISED ? C : __ddiv_rn(C, k.Td);
+    const int e = __double2int_rz(rank_exact_g<POW2, TIES_RIGHT>(k.r, k.n_total, k.inv_n, g, (double)guess, 0.0, k.n_total));
+    return min(max(e, 0), k.n_total_i);
+}
+template <bool POW2, bool TIES_RIGHT, bool NORMALISED>
+__device__ __forceinline__ int rank_of(double C, const RankConsts& k) {
+    bool near_integer;
+    int e = rank_fast<NORMALISED>(C, k, near_integer);
+    if (near_integer) e = rank_slow<POW2, TIES_RIGHT, NORMALISED>(C, e, k);
     return e;
+}
+
+// ranks of the lane's RF_ITEMS cumulative values c[k] (NORMALISED) or C0 + q[0] + ... + q[k] (integer weights): the
+// eight fast paths are independent instruction streams the scheduler can interleave; the exact comparisons (rare) sit
+// behind ONE branch
+template <bool POW2, bool TIES_RIGHT, bool NORMALISED>
+__device__ __forceinline__ void ranks_of(double C0, const double (&q)[RF_ITEMS], const RankConsts& rc, int (&e)[RF_ITEMS]) {
+    unsigned int flags = 0;
+    double C = C0;
+#pragma unroll
+    for (int k = 0; k < RF_ITEMS; ++k) {
+        C = NORMALISED ? q[k] : C + q[k];
+        bool near_integer;
+        e[k] = rank_fast<NORMALISED>(C, rc, near_integer);
+        flags |= near_integer ? (1u << k) : 0u;
+    }
+    if (flags) {
+        C = C0;
+#pragma unroll
+        for (int k = 0; k < RF_ITEMS; ++k) {
+            C = NORMALISED ? q[k] : C + q[k];
+            if (flags & (1u << k)) e[k] = rank_slow<POW2, TIES_RIGHT, NORMALISED>(C, e[k], rc);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -336,6 +377,7 @@ k_resample_fused(const __grid_constant__ FusedArgs a) {
     if (tid == 0) s_vb = atomicAdd(a.counters, 1u);               // CTAs are numbered in the order they start
     __syncthreads();
     const int vb = (int)s_vb;
+    if (a.trace && tid == 0) { a.trace[8 * vb] = global_timer_ns(); unsigned int smid; asm("mov.u32 %0, %%smid;" : "=r"(smid)); a.trace[8 * vb + 4] = smid; }
     const float nm = HAS_LL ? weight_exp_offset((float)a.stats[0]) : 0.0f;       // -M log2(e), see weight_exp()
     const int sexp = quantisation_exponent(a.stats[1]);
     const float scale_f = __int_as_float((127 + sexp) << 23);     // 2^sexp, 0 <= sexp <= 52
@@ -369,32 +411,56 @@ k_resample_fused(const __grid_constant__ FusedArgs a) {
     sum = warp_sum_f64(sum);
     if (lane == 0) s_wsum[wid] = sum;
     __syncthreads();
+    if (a.trace && tid == 0) a.trace[8 * vb + 1] = global_timer_ns();
 
-    // ---- phase 2: publish the CTA aggregate; every thread collects a few of the other CTAs' -------------------
+    // ---- phase 2: publish the CTA aggregate; the LAST CTA to arrive scans all of them and hands every CTA its exclusive
+    //      prefix and the total.  One thread per CTA polls one word: polling by everyone for everything (nblocks^2 loads per
+    //      round) floods the L2 and slows the CTAs that are still streaming their rows.
+    uint64_t* const prefix = a.status + RF_MAX_BLOCKS;            // [i] exclusive prefix of CTA i, [nblocks] the total
     if (tid == 0) {
         double agg = 0.0;
 #pragma unroll
         for (int w = 0; w < RF_WARPS; ++w) agg += s_wsum[w];
         st_status(a.status + vb, status_pack(ST_AGGREGATE, 0u, (uint64_t)__double2ll_rn(agg)));
-    }
-    {
-        uint64_t excl = 0, tot = 0;
-        for (int i = tid; i < nblocks; i += RF_THREADS) {
-            uint64_t word = ld_status(a.status + i);
-            while ((word >> 62) == 0ull) { __nanosleep(32); word = ld_status(a.status + i); }
-            const uint64_t v = word & ((1ull << 54) - 1ull);
-            tot += v;
-            if (i < vb) excl += v;
-        }
-        excl = warp_sum_u64(excl);
-        tot = warp_sum_u64(tot);
-        if (lane == 0) { s_part[wid][0] = excl; s_part[wid][1] = tot; }
+        __threadfence();
+        s_vb = atomicAdd(a.counters + 4, 1u);                     // arrival ticket
     }
     __syncthreads();
-    uint64_t excl_u = 0, tot_u = 0;
+    if (s_vb == (unsigned int)nblocks - 1u) {                     // every aggregate is visible now
+        __threadfence();
+        // block-wide exclusive scan of nblocks values: thread t owns a contiguous chunk
+        const int chunk = (nblocks + RF_THREADS - 1) / RF_THREADS;
+        const int i0 = tid * chunk;
+        uint64_t part = 0;
+        for (int k = 0; k < chunk; ++k)
+            if (i0 + k < nblocks) part += ld_status(a.status + i0 + k) & ((1ull << 54) - 1ull);
+        const uint64_t incl_w = warp_inclusive_scan_u64(part, lane);
+        if (lane == 31) s_part[wid][0] = incl_w;
+        __syncthreads();
+        uint64_t base = 0;
 #pragma unroll
-    for (int w = 0; w < RF_WARPS; ++w) { excl_u += s_part[w][0]; tot_u += s_part[w][1]; }
+        for (int w = 0; w < RF_WARPS; ++w) base += (w < wid) ? s_part[w][0] : 0ull;
+        uint64_t run = base + incl_w - part;
+        for (int k = 0; k < chunk; ++k) {
+            if (i0 + k < nblocks) {
+                st_status(prefix + i0 + k, status_pack(ST_PREFIX, 0u, run));
+                run += ld_status(a.status + i0 + k) & ((1ull << 54) - 1ull);
+            }
+        }
+        if (tid == RF_THREADS - 1) st_status(prefix + nblocks, status_pack(ST_PREFIX, 0u, run));
+    }
+    if (tid == 0) {
+        uint64_t w0_ = ld_status(prefix + vb);
+        while ((w0_ >> 62) == 0ull) { __nanosleep(200); w0_ = ld_status(prefix + vb); }
+        uint64_t w1_ = ld_status(prefix + nblocks);
+        while ((w1_ >> 62) == 0ull) { __nanosleep(100); w1_ = ld_status(prefix + nblocks); }
+        s_part[0][0] = w0_ & ((1ull << 54) - 1ull);
+        s_part[0][1] = w1_ & ((1ull << 54) - 1ull);
+    }
+    __syncthreads();
+    const uint64_t excl_u = s_part[0][0], tot_u = s_part[0][1];
     if (tid == 0 && vb == 0 && a.total_out) *a.total_out = tot_u;
+    if (a.trace && tid == 0) a.trace[8 * vb + 2] = global_timer_ns();
 
     // ---- phase 3: scan + rank + fill, warp-autonomous ---------------------------------------------------------
     RankConsts rc;
@@ -428,11 +494,7 @@ k_resample_fused(const __grid_constant__ FusedArgs a) {
             carry += __shfl_sync(0xffffffffu, incl, 31);
             int e[RF_ITEMS];
             if (!degenerate) {
-#pragma unroll
-                for (int k = 0; k < RF_ITEMS; ++k) {
-                    C += q[k];
-                    e[k] = rank_of<POW2, false, false>(C, rc);
-                }
+                ranks_of<POW2, false, false>(C, q, rc, e);
             } else {
 #pragma unroll
                 for (int k = 0; k < RF_ITEMS; ++k)          // only the last row of the whole population has offspring
@@ -451,6 +513,7 @@ k_resample_fused(const __grid_constant__ FusedArgs a) {
 
     // ---- tail: wait for every CTA, drain the heavy-run queue, reset the launch state --------------------------
     __syncthreads();
+    if (a.trace && tid == 0) a.trace[8 * vb + 3] = global_timer_ns();
     if (tid == 0) {
         __threadfence();
         atomicAdd(a.counters + 1, 1u);
@@ -463,8 +526,9 @@ k_resample_fused(const __grid_constant__ FusedArgs a) {
     if (tid == 0) s_vb = atomicAdd(a.counters + 3, 1u);
     __syncthreads();
     if (s_vb == (unsigned int)nblocks - 1u) {                     // last CTA out: leave everything zero for the next launch
-        for (int i = tid; i < nblocks; i += RF_THREADS) a.status[i] = 0ull;
-        if (tid < 4) a.counters[tid] = 0u;
+        for (int i = tid; i < nblocks; i += RF_THREADS) { a.status[i] = 0ull; a.status[RF_MAX_BLOCKS + i] = 0ull; }
+        if (tid == 0) a.status[RF_MAX_BLOCKS + nblocks] = 0ull;
+        if (tid < 5) a.counters[tid] = 0u;
     }
 }
 
@@ -507,8 +571,7 @@ k_resample_search_f64(const __grid_constant__ FusedArgs a, int64_t tiles_per_war
             for (int k = 0; k < RF_ITEMS; ++k) c[k] = __ddiv_rn(c[k], rc.Td);        // cumsum /= cumsum[-1]  (:90)
         }
         int e[RF_ITEMS];
-#pragma unroll
-        for (int k = 0; k < RF_ITEMS; ++k) e[k] = rank_of<POW2, TIES_RIGHT, true>(c[k], rc);
+        ranks_of<POW2, TIES_RIGHT, true>(0.0, c, rc, e);
         if (row0 + RF_ITEMS >= a.n_src) {
             // the last row takes whatever is left (TIES_RIGHT with u = 1.0: the reference kernel would index one past
             // the end, particle.py:259-263; a cumsum that does not end at 1.0)
@@ -569,7 +632,7 @@ static int launch_fused(gse_ctx* ctx, FusedArgs& a, int variant, cudaStream_t s)
     int64_t blocks = groups < ctx->fused_resident[variant] ? groups : ctx->fused_resident[variant];
     a.rows_per_block = gse_div_up(groups, blocks) * group;
     blocks = gse_div_up(a.n_src, a.rows_per_block);
-    GSE_REQUIRE(blocks <= ctx->max_tiles, "workspace too small");
+    GSE_REQUIRE(blocks <= ctx->max_tiles && blocks < RF_MAX_BLOCKS, "workspace too small");
     k_resample_fused<LL, BASE, POW2, MINB><<<(unsigned)blocks, RF_THREADS, 0, s>>>(a);
     GSE_CHECK_LAUNCH(ctx);
     return GSE_OK;
@@ -597,6 +660,7 @@ extern "C" int gse_resample_fused(gse_ctx* ctx, const float* loglik_dev, const d
     a.n_src = n_src;
     a.first_shard = (src_row0 == 0) ? 1 : 0;
     a.total_out = total_dev;
+    a.trace = ctx->fused_trace;
     fill_common(ctx, a, r, n_total, out0, n_out, idx_out_dev, src_row0);
     cudaStream_t s = (cudaStream_t)stream;
     const bool pow2 = (n_total & (n_total - 1)) == 0;

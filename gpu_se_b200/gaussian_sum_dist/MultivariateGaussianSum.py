@@ -4,7 +4,8 @@ Mirrors gaussian_sum_dist/MultivariateGaussianSum.py:7-97 of the reference: same
 (``means, covariances, weights, library``), same ``means / covariances / weights`` float32
 attributes, ``pdf(x)`` and ``draw(shape)``.  ``library`` is accepted and ignored -- there is one
 backend.  ``pdf`` runs gse_mixture_pdf (float64), ``draw`` runs the Philox sampler
-gse_mixture_draw; rows of a draw are NOT grouped by component.
+gse_mixture_draw for any dimension up to 5 (state noise, measurement noise, x0); rows of a draw are NOT
+grouped by component.
 """
 import numpy
 import torch
@@ -71,35 +72,15 @@ class MultivariateGaussianSum:
 
     # -- draw ----------------------------------------------------------------------------
     def draw(self, shape=(1,)):
-        """(*shape, Nx) float32 samples on the device (:65-97)."""
-        if self._Nx != _lib.GSE_NX:
-            return self._draw_host(shape)
+        """(*shape, Nx) float32 samples on the device (:65-97), any Nx <= 5."""
         if not isinstance(shape, tuple):
             shape = (shape,)
         size = int(numpy.prod(shape))
         ctx = self._context()
         ld = _device.round_up(max(size, 1), 4)
-        buf = torch.empty((_lib.GSE_NX, ld), dtype=torch.float32, device=ctx.device)
+        buf = torch.empty((self._Nx, ld), dtype=torch.float32, device=ctx.device)
         mix = self.as_gse_mixture()
         _lib.check(_lib.lib.gse_mixture_draw(ctx.handle, mix, buf.data_ptr(), ld, size, self._seed, self._draws, 0,
                                              _device.stream_ptr(ctx.device)))
         self._draws += 1
         return _device.wrap(buf[:, :size].t().reshape(shape + (self._Nx,)))
-
-    def _draw_host(self, shape):
-        """Measurement-noise sized mixtures (Nx != 5) are only ever drawn a sample at a time by the
-        plant simulation (sim_base.py:284); they are drawn on the host and moved over."""
-        if not isinstance(shape, tuple):
-            shape = (shape,)
-        size = int(numpy.prod(shape))
-        rng = numpy.random.default_rng((self._seed, self._draws))
-        self._draws += 1
-        comp = rng.choice(self._Nd, size=size, p=numpy.asarray(self.weights, dtype=numpy.float64) / float(numpy.sum(self.weights, dtype=numpy.float64)))
-        out = numpy.empty((size, self._Nx), dtype=numpy.float32)
-        for d in range(self._Nd):
-            sel = comp == d
-            k = int(sel.sum())
-            if k:
-                out[sel] = rng.multivariate_normal(self.means[d], self._covariances64[d], k)
-        dev = _device.resolve_device(self._device)
-        return _device.wrap(torch.as_tensor(out.reshape(shape + (self._Nx,)), device=dev))

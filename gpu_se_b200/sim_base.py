@@ -109,11 +109,9 @@ class Simulation:
         self.performance = None
 
     def _host_draw(self, pdf):
-        """One sample of a mixture on the host (the plant is a single state vector; sim_base.py:281-284
-        does the same through cupy and a D2H copy)."""
-        w = numpy.asarray(pdf.weights, dtype=numpy.float64)
-        d = self._rng.choice(len(w), p=w / w.sum())
-        return self._rng.multivariate_normal(numpy.asarray(pdf.means[d], dtype=numpy.float64), pdf._covariances64[d])
+        """One sample of a mixture for the host-side plant: drawn by the device sampler and copied over, exactly as
+        the reference does it (``state_pdf.draw().get()``, sim_base.py:281-284)."""
+        return numpy.asarray(pdf.draw().get()[0], dtype=numpy.float64)
 
     def simulate(self):
         """The loop of sim_base.Simulation.simulate (:243-309)."""
@@ -164,13 +162,33 @@ class Simulation:
         return float(numpy.median(per_period) / (self.dt_control * 60.0))
 
 
+def _simpson_avg(y, x):
+    """scipy.integrate.simps(y, x) as the reference's SciPy evaluated it (``even='avg'``): composite Simpson for an
+    odd number of samples; for an even number the average of (Simpson on the first N-1 samples + trapezoid on the
+    last interval) and (trapezoid on the first interval + Simpson on the last N-1 samples)."""
+    y, x = numpy.asarray(y, dtype=numpy.float64), numpy.asarray(x, dtype=numpy.float64)
+    n = len(x)
+    if n < 2:
+        return 0.0
+    if n == 2:
+        return 0.5 * (x[1] - x[0]) * (y[0] + y[1])
+
+    def odd(yy, xx):                                   # composite Simpson, non-uniform spacing allowed
+        h0, h1 = numpy.diff(xx)[0::2], numpy.diff(xx)[1::2]
+        hs, hp, hd = h0 + h1, h0 * h1, h0 / h1
+        return float(numpy.sum(hs / 6.0 * (yy[0:-2:2] * (2.0 - 1.0 / hd) + yy[1:-1:2] * (hs * hs / hp)
+                                           + yy[2::2] * (2.0 - hd))))
+
+    if n % 2 == 1:
+        return odd(y, x)
+    first = odd(y[:-1], x[:-1]) + 0.5 * (x[-1] - x[-2]) * (y[-1] + y[-2])
+    last = odd(y[1:], x[1:]) + 0.5 * (x[1] - x[0]) * (y[0] + y[1])
+    return 0.5 * (first + last)
+
+
 def performance(ys, r, ts):
-    """Integral squared error between two output trajectories (sim_base.py:164-185; Simpson's rule
-    -- scipy.integrate.simps no longer exists, so the composite rule is written out)."""
-    se = numpy.sum((numpy.asarray(r) - numpy.asarray(ys)) ** 2, axis=1)
-    n = len(ts) - (1 - len(ts) % 2)                    # Simpson needs an odd number of samples
-    h = ts[1] - ts[0]
-    ise = h / 3 * (se[0] + se[n - 1] + 4 * se[1:n - 1:2].sum() + 2 * se[2:n - 2:2].sum())
-    if n < len(ts):
-        ise += 0.5 * h * (se[-1] + se[-2])
-    return float(ise)
+    """The reference's closed-loop performance measure (sim_base.py:164-185): per output axis the TIME-WEIGHTED
+    squared error ``(ys - r)**2 * ts`` integrated over ``ts`` with Simpson's rule, summed over the axes."""
+    se = (numpy.asarray(ys, dtype=numpy.float64) - numpy.asarray(r, dtype=numpy.float64)) ** 2
+    ts = numpy.asarray(ts, dtype=numpy.float64)
+    return float(sum(_simpson_avg(se_ax * ts, ts) for se_ax in numpy.rollaxis(se, 1)))

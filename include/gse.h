@@ -131,7 +131,7 @@ int gse_ctx_use_step_params(gse_ctx* ctx, int enable);
 
 /* ---- sampling / density of a Gaussian sum (MultivariateGaussianSum.py:39-97) ---------------- */
 
-/* x[c*ld + i] = sample i of `mix` (nx = 5), i in [0, n): Philox4x32-10 stream keyed by
+/* x[c*ld + i] = component c of sample i of `mix` (nx <= 5 columns), i in [0, n): Philox4x32-10 stream keyed by
  * (seed; counter = (index0 + i, step, subsequence)).  Replaces x0.draw(N) in
  * ParticleFilter.__init__ (particle.py:49) and MultivariateGaussianSum.draw (:65-97); rows are
  * NOT grouped by component (quirk Q5 of SURVEY.md is not reproduced). */
@@ -345,6 +345,11 @@ int gse_gsf_sigma_points(gse_ctx* ctx, const float* mean_dev, const float* cov_d
 int gse_gsf_moments(gse_ctx* ctx, const float* mean_dev, const float* cov_dev, int64_t ld,
                     int64_t n, const int32_t* idx_dev, const float* loglik_dev, const double* base_dev,
                     const double* stats_dev, double* out_dev, void* stream);
+
+/* Debugging aid: with GSE_FUSED_TRACE set in the environment when the context is created, gse_resample_fused records
+ * four %globaltimer stamps per CTA (start, after its sum, after the grid-wide aggregate exchange, after its fill).
+ * Copies up to max_words uint64 words to host_out (synchronises); returns the number copied, 0 when tracing is off. */
+int64_t gse_ctx_read_trace(gse_ctx* ctx, uint64_t* host_out, int64_t max_words);
 
 /* ---- introspection ------------------------------------------------------------------------------ */
 
