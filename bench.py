@@ -41,7 +41,7 @@ U_NOMINAL = numpy.array([0.06, 0.2])
 #   the sharded path): scan 4 R + 8 W, search 8 R + 4 W
 STAGE_BYTES = {"predict": 44, "update": 12, "resample": 8, "scan": 12, "search": 12}
 # sharded run: the same, plus the all-gather of the shard totals ("offsets", no HBM traffic to speak of)
-STAGE_BYTES_SHARDED = {"predict": 44, "update": 12, "scan": 12, "offsets": 0, "search": 12}
+STAGE_BYTES_SHARDED = {"predict": 44, "update": 12, "resample": 8}
 
 
 def workload_name(log2n):
@@ -361,8 +361,10 @@ def run_ours(args):
                                      [0.85, 0.15])
     x0 = g.MultivariateGaussianSum(state_means + numpy.array(X_STEADY)[None, :], state_covs, [0.75, 0.25])
     f, gg = g.Bioreactor.homeostatic_DEs, g.Bioreactor.static_outputs
+    parity = None
     if world > 1 or args.sharded:
         from gpu_se_b200.sharded import ShardedParticleFilter
+        parity = sharded_parity(g, dev, world, rank)
         pf = ShardedParticleFilter(f, gg, n_total, x0, state, meas, device=dev, seed=1234)
     elif args.workload == "gsf":
         pf = g.GaussianSumUnscentedKalmanFilter(f, gg, n_total, x0, state, meas, device=dev, seed=1234)
@@ -371,7 +373,7 @@ def run_ours(args):
     if args.graphs:
         pf.enable_graphs()
     from gpu_se_b200.filter import _base
-    two_stage = (world > 1 or args.sharded) or not _base.FUSED_RESAMPLE
+    two_stage = not _base.FUSED_RESAMPLE and not (world > 1 or args.sharded)
 
     K, W = args.steps, max(args.warmup, 3)
     us, zs = trajectory(2 * (K + W), seed=7)
@@ -503,6 +505,7 @@ def run_ours(args):
                 "note": "u, z are host arrays passed per call; particles stay resident (as in the reference's GPU "
                         "class); point_estimate() read back every step"},
         "gpu_launches": int(lsum[0]),
+        "sharded_parity": parity,
         "clocks": clocks,
         "last_estimate": [float(v) for v in est],
     }
@@ -511,6 +514,62 @@ def run_ours(args):
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def sharded_parity(g, dev, world, rank, n=(1 << 20) + 8):
+    """World >= 2 parity cannot run in the driver's 1-GPU test tier: before timing, every `bench.py --gpus N` run checks
+    that N shards of one population reproduce the single-GPU filter of the same seed BIT FOR BIT (particles after
+    predict / update / resample cycles, resample -> resample, assigned weights) and that the global estimates agree."""
+    import torch
+    import torch.distributed as dist
+    from gpu_se_b200.model.BioreactorModel import X_STEADY
+    from gpu_se_b200.sharded import ShardedParticleFilter
+    sm, sc = numpy.zeros((2, 5)), numpy.array([numpy.diag([1e-4, 1e-7, 1e-3, 1e-3, 1e-7]),
+                                               numpy.diag([1e-3, 1e-6, 1e-2, 1e-2, 1e-6])])
+    state = g.MultivariateGaussianSum(sm, sc, [0.75, 0.25])
+    meas = g.MultivariateGaussianSum([[1e-1, 0], [0, -1e-1]], [[[6e-2, 0], [0, 8e-2]], [[500, 100], [100, 700]]], [0.85, 0.15])
+    x0 = g.MultivariateGaussianSum(sm + numpy.array(X_STEADY)[None, :], sc, [0.75, 0.25])
+    f, gg = g.Bioreactor.homeostatic_DEs, g.Bioreactor.static_outputs
+    us, zs = trajectory(4, seed=11)
+    wts = numpy.random.default_rng(5).random(n) ** 6
+
+    def cycles(pf, assign):
+        ests = []
+        for k in range(3):
+            pf.predict(us[k], DT)
+            pf.update(us[k], zs[k])
+            pf.resample(r=0.1 + 0.3 * k)
+            ests.append(pf.point_estimate())
+        pf.resample(r=0.77)                         # resample -> resample, no update in between
+        assign(pf, wts)
+        pf.resample(r=0.41)
+        ests.append(pf.point_estimate())
+        pf.predict(us[3], DT)
+        return ests
+
+    spf = ShardedParticleFilter(f, gg, n, x0, state, meas, device=dev, seed=4321)
+    got = cycles(spf, lambda p, w: p.set_global_weights(w))
+    parts = [torch.empty((b - a, 5), dtype=torch.float32, device=dev) for a, b in spf.bounds]
+    for s in range(world):
+        if s == rank:
+            parts[s].copy_(spf.particles)
+        dist.broadcast(parts[s], src=s)
+    ok = torch.ones(1, dtype=torch.int32, device=dev)
+    if rank == 0:
+        pf = g.ParticleFilter(f, gg, n, x0, state, meas, device=dev, seed=4321)
+
+        def assign(p, w):
+            p.weights = w
+        ref = cycles(pf, assign)
+        same = bool(torch.equal(torch.cat(parts), pf.particles.as_subclass(torch.Tensor)))
+        same = same and all(numpy.allclose(a, b, rtol=1e-9, atol=1e-12) for a, b in zip(got, ref))
+        ok[0] = 1 if same else 0
+        del pf
+    dist.broadcast(ok, src=0)
+    spf.close()
+    del spf
+    torch.cuda.empty_cache()
+    return bool(int(ok[0]))
 
 
 def emit(line):

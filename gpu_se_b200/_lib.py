@@ -31,13 +31,14 @@ class gse_mixture(ctypes.Structure):
 
 GSE_ERR_CHOLESKY, GSE_ERR_SINGULAR_PYY, GSE_ERR_PEER_TIMEOUT, GSE_ERR_QUEUE_OVERFLOW, GSE_ERR_ZERO_WEIGHTS = 1, 2, 4, 8, 16
 GSE_MAX_SHARDS, GSE_IPC_HANDLE_BYTES = 8, 64
-GSE_MAILBOX_BYTES = 2 * GSE_MAX_SHARDS * 64
+GSE_MAILBOX_BYTES = 2 * GSE_MAX_SHARDS * 512
 
 
 class gse_shards(ctypes.Structure):
     _fields_ = [("nshards", ctypes.c_int32), ("rows", ctypes.c_int64 * (GSE_MAX_SHARDS + 1)),
                 ("cumsum_dev", ctypes.c_void_p * GSE_MAX_SHARDS), ("state_dev", ctypes.c_void_p * GSE_MAX_SHARDS),
-                ("ld", ctypes.c_int64 * GSE_MAX_SHARDS), ("offsets_dev", ctypes.c_void_p)]
+                ("ld", ctypes.c_int64 * GSE_MAX_SHARDS), ("offsets_dev", ctypes.c_void_p),
+                ("idx_dev", ctypes.c_void_p * GSE_MAX_SHARDS)]
 
 
 class gse_step_params(ctypes.Structure):
@@ -66,6 +67,8 @@ SIGNATURES = {
     "gse_scan_weights": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "gse_resample_search": (c_int, [c_vp, c_vp, c_i64, c_vp, c_dbl, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "gse_resample_fused": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_dbl, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "gse_resample_fused_sharded": (c_int, [c_vp, c_vp, c_vp, c_vp, c_dbl, c_shards_p, ctypes.POINTER(c_vp), c_int,
+                                           ctypes.c_uint, ctypes.c_uint, c_vp, c_vp]),
     "gse_resample_search_f64": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_dbl, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "gse_ctx_errors": (ctypes.c_uint, [c_vp, c_int]),
     "gse_gather_rows": (c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_vp]),
@@ -80,6 +83,7 @@ SIGNATURES = {
     "gse_pf_moments_sharded": (c_int, [c_vp, c_shards_p, c_vp, c_i64, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]),
     "gse_peer_allgather_stats": (c_int, [c_vp, ctypes.POINTER(c_vp), c_int, c_int, ctypes.c_uint, c_vp, c_vp]),
     "gse_peer_allgather_totals": (c_int, [c_vp, ctypes.POINTER(c_vp), c_int, c_int, ctypes.c_uint, c_vp, c_vp, c_vp]),
+    "gse_peer_allgather_moments": (c_int, [c_vp, ctypes.POINTER(c_vp), c_int, c_int, ctypes.c_uint, c_vp, c_vp]),
     "gse_ctx_upload_step_params": (c_int, [c_vp, ctypes.POINTER(gse_step_params), c_vp]),
     "gse_ctx_use_step_params": (c_int, [c_vp, c_int]),
     "gse_merge_stats": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp]),
@@ -87,6 +91,9 @@ SIGNATURES = {
     "gse_threshold_u64": (c_u64, [c_dbl, c_u64]),
     "gse_gsf_predict": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_dbl_p, c_dbl, c_u64, c_u64,
                                 c_i64, c_vp, c_i64, c_vp]),
+    "gse_gsf_predict_sharded": (c_int, [c_vp, c_shards_p, c_vp, c_vp, c_vp, c_i64, c_i64, c_dbl_p, c_dbl, c_u64, c_u64,
+                                        c_i64, c_vp, c_i64, c_vp]),
+    "gse_gsf_moments_sharded": (c_int, [c_vp, c_shards_p, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "gse_gsf_update": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_dbl_p, c_dbl_p, c_vp, c_vp]),
     "gse_gsf_sigma_points": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp]),
     "gse_gsf_moments": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libgse_b200.so")
 SOURCES = ["gse_api.cu", "gse_pf.cu", "gse_resample.cu", "gse_resample_fused.cu", "gse_gsf.cu"]
-HEADERS = ["gse_common.cuh", "gse_resample_common.cuh", os.path.join("..", "..", "include", "gse.h")]
+HEADERS = ["gse_common.cuh", "gse_resample_common.cuh", "gse_mailbox.cuh", os.path.join("..", "..", "include", "gse.h")]
 FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "-shared"]
 

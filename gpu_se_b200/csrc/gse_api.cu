@@ -260,11 +260,11 @@ extern "C" int gse_ctx_create(int device, int model_id, int64_t n_max, const gse
     c->heavy_queue = (int4*)(base + o_queue);
     {
         const char* v = getenv("GSE_PREDICT_MINB");               // tuning knob: CTAs per SM of the predict kernel
-        c->predict_minb = (v && (atoi(v) == 4 || atoi(v) == 6)) ? atoi(v) : 5;
+        c->predict_minb = (v && atoi(v) == 5) ? 5 : 4;
     }
     {
-        const char* v = getenv("GSE_FUSED_MINB");                 // tuning knob: 3 = 85 registers, 24 warps per SM
-        c->fused_minb = (v && atoi(v) == 3) ? 3 : 4;
+        const char* v = getenv("GSE_FUSED_MINB");                 // 3 CTAs per SM (80 registers, no spills) measured 70 us against 72 us at 4 (64 registers); GSE_FUSED_MINB=4 to compare
+        c->fused_minb = (v && atoi(v) == 4) ? 4 : 3;
     }
     if (getenv("GSE_FUSED_TRACE")) {
         if (cudaMalloc((void**)&c->fused_trace, sizeof(unsigned long long) * 8 * 4096) != cudaSuccess) c->fused_trace = NULL;

@@ -108,10 +108,10 @@ struct gse_ctx {
     uint64_t* fused_status;   // fused resample: one aggregate word per CTA, zero between launches
     int4* heavy_queue;        // fused resample: runs of one heavy source handed to the whole grid (start, end, ancestor)
     int heavy_queue_cap;
-    int fused_resident[12];   // co-resident CTAs of each k_resample_fused instantiation (0: not queried yet)
-    int predict_minb;         // CTAs per SM of the benchmark's predict specialisation (5; GSE_PREDICT_MINB = 4 / 6 for tuning)
+    int fused_resident[16];   // co-resident CTAs of each k_resample_fused instantiation (0: not queried yet)
+    int predict_minb;         // CTAs per SM of the benchmark's predict specialisation (4; GSE_PREDICT_MINB=5: the 48-register build)
     unsigned long long* fused_trace;   // GSE_FUSED_TRACE=1: per-CTA phase time stamps of the last fused resample (debugging)
-    int fused_minb;           // CTAs per SM the fused kernel is compiled for (4; GSE_FUSED_MINB=3 for tuning)
+    int fused_minb;           // CTAs per SM the fused kernel is compiled for (3; GSE_FUSED_MINB=4 to compare)
     unsigned int* err_host;   // device-error word: pinned, mapped host memory the kernels OR their GSE_ERR_* bits into
     unsigned int* err_dev;    // its device alias
     int64_t* part;            // merge-path split points
@@ -313,9 +313,14 @@ __device__ __forceinline__ void draw_mixture5(const MixSampler5& sp, uint64_t in
 //   (n[2 p], n[2 p + 1]) = BM(w[2 p], w[2 p + 1]),  p = 0..9;  row r of the group takes n[5 r .. 5 r + 4] and
 //   selector w[20 + r]
 // Still a pure function of the GLOBAL row index (restated in oracle/philox.py: grouped_normals5).
+// the four component selectors of a group (Philox call 5 of the grouped layout)
+__device__ __forceinline__ Philox4 draw_selectors_x4(uint64_t group, uint32_t step, uint32_t k0, uint32_t k1) {
+    return philox4x32_10((uint32_t)group, (uint32_t)(group >> 32), step, 0x80000005u, k0, k1);
+}
+
 template <bool DIAG, int ND>
 __device__ __forceinline__ void draw_mixture5_x4(const MixSampler5& sp, uint64_t group, uint32_t step, uint32_t k0,
-                                                 uint32_t k1, float out[4][5]) {
+                                                 uint32_t k1, const Philox4& S, float out[4][5]) {
     // every Philox call is turned into its four normals at once (its words die there): 20 normals + 4 selectors live
     float z[20];
 #pragma unroll
@@ -324,7 +329,6 @@ __device__ __forceinline__ void draw_mixture5_x4(const MixSampler5& sp, uint64_t
         box_muller(P.x, P.y, z[4 * j], z[4 * j + 1]);
         box_muller(P.z, P.w, z[4 * j + 2], z[4 * j + 3]);
     }
-    const Philox4 S = philox4x32_10((uint32_t)group, (uint32_t)(group >> 32), step, 0x80000005u, k0, k1);
     const uint32_t sel[4] = {S.x, S.y, S.z, S.w};
     const int dg[5] = {0, 2, 5, 9, 14};
 #pragma unroll
@@ -356,6 +360,12 @@ __device__ __forceinline__ void draw_mixture5_x4(const MixSampler5& sp, uint64_t
             }
         }
     }
+}
+
+template <bool DIAG, int ND>
+__device__ __forceinline__ void draw_mixture5_x4(const MixSampler5& sp, uint64_t group, uint32_t step, uint32_t k0,
+                                                 uint32_t k1, float out[4][5]) {
+    draw_mixture5_x4<DIAG, ND>(sp, group, step, k0, k1, draw_selectors_x4(group, step, k0, k1), out);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -613,6 +623,16 @@ __device__ __forceinline__ unsigned int ld_status32(const unsigned int* p) {
     unsigned int v;
     asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+
+// The shard table arrives as a kernel parameter; indexing a parameter array with a run-time index makes the compiler
+// copy the whole struct to local memory.  Kernels that look shards up copy the table to shared memory once per CTA
+// (call before any early return) and index that.
+__device__ __forceinline__ void stage_shards(GatherShards* s_dst, const GatherShards& src) {
+    const unsigned int* w = reinterpret_cast<const unsigned int*>(&src);
+    unsigned int* d = reinterpret_cast<unsigned int*>(s_dst);
+    for (unsigned int i = threadIdx.x; i < sizeof(GatherShards) / 4; i += blockDim.x) d[i] = w[i];
+    __syncthreads();
 }
 
 __device__ __forceinline__ int shard_of(const GatherShards& g, int64_t k) {

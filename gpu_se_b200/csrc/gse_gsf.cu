@@ -124,23 +124,37 @@ extern "C" int gse_gsf_sigma_points(gse_ctx* ctx, const float* mean_dev, const f
 // ------------------------------------------------------------------------------------------------
 // G1: predict (gs_ukf.py:82-103)
 // ------------------------------------------------------------------------------------------------
-template <bool DIAG, bool HOST_NOISE>
+// SHARDED: idx holds GLOBAL ancestor rows of a multi-GPU population; the (20, ld) state of the owning shard is read
+// through peer memory (rows 0-4 the mean, 5-19 the covariance triangle)
+template <bool DIAG, bool HOST_NOISE, bool SHARDED>
 __global__ void __launch_bounds__(GSF_THREADS)
 k_gsf_predict(const float* mean_src, const float* cov_src, int64_t lds, const int32_t* __restrict__ idx,
-              float* mean, float* cov, int64_t ld, int64_t n, ModelInputs in_arg,
+              const __grid_constant__ GatherShards shards_arg, float* mean, float* cov, int64_t ld, int64_t n, ModelInputs in_arg,
               const __grid_constant__ MixSampler5 sp, uint32_t k0, uint32_t k1, uint32_t step, int64_t index0,
               const float* __restrict__ noise, int64_t ldn, const gse_step_params* __restrict__ params,
               unsigned int* err) {
+    __shared__ GatherShards s_shards;
+    if (SHARDED) stage_shards(&s_shards, shards_arg);
+    const GatherShards& shards = SHARDED ? s_shards : shards_arg;
     const int64_t i = (int64_t)blockIdx.x * GSF_THREADS + threadIdx.x;
     if (i >= n) return;
     const ModelInputs in = model_inputs(in_arg, params, 1);
     if (params) step = (uint32_t)params->step;
-    const int64_t is = idx ? (int64_t)idx[i] : i;          // pending resample: read through the ancestor index
     float m[5], P[15], L[15];
+    if (SHARDED) {
+        int64_t lsrc;
+        const float* src = shard_row(shards, idx[i], lsrc);
 #pragma unroll
-    for (int j = 0; j < 5; ++j) m[j] = mean_src[j * lds + is];
+        for (int j = 0; j < 5; ++j) m[j] = src[j * lsrc];
 #pragma unroll
-    for (int j = 0; j < 15; ++j) P[j] = cov_src[j * lds + is];
+        for (int j = 0; j < 15; ++j) P[j] = src[(5 + j) * lsrc];
+    } else {
+        const int64_t is = idx ? (int64_t)idx[i] : i;      // pending resample: read through the ancestor index
+#pragma unroll
+        for (int j = 0; j < 5; ++j) m[j] = mean_src[j * lds + is];
+#pragma unroll
+        for (int j = 0; j < 15; ++j) P[j] = cov_src[j * lds + is];
+    }
     cholesky5_retry(P, L, err);
 
     float sg[GSE_NSIGMA][5];
@@ -192,16 +206,13 @@ k_gsf_predict(const float* mean_src, const float* cov_src, int64_t lds, const in
     for (int j = 0; j < 15; ++j) cov[j * ld + i] = C[j];
 }
 
-extern "C" int gse_gsf_predict(gse_ctx* ctx, const float* mean_src_dev, const float* cov_src_dev, int64_t ld_src,
-                               const int32_t* idx_dev, float* mean_dev, float* cov_dev, int64_t ld, int64_t n,
-                               const double u[GSE_NU], double dt, uint64_t seed, uint64_t step, int64_t index0,
-                               const float* noise_dev, int64_t ld_noise, void* stream) {
-    GSE_REQUIRE(ctx != NULL && u != NULL && mean_dev != NULL && cov_dev != NULL && mean_src_dev != NULL &&
-                cov_src_dev != NULL, "NULL argument");
+static int launch_gsf_predict(gse_ctx* ctx, const float* mean_src_dev, const float* cov_src_dev, int64_t ld_src,
+                              const int32_t* idx_dev, const GatherShards* shards, float* mean_dev, float* cov_dev,
+                              int64_t ld, int64_t n, const double u[GSE_NU], double dt, uint64_t seed, uint64_t step,
+                              int64_t index0, const float* noise_dev, int64_t ld_noise, void* stream) {
+    GSE_REQUIRE(ctx != NULL && u != NULL && mean_dev != NULL && cov_dev != NULL, "NULL argument");
     gse_device_guard guard(ctx->device);
     GSE_REQUIRE(n >= 1 && n <= ctx->n_max && ld >= n, "n / ld out of range");
-    GSE_REQUIRE(idx_dev == NULL || mean_src_dev != mean_dev, "a gathering predict cannot run in place");
-    GSE_REQUIRE(idx_dev != NULL || ld_src >= n, "ld_src too small");
     GSE_REQUIRE(noise_dev == NULL || ld_noise >= n, "ld_noise too small");
     ModelInputs in;
     in.feed = (float)(u[0] * (5000.0 / 180.0));
@@ -210,14 +221,49 @@ extern "C" int gse_gsf_predict(gse_ctx* ctx, const float* mean_src_dev, const fl
     const unsigned blocks = (unsigned)gse_div_up(n, GSF_THREADS);
     cudaStream_t s = (cudaStream_t)stream;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-    if (noise_dev)
-        k_gsf_predict<true, true><<<blocks, GSF_THREADS, 0, s>>>(mean_src_dev, cov_src_dev, ld_src, idx_dev, mean_dev, cov_dev, ld, n, in, ctx->state_sampler, k0, k1, (uint32_t)step, index0, noise_dev, ld_noise, ctx->step_params, ctx->err_dev);
-    else if (ctx->state_sampler.diag)
-        k_gsf_predict<true, false><<<blocks, GSF_THREADS, 0, s>>>(mean_src_dev, cov_src_dev, ld_src, idx_dev, mean_dev, cov_dev, ld, n, in, ctx->state_sampler, k0, k1, (uint32_t)step, index0, NULL, 0, ctx->step_params, ctx->err_dev);
-    else
-        k_gsf_predict<false, false><<<blocks, GSF_THREADS, 0, s>>>(mean_src_dev, cov_src_dev, ld_src, idx_dev, mean_dev, cov_dev, ld, n, in, ctx->state_sampler, k0, k1, (uint32_t)step, index0, NULL, 0, ctx->step_params, ctx->err_dev);
+    GatherShards none;
+    memset(&none, 0, sizeof(none));
+    const GatherShards& sh = shards ? *shards : none;
+#define LAUNCH_G1(DIAG, HOST, SH)                                                                                   \
+    k_gsf_predict<DIAG, HOST, SH><<<blocks, GSF_THREADS, 0, s>>>(mean_src_dev, cov_src_dev, ld_src, idx_dev, sh, mean_dev, \
+                                                                 cov_dev, ld, n, in, ctx->state_sampler, k0, k1,     \
+                                                                 (uint32_t)step, index0, noise_dev, ld_noise,       \
+                                                                 ctx->step_params, ctx->err_dev)
+    if (shards) {
+        if (noise_dev) LAUNCH_G1(true, true, true);
+        else if (ctx->state_sampler.diag) LAUNCH_G1(true, false, true);
+        else LAUNCH_G1(false, false, true);
+    } else {
+        if (noise_dev) LAUNCH_G1(true, true, false);
+        else if (ctx->state_sampler.diag) LAUNCH_G1(true, false, false);
+        else LAUNCH_G1(false, false, false);
+    }
+#undef LAUNCH_G1
     GSE_CHECK_LAUNCH(ctx);
     return GSE_OK;
+}
+
+extern "C" int gse_gsf_predict(gse_ctx* ctx, const float* mean_src_dev, const float* cov_src_dev, int64_t ld_src,
+                               const int32_t* idx_dev, float* mean_dev, float* cov_dev, int64_t ld, int64_t n,
+                               const double u[GSE_NU], double dt, uint64_t seed, uint64_t step, int64_t index0,
+                               const float* noise_dev, int64_t ld_noise, void* stream) {
+    GSE_REQUIRE(mean_src_dev != NULL && cov_src_dev != NULL, "NULL argument");
+    GSE_REQUIRE(idx_dev == NULL || mean_src_dev != mean_dev, "a gathering predict cannot run in place");
+    GSE_REQUIRE(idx_dev != NULL || ld_src >= n, "ld_src too small");
+    return launch_gsf_predict(ctx, mean_src_dev, cov_src_dev, ld_src, idx_dev, NULL, mean_dev, cov_dev, ld, n, u, dt, seed,
+                              step, index0, noise_dev, ld_noise, stream);
+}
+
+extern "C" int gse_gsf_predict_sharded(gse_ctx* ctx, const gse_shards* shards, const int32_t* idx_dev, float* mean_dev,
+                                       float* cov_dev, int64_t ld, int64_t n, const double u[GSE_NU], double dt,
+                                       uint64_t seed, uint64_t step, int64_t index0, const float* noise_dev,
+                                       int64_t ld_noise, void* stream) {
+    GSE_REQUIRE(idx_dev != NULL, "idx is NULL");
+    GatherShards g;
+    int rc = gse_build_gather_shards(shards, mean_dev, &g);
+    if (rc) return rc;
+    return launch_gsf_predict(ctx, NULL, NULL, 0, idx_dev, &g, mean_dev, cov_dev, ld, n, u, dt, seed, step, index0,
+                              noise_dev, ld_noise, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -2,6 +2,7 @@
 // and the stand-alone mixture pdf / weight read-back helpers.  One thread owns 4 consecutive rows
 // so that every SoA column moves as 128-bit coalesced vectors.
 #include "gse_common.cuh"
+#include "gse_mailbox.cuh"
 
 #define PF_THREADS 256
 #ifndef PREDICT_MINB
@@ -69,11 +70,14 @@ extern "C" int gse_mixture_draw(gse_ctx* ctx, const gse_mixture* mix, float* x_d
 // always the case except for a shard that starts off a multiple of four
 template <bool DIAG, bool HOST_NOISE, bool ONE_STEP, int ND, int GMODE, bool ALIGNED, int MINB>
 __global__ void __launch_bounds__(PF_THREADS, MINB)
-k_pf_predict(const float* xs, int64_t lds, const int32_t* __restrict__ idx, const __grid_constant__ GatherShards shards,
+k_pf_predict(const float* xs, int64_t lds, const int32_t* __restrict__ idx, const __grid_constant__ GatherShards shards_arg,
              float* xd, int64_t ldd, int64_t n,
              ModelInputs in_arg, int n_sub, const __grid_constant__ MixSampler5 sp, uint32_t k0, uint32_t k1,
              uint32_t step, int64_t index0, const float* __restrict__ noise, int64_t ldn,
              const gse_step_params* __restrict__ params) {
+    __shared__ GatherShards s_shards;
+    if (GMODE == 2) stage_shards(&s_shards, shards_arg);
+    const GatherShards& shards = GMODE == 2 ? s_shards : shards_arg;
     const int64_t g = (int64_t)blockIdx.x * PF_THREADS + threadIdx.x;
     const int64_t row0 = g * ROWS_PER_THREAD;
     if (row0 >= n) return;
@@ -204,12 +208,14 @@ static int launch_predict(gse_ctx* ctx, const float* x_src_dev, int64_t ld_src, 
     k_pf_predict<DIAG, HOST, ONE, ND, GMODE, AL, MB><<<blocks, PF_THREADS, 0, s>>>(                              \
         x_src_dev, ld_src, idx_dev, *shards, x_dst_dev, ld_dst, n, in, n_sub, ctx->state_sampler, k0, k1,        \
         (uint32_t)step, index0, noise_dev, ld_noise, ctx->step_params)
-// (the benchmark's specialisation -- diagonal two-component noise, one Euler step, aligned rows -- is also compiled for
-//  4 and 6 CTAs per SM: GSE_PREDICT_MINB, a tuning knob)
+// The benchmark's specialisation (diagonal two-component noise, one Euler step, aligned rows) runs at 4 CTAs per SM
+// (64 registers): measured at 2^24 rows 132 us against 139 us at 5 CTAs (48 registers) and 143 us at 6 (40, spills);
+// GSE_PREDICT_MINB=5 selects the 48-register build for comparison.  (Tying the gather addresses to the first Philox call
+// so that the scheduler runs it under the ancestor-index load changed nothing: 132.1 us.)
 #define LAUNCH_PREDICT_GA(DIAG, HOST, ONE, ND, GMODE, AL)                                                        \
     do {                                                                                                         \
-        if ((ND) == 2 && (AL) && ctx->predict_minb == 4) LAUNCH_PREDICT_GAM(DIAG, HOST, ONE, ND, GMODE, AL, ((ND) == 2 && (AL)) ? 4 : PREDICT_MINB); \
-        else if ((ND) == 2 && (AL) && ctx->predict_minb == 6) LAUNCH_PREDICT_GAM(DIAG, HOST, ONE, ND, GMODE, AL, ((ND) == 2 && (AL)) ? 6 : PREDICT_MINB); \
+        constexpr bool tuned = (ND) == 2 && (AL);                                                                \
+        if (tuned && ctx->predict_minb == 4) LAUNCH_PREDICT_GAM(DIAG, HOST, ONE, ND, GMODE, AL, (tuned ? 4 : PREDICT_MINB)); \
         else LAUNCH_PREDICT_GAM(DIAG, HOST, ONE, ND, GMODE, AL, PREDICT_MINB);                                   \
     } while (0)
 #define LAUNCH_PREDICT_G(DIAG, HOST, ONE, ND, GMODE)                                                             \
@@ -389,44 +395,17 @@ extern "C" int gse_loglik_max(gse_ctx* ctx, const float* loglik_dev, int64_t n, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// All-gather of one small record per shard over peer-mapped mailboxes: the collective and the
-// reduction that consumes it are ONE single-warp kernel, no NCCL launch, no host involvement.
-// Lane t writes this rank's record and the epoch into slot [rank] of peer t's mailbox (stores over
-// NVLink, payload fenced before the flag), then spins on slot [t] of its own mailbox until peer t's
-// record of the same epoch has landed.  Slots are double-buffered by epoch parity: a peer can only
-// reuse a slot two exchanges later, which needs this rank's next flag, written after it has read.
+// All-gathers over the peer mailboxes (gse_mailbox.cuh) fused with the reduction that consumes them: ONE single-warp
+// kernel per exchange, no NCCL launch, no host involvement.
 // ------------------------------------------------------------------------------------------------
-#define MBOX_SLOT_BYTES 64
-struct MailboxTable {
-    unsigned char* box[GSE_MAX_SHARDS];
-};
-
-__device__ __forceinline__ void mbox_exchange(const MailboxTable& mb, int rank, int nshards, unsigned int epoch,
-                                              unsigned long long w0, unsigned long long w1, int lane,
-                                              unsigned long long& r0, unsigned long long& r1) {
-    r0 = 0; r1 = 0;
-    if (lane < nshards) {
-        const size_t par = (size_t)(epoch & 1u) * GSE_MAX_SHARDS;
-        volatile unsigned long long* dst = (volatile unsigned long long*)(mb.box[lane] + (par + rank) * MBOX_SLOT_BYTES);
-        dst[0] = w0;
-        dst[1] = w1;
-        __threadfence_system();
-        *(volatile unsigned int*)(dst + 4) = epoch;
-        volatile unsigned long long* src = (volatile unsigned long long*)(mb.box[rank] + (par + lane) * MBOX_SLOT_BYTES);
-        while (*(volatile unsigned int*)(src + 4) != epoch) __nanosleep(40);
-        __threadfence_system();
-        r0 = src[0];
-        r1 = src[1];
-    }
-}
-
 // records (M_s, S_s) -> stats[0..1] = (max M_s, sum S_s exp(M_s - M)), merged in shard order
 __global__ void __launch_bounds__(32)
-k_mbox_stats(const __grid_constant__ MailboxTable mb, int rank, int nshards, unsigned int epoch, double* stats) {
+k_mbox_stats(const __grid_constant__ MailboxTable mb, int rank, int nshards, unsigned int epoch, double* stats,
+             unsigned int* err) {
     const int lane = threadIdx.x;
     unsigned long long r0, r1;
     mbox_exchange(mb, rank, nshards, epoch, (unsigned long long)__double_as_longlong(stats[0]),
-                  (unsigned long long)__double_as_longlong(stats[1]), lane, r0, r1);
+                  (unsigned long long)__double_as_longlong(stats[1]), lane, r0, r1, err);
     const double m_s = lane < nshards ? __longlong_as_double((long long)r0) : -INFINITY;
     const double s_s = lane < nshards ? __longlong_as_double((long long)r1) : 0.0;
     double M = m_s;
@@ -441,10 +420,10 @@ k_mbox_stats(const __grid_constant__ MailboxTable mb, int rank, int nshards, uns
 // records T_s (uint64) -> offsets[0..nshards] = exclusive prefix of the shard totals, total last
 __global__ void __launch_bounds__(32)
 k_mbox_offsets(const __grid_constant__ MailboxTable mb, int rank, int nshards, unsigned int epoch,
-               const uint64_t* __restrict__ total, uint64_t* __restrict__ offsets) {
+               const uint64_t* __restrict__ total, uint64_t* __restrict__ offsets, unsigned int* err) {
     const int lane = threadIdx.x;
     unsigned long long r0, r1;
-    mbox_exchange(mb, rank, nshards, epoch, (unsigned long long)total[0], 0ull, lane, r0, r1);
+    mbox_exchange(mb, rank, nshards, epoch, (unsigned long long)total[0], 0ull, lane, r0, r1, err);
     unsigned long long incl = r0;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -455,15 +434,37 @@ k_mbox_offsets(const __grid_constant__ MailboxTable mb, int rank, int nshards, u
     if (lane == 0) offsets[0] = 0;
 }
 
-static int build_mailboxes(void* const boxes[GSE_MAX_SHARDS], int rank, int nshards, MailboxTable* mb) {
-    GSE_REQUIRE(boxes != NULL && nshards >= 1 && nshards <= GSE_MAX_SHARDS && rank >= 0 && rank < nshards,
-                "bad mailbox arguments");
-    memset(mb, 0, sizeof(*mb));
+// records of 48 doubles (the output block of the moments kernels: S0, S1[5], S2[15], pivot[5], extra[15], M, S, ...):
+// merged in shard order into the moments of the whole population about shard 0's pivot,
+//   S0 = sum s0,  S1 = sum (s1 + s0 d),  S2 = sum (s2 + s1 d' + d s1' + s0 d d'),  d = pivot_s - pivot_0,
+// the extra block (GS-UKF: sum w P) is a plain sum.  Every rank ends up with the same 48 doubles.
+#define MOM_WORDS 48
+__global__ void __launch_bounds__(32)
+k_mbox_moments(const __grid_constant__ MailboxTable mb, int rank, int nshards, unsigned int epoch, double* mom,
+               unsigned int* err) {
+    const int lane = threadIdx.x;
+    mbox_exchange_block(mb, rank, nshards, epoch, reinterpret_cast<const unsigned long long*>(mom), MOM_WORDS, lane, err);
+    if (lane != 0) return;
+    double S0 = 0.0, S1[5] = {0, 0, 0, 0, 0}, S2[15], X[15], p[5];
+    for (int k = 0; k < 15; ++k) { S2[k] = 0.0; X[k] = 0.0; }
     for (int t = 0; t < nshards; ++t) {
-        GSE_REQUIRE(boxes[t] != NULL, "mailbox pointer is NULL");
-        mb->box[t] = (unsigned char*)boxes[t];
+        volatile unsigned long long* src = mbox_slot(mb, rank, t, epoch);
+        double m[41];
+        for (int k = 0; k < 41; ++k) m[k] = __longlong_as_double((long long)src[k]);
+        if (t == 0) for (int j = 0; j < 5; ++j) p[j] = m[21 + j];
+        double d[5];
+        for (int j = 0; j < 5; ++j) d[j] = m[21 + j] - p[j];
+        int q = 0;
+        for (int i = 0; i < 5; ++i)
+            for (int j = 0; j <= i; ++j, ++q)
+                S2[q] += m[6 + q] + m[1 + i] * d[j] + d[i] * m[1 + j] + m[0] * d[i] * d[j];
+        for (int j = 0; j < 5; ++j) S1[j] += m[1 + j] + m[0] * d[j];
+        S0 += m[0];
+        for (int k = 0; k < 15; ++k) X[k] += m[26 + k];
     }
-    return GSE_OK;
+    mom[0] = S0;
+    for (int j = 0; j < 5; ++j) { mom[1 + j] = S1[j]; mom[21 + j] = p[j]; }
+    for (int k = 0; k < 15; ++k) { mom[6 + k] = S2[k]; mom[26 + k] = X[k]; }
 }
 
 extern "C" int gse_peer_allgather_stats(gse_ctx* ctx, void* const mailboxes[GSE_MAX_SHARDS], int rank, int nshards,
@@ -471,9 +472,9 @@ extern "C" int gse_peer_allgather_stats(gse_ctx* ctx, void* const mailboxes[GSE_
     GSE_REQUIRE(ctx != NULL && stats_dev != NULL && epoch != 0, "bad arguments");
     gse_device_guard guard(ctx->device);
     MailboxTable mb;
-    int rc = build_mailboxes(mailboxes, rank, nshards, &mb);
+    int rc = gse_build_mailboxes(mailboxes, rank, nshards, &mb);
     if (rc) return rc;
-    k_mbox_stats<<<1, 32, 0, (cudaStream_t)stream>>>(mb, rank, nshards, epoch, stats_dev);
+    k_mbox_stats<<<1, 32, 0, (cudaStream_t)stream>>>(mb, rank, nshards, epoch, stats_dev, ctx->err_dev);
     GSE_CHECK_LAUNCH(ctx);
     return GSE_OK;
 }
@@ -484,9 +485,21 @@ extern "C" int gse_peer_allgather_totals(gse_ctx* ctx, void* const mailboxes[GSE
     GSE_REQUIRE(ctx != NULL && total_dev != NULL && offsets_dev != NULL && epoch != 0, "bad arguments");
     gse_device_guard guard(ctx->device);
     MailboxTable mb;
-    int rc = build_mailboxes(mailboxes, rank, nshards, &mb);
+    int rc = gse_build_mailboxes(mailboxes, rank, nshards, &mb);
     if (rc) return rc;
-    k_mbox_offsets<<<1, 32, 0, (cudaStream_t)stream>>>(mb, rank, nshards, epoch, total_dev, offsets_dev);
+    k_mbox_offsets<<<1, 32, 0, (cudaStream_t)stream>>>(mb, rank, nshards, epoch, total_dev, offsets_dev, ctx->err_dev);
+    GSE_CHECK_LAUNCH(ctx);
+    return GSE_OK;
+}
+
+extern "C" int gse_peer_allgather_moments(gse_ctx* ctx, void* const mailboxes[GSE_MAX_SHARDS], int rank, int nshards,
+                                          unsigned int epoch, double* mom_dev, void* stream) {
+    GSE_REQUIRE(ctx != NULL && mom_dev != NULL && epoch != 0, "bad arguments");
+    gse_device_guard guard(ctx->device);
+    MailboxTable mb;
+    int rc = gse_build_mailboxes(mailboxes, rank, nshards, &mb);
+    if (rc) return rc;
+    k_mbox_moments<<<1, 32, 0, (cudaStream_t)stream>>>(mb, rank, nshards, epoch, mom_dev, ctx->err_dev);
     GSE_CHECK_LAUNCH(ctx);
     return GSE_OK;
 }
@@ -545,9 +558,12 @@ extern "C" int gse_weights_linear(gse_ctx* ctx, const float* loglik_dev, const d
 template <int NEXTRA, int GMODE>      // GMODE as in k_pf_predict
 __global__ void __launch_bounds__(MOM_THREADS, NEXTRA < 0 ? 4 : (NEXTRA == 0 ? 2 : 1))
 k_moments(const float* __restrict__ x, const float* __restrict__ extra, int64_t ld, int64_t n,
-          const int32_t* __restrict__ idx, const __grid_constant__ GatherShards shards,
+          const int32_t* __restrict__ idx, const __grid_constant__ GatherShards shards_arg,
           const float* __restrict__ loglik, const double* __restrict__ base,
           const double* __restrict__ stats, double* partials, unsigned int* ticket, double* out) {
+    __shared__ GatherShards s_shards;
+    if (GMODE == 2) stage_shards(&s_shards, shards_arg);
+    const GatherShards& shards = GMODE == 2 ? s_shards : shards_arg;
     constexpr bool MEAN = NEXTRA < 0;
     constexpr int NV = MEAN ? 6 : 21 + NEXTRA;
     const float M = (float)stats[0];
@@ -570,18 +586,18 @@ k_moments(const float* __restrict__ x, const float* __restrict__ extra, int64_t 
         const int64_t row0 = g * 4;
         float4 c[5];
         int id[4] = {0, 0, 0, 0};
+        const float* qs[4] = {NULL, NULL, NULL, NULL};     // GMODE 2: column 0 of each row in its owner's buffer
+        int64_t ls[4] = {0, 0, 0, 0};
         if (GMODE != 0) {
             const int4 id4 = *reinterpret_cast<const int4*>(idx + row0);
             id[0] = id4.x; id[1] = (row0 + 1 < n) ? id4.y : id4.x; id[2] = (row0 + 2 < n) ? id4.z : id4.x;
             id[3] = (row0 + 3 < n) ? id4.w : id4.x;
             if (GMODE == 2) {
-                int64_t l0, l1, l2, l3;
-                const float* q0 = shard_row(shards, id[0], l0);
-                const float* q1 = shard_row(shards, id[1], l1);
-                const float* q2 = shard_row(shards, id[2], l2);
-                const float* q3 = shard_row(shards, id[3], l3);
 #pragma unroll
-                for (int j = 0; j < 5; ++j) c[j] = make_float4(q0[j * l0], q1[j * l1], q2[j * l2], q3[j * l3]);
+                for (int r = 0; r < 4; ++r) qs[r] = shard_row(shards, id[r], ls[r]);
+#pragma unroll
+                for (int j = 0; j < 5; ++j)
+                    c[j] = make_float4(qs[0][j * ls[0]], qs[1][j * ls[1]], qs[2][j * ls[2]], qs[3][j * ls[3]]);
             } else {
 #pragma unroll
                 for (int j = 0; j < 5; ++j)
@@ -616,8 +632,11 @@ k_moments(const float* __restrict__ x, const float* __restrict__ extra, int64_t 
                 }
                 if (NEXTRA > 0) {
 #pragma unroll
-                    for (int k = 0; k < NEXTRA; ++k)
-                        acc[21 + k] = fma(w, (double)extra[k * ld + (GMODE == 1 ? (int64_t)id[r] : row0 + r)], acc[21 + k]);
+                    for (int k = 0; k < NEXTRA; ++k) {
+                        const float ex = GMODE == 2 ? qs[r][(5 + k) * ls[r]]
+                                                    : extra[k * ld + (GMODE == 1 ? (int64_t)id[r] : row0 + r)];
+                        acc[21 + k] = fma(w, (double)ex, acc[21 + k]);
+                    }
                 }
             }
         }
@@ -663,8 +682,11 @@ k_moments(const float* __restrict__ x, const float* __restrict__ extra, int64_t 
 template <int GMODE>
 __global__ void __launch_bounds__(MOM_THREADS)
 k_means(const float* __restrict__ x, int64_t ld, int64_t n, const int32_t* __restrict__ idx,
-        const __grid_constant__ GatherShards shards, const float* __restrict__ loglik,
+        const __grid_constant__ GatherShards shards_arg, const float* __restrict__ loglik,
         const double* __restrict__ stats, double* partials, unsigned int* ticket, double* out) {
+    __shared__ GatherShards s_shards;
+    if (GMODE == 2) stage_shards(&s_shards, shards_arg);
+    const GatherShards& shards = GMODE == 2 ? s_shards : shards_arg;
     constexpr int NV = 6;
     const float M = (float)stats[0];
     double acc[NV];
@@ -739,7 +761,7 @@ k_means(const float* __restrict__ x, int64_t ld, int64_t n, const int32_t* __res
     if (threadIdx.x == 0) *ticket = 0u;
 }
 
-static int launch_moments(gse_ctx* ctx, const float* x, const float* extra, int64_t ld, int64_t n,
+static int launch_moments(gse_ctx* ctx, const float* x, const float* extra, bool gsf, int64_t ld, int64_t n,
                           const int32_t* idx, const GatherShards* shards, bool mean_only, const float* loglik, const double* base, const double* stats, double* out,
                           void* stream) {
     GSE_REQUIRE(ctx != NULL && stats != NULL && out != NULL, "ctx / stats / out is NULL");
@@ -749,7 +771,7 @@ static int launch_moments(gse_ctx* ctx, const float* x, const float* extra, int6
     GatherShards none;
     memset(&none, 0, sizeof(none));
     const GatherShards& sh = shards ? *shards : none;
-    GSE_REQUIRE(shards == NULL || (idx != NULL && extra == NULL), "sharded moments need idx and no extra columns");
+    GSE_REQUIRE(shards == NULL || idx != NULL, "sharded moments need idx");
     const int64_t groups = gse_div_up(n, 4);
     int64_t blocks = gse_div_up(groups, MOM_THREADS);
     const int64_t cap = (int64_t)ctx->num_sms * 8;
@@ -763,7 +785,7 @@ static int launch_moments(gse_ctx* ctx, const float* x, const float* extra, int6
 #define LAUNCH_MEANS(G)                                                                                      \
     k_means<G><<<(unsigned)blocks, MOM_THREADS, 0, (cudaStream_t)stream>>>(x, ld, n, idx, sh, loglik, stats,     \
                                                                            ctx->red_partials, ctx->ticket + 2, out)
-    if (extra) { if (idx) LAUNCH_MOM(15, 1, extra); else LAUNCH_MOM(15, 0, extra); }
+    if (gsf) { if (shards) LAUNCH_MOM(15, 2, extra); else if (idx) LAUNCH_MOM(15, 1, extra); else LAUNCH_MOM(15, 0, extra); }
     else if (mean_only && base == NULL) {                  // the common point_estimate: float32 group sums
         if (shards) LAUNCH_MEANS(2);
         else if (idx) LAUNCH_MEANS(1);
@@ -783,7 +805,7 @@ static int launch_moments(gse_ctx* ctx, const float* x, const float* extra, int6
 extern "C" int gse_pf_moments(gse_ctx* ctx, const float* x_dev, int64_t ld, int64_t n, const int32_t* idx_dev,
                               const float* loglik_dev, const double* base_dev, const double* stats_dev,
                               int mean_only, double* out_dev, void* stream) {
-    return launch_moments(ctx, x_dev, NULL, ld, n, idx_dev, NULL, mean_only != 0, loglik_dev, base_dev, stats_dev,
+    return launch_moments(ctx, x_dev, NULL, false, ld, n, idx_dev, NULL, mean_only != 0, loglik_dev, base_dev, stats_dev,
                           out_dev, stream);
 }
 
@@ -793,7 +815,7 @@ extern "C" int gse_pf_moments_sharded(gse_ctx* ctx, const gse_shards* shards, co
     GatherShards g;
     int rc = gse_build_gather_shards(shards, NULL, &g);
     if (rc) return rc;
-    return launch_moments(ctx, NULL, NULL, 0, n, idx_dev, &g, mean_only != 0, loglik_dev, base_dev, stats_dev, out_dev,
+    return launch_moments(ctx, NULL, NULL, false, 0, n, idx_dev, &g, mean_only != 0, loglik_dev, base_dev, stats_dev, out_dev,
                           stream);
 }
 
@@ -801,8 +823,17 @@ extern "C" int gse_gsf_moments(gse_ctx* ctx, const float* mean_dev, const float*
                                const int32_t* idx_dev, const float* loglik_dev, const double* base_dev,
                                const double* stats_dev, double* out_dev, void* stream) {
     GSE_REQUIRE(cov_dev != NULL, "cov is NULL");
-    return launch_moments(ctx, mean_dev, cov_dev, ld, n, idx_dev, NULL, false, loglik_dev, base_dev, stats_dev, out_dev,
+    return launch_moments(ctx, mean_dev, cov_dev, true, ld, n, idx_dev, NULL, false, loglik_dev, base_dev, stats_dev, out_dev,
                           stream);
+}
+
+extern "C" int gse_gsf_moments_sharded(gse_ctx* ctx, const gse_shards* shards, const int32_t* idx_dev, int64_t n,
+                                       const float* loglik_dev, const double* base_dev, const double* stats_dev,
+                                       double* out_dev, void* stream) {
+    GatherShards g;
+    int rc = gse_build_gather_shards(shards, NULL, &g);
+    if (rc) return rc;
+    return launch_moments(ctx, NULL, NULL, true, 0, n, idx_dev, &g, false, loglik_dev, base_dev, stats_dev, out_dev, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -861,8 +861,10 @@ k_gather_rows(const int32_t* __restrict__ idx, int64_t n_out, const float* __res
 // dst[:, i] = state of global row idx[i], pulled from whichever shard owns it (peer memory over NVLink)
 template <bool VEC>
 __global__ void __launch_bounds__(GR_THREADS)
-k_gather_rows_sharded(const __grid_constant__ GatherShards g, const int32_t* __restrict__ idx, int64_t n_out,
+k_gather_rows_sharded(const __grid_constant__ GatherShards g_arg, const int32_t* __restrict__ idx, int64_t n_out,
                       float* __restrict__ dst, int64_t ld_dst, int ncols) {
+    __shared__ GatherShards g;
+    stage_shards(&g, g_arg);
     if (VEC) {
         const int64_t row0 = ((int64_t)blockIdx.x * GR_THREADS + threadIdx.x) * 4;
         if (row0 >= n_out) return;

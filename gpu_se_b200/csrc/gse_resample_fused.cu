@@ -23,6 +23,7 @@
 // gse_resample_search_f64 feeds the same rank + fill code with a caller's own float64 cumulative sum
 // (`resample_from_cumsum`, SURVEY.md section 7 contract (ii)).
 #include "gse_resample_common.cuh"
+#include "gse_mailbox.cuh"
 
 #define RF_THREADS 256
 #define RF_WARPS (RF_THREADS / 32)
@@ -60,6 +61,13 @@ struct FusedArgs {
     int first_shard;           // local row 0 is the first row of the whole population (e_{-1} = 0)
     int normalise;             // f64 entry: divide by cumsum[n_src - 1] on the fly (`cumsum /= cumsum[-1]`, :90)
     uint64_t* total_out;       // receives the integer total (NULL to skip)
+    // sharded population (SHARDED kernels): every rank ranks its OWN rows against the global total and writes the
+    // ancestor of every output it sources straight into the index buffer of the shard that owns the output slot
+    int nshards, rank;
+    unsigned int epoch_totals, epoch_done;     // mailbox sequence numbers of the two exchanges inside the kernel
+    int shard_lo[GSE_MAX_SHARDS + 1];          // shard t owns the output slots [shard_lo[t], shard_lo[t + 1])
+    int32_t* shard_idx[GSE_MAX_SHARDS];        // shard t's index buffer (its local slot 0), peer memory for t != rank
+    MailboxTable mb;
     unsigned long long* trace; // GSE_FUSED_TRACE: 8 words per CTA (globaltimer at start / phase 1 / 2 / 3 done, SM id, ...), or NULL
 };
 
@@ -210,6 +218,20 @@ __device__ __forceinline__ void ranks_of(double C0, const double (&q)[RF_ITEMS],
 // the markers over the runs (carry = the source covering the window's first output) and the window leaves as two
 // coalesced 128-bit stores per lane.  Only the first and the last window of a sub-run are partial (masked scalar stores).
 // ------------------------------------------------------------------------------------------------
+// shard table of the SHARDED kernels in shared memory (indexing the kernel parameter with a run-time index would push
+// the whole argument struct into local memory)
+struct ShardTable {
+    int nshards;
+    int lo[GSE_MAX_SHARDS + 1];
+    int32_t* idx[GSE_MAX_SHARDS];
+};
+__device__ __forceinline__ int shard_of_output(const ShardTable& st, int j) {
+    int t = 0;
+#pragma unroll
+    for (int u = 1; u < GSE_MAX_SHARDS; ++u) t += (u < st.nshards && j >= st.lo[u]) ? 1 : 0;
+    return t;
+}
+
 struct WarpFill {
     int wb;            // first output of the oldest window not yet flushed (multiple of RF_WIN)
     int carry_m;       // marker of the source that covers output wb (0: none yet -- only below the sub-run's first output)
@@ -219,8 +241,11 @@ struct WarpFill {
     int* ring;
     int32_t* out;      // idx_out - out_lo
     bool vec_ok;       // out + (multiple of 4) is 16-byte aligned
+    const ShardTable* st;   // SHARDED kernels: where each output slot lives
 
-    __device__ __forceinline__ void begin(int E0, const FusedArgs& a, int vbase_, int* ring_, int lane) {
+    __device__ __forceinline__ void begin(int E0, const FusedArgs& a, int vbase_, int* ring_, int lane,
+                                          const ShardTable* st_ = NULL) {
+        st = st_;
         ring = ring_;
         vbase = vbase_;
         out = a.idx_out - a.out_lo;
@@ -235,7 +260,8 @@ struct WarpFill {
 
     // complete window [wb, wb + RF_WIN): prefix maximum of its markers, store, clear, advance.  Lane l owns the outputs
     // wb + 4 l + {0..3} and wb + 128 + 4 l + {0..3}: both 128-bit stores of the warp are fully coalesced.
-    __device__ __forceinline__ void flush(int lane, int mhi) {
+    template <bool SHARDED>
+    __device__ __forceinline__ void flush(int lane, int mhi, const FusedArgs& fa) {
         int4* r4 = reinterpret_cast<int4*>(ring + (wb & (RF_RING - 1)));
         int4 a = r4[lane], b = r4[32 + lane];
         r4[lane] = make_int4(0, 0, 0, 0);
@@ -257,6 +283,28 @@ struct WarpFill {
         a = make_int4(max(a.x, ea) + va, max(a.y, ea) + va, max(a.z, ea) + va, max(a.w, ea) + va);
         b = make_int4(max(b.x, eb) + va, max(b.y, eb) + va, max(b.z, eb) + va, max(b.w, eb) + va);
         carry_m = max(tot_a, __shfl_sync(0xffffffffu, ib, 31));
+        if (SHARDED) {
+            // the window usually lies inside one shard's slots: two coalesced 128-bit stores into that shard's buffer
+            // (over NVLink when it is a peer's); windows across a shard boundary or the sub-run's ends go element-wise
+            const int t0 = shard_of_output(*st, wb), t1 = shard_of_output(*st, wb + RF_WIN - 1);
+            if (t0 == t1 && wb >= mlo && wb + RF_WIN <= mhi) {
+                int32_t* o = st->idx[t0] + (wb - st->lo[t0]) + 4 * lane;
+                *reinterpret_cast<int4*>(o) = a;
+                *reinterpret_cast<int4*>(o + 128) = b;
+            } else {
+                const int vals[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int p = wb + 4 * lane + (i & 3) + (i >> 2) * 128;
+                    if (p >= mlo && p < mhi) {
+                        const int t = shard_of_output(*st, p);
+                        st->idx[t][p - st->lo[t]] = vals[i];
+                    }
+                }
+            }
+            wb += RF_WIN;
+            return;
+        }
         int32_t* o = out + wb + 4 * lane;
         if (vec_ok && wb >= mlo && wb + RF_WIN <= mhi) {
             *reinterpret_cast<int4*>(o) = a;
@@ -277,6 +325,7 @@ struct WarpFill {
 
     // one tile: lane's sources have ranks e[0..7], the source before the lane's first has rank ep; the tile's outputs are
     // [E0, E1); mbase = marker of the tile's first source
+    template <bool SHARDED>
     __device__ __forceinline__ void tile(const int (&e)[RF_ITEMS], int ep, int E0, int E1, int mbase, const FusedArgs& a,
                                          int lane) {
         const int E1c = min(E1, hi_al);
@@ -303,7 +352,7 @@ struct WarpFill {
             __syncwarp();
             bool again = E1c > limit;
             while (wb + RF_WIN <= min(E1c, limit)) {
-                flush(lane, a.out_hi);
+                flush<SHARDED>(lane, a.out_hi, a);
                 if (maybe_heavy && carry_m >= mbase) {
                     // the source covering the new window is one of this tile's: does its run go on for long?
                     // (one shuffle per k, then a uniform select: indexing e[] with li would push the array into local memory)
@@ -339,42 +388,60 @@ struct WarpFill {
     }
 
     // end of the sub-run: its last outputs sit in a partial window
+    template <bool SHARDED>
     __device__ __forceinline__ void finish(int E1, const FusedArgs& a, int lane) {
         const int mhi = min(E1, a.out_hi);
         __syncwarp();
-        if (wb < mhi) flush(lane, mhi);
+        if (wb < mhi) flush<SHARDED>(lane, mhi, a);
     }
 };
 
+// [p, end) of one destination buffer <- val: head up to 16-byte alignment, 128-bit body, tail
+__device__ __forceinline__ void warp_fill_const(int32_t* out, int p, int end, int val, int lane) {
+    const int head = min(end, p + (int)((4 - (((uintptr_t)(out + p) >> 2) & 3)) & 3));
+    if (p + lane < head) out[p + lane] = val;
+    p = head;
+    const int4 v4 = make_int4(val, val, val, val);
+    for (int q = p + 4 * lane; q + 4 <= end; q += 128) *reinterpret_cast<int4*>(out + q) = v4;
+    const int body_end = p + ((end - p) & ~3);
+    if (body_end + lane < end) out[body_end + lane] = val;
+}
+
 // drain of the heavy-run queue by every warp of the grid (after all CTAs have finished phase 3)
-__device__ __forceinline__ void drain_queue(const FusedArgs& a, int vb, int nblocks, int lane, int wid) {
+template <bool SHARDED>
+__device__ __forceinline__ void drain_queue(const FusedArgs& a, const ShardTable* st, int vb, int nblocks, int lane, int wid) {
     const int qn = min((int)ld_status32(a.counters + 2), a.queue_cap);
     for (int i = vb * RF_WARPS + wid; i < qn; i += nblocks * RF_WARPS) {
         const int4 ent = __ldcg(a.queue + i);
-        int32_t* out = a.idx_out - a.out_lo;
-        int p = ent.x;
-        const int end = ent.y, val = ent.z;
-        // head up to 16-byte alignment, 128-bit body, tail
-        const int head = min(end, p + (int)((4 - (((uintptr_t)(out + p) >> 2) & 3)) & 3));
-        if (p + lane < head) out[p + lane] = val;
-        p = head;
-        const int4 v4 = make_int4(val, val, val, val);
-        for (int q = p + 4 * lane; q + 4 <= end; q += 128) *reinterpret_cast<int4*>(out + q) = v4;
-        const int body_end = p + ((end - p) & ~3);
-        if (body_end + lane < end) out[body_end + lane] = val;
+        if (!SHARDED) {
+            warp_fill_const(a.idx_out - a.out_lo, ent.x, ent.y, ent.z, lane);
+        } else {
+            for (int t = shard_of_output(*st, ent.x); t < st->nshards && st->lo[t] < ent.y; ++t) {
+                const int lo = max(ent.x, st->lo[t]), hi = min(ent.y, st->lo[t + 1]);
+                if (hi > lo) warp_fill_const(st->idx[t] - st->lo[t], lo, hi, ent.z, lane);
+            }
+        }
     }
 }
 
-template <bool HAS_LL, bool HAS_BASE, bool POW2, int MINB>
+template <bool HAS_LL, bool HAS_BASE, bool POW2, int MINB, bool SHARDED>
 __global__ void __launch_bounds__(RF_THREADS, MINB)
 k_resample_fused(const __grid_constant__ FusedArgs a) {
     __shared__ __align__(16) int s_ring[RF_WARPS][RF_RING];
     __shared__ double s_wsum[RF_WARPS];
     __shared__ uint64_t s_part[RF_WARPS][2];
     __shared__ unsigned int s_vb;
+    __shared__ ShardTable s_st;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int nblocks = gridDim.x;
     if (tid == 0) s_vb = atomicAdd(a.counters, 1u);               // CTAs are numbered in the order they start
+    if (SHARDED && tid == 32) {
+        s_st.nshards = a.nshards;
+#pragma unroll
+        for (int t = 0; t <= GSE_MAX_SHARDS; ++t) s_st.lo[t] = a.shard_lo[t];
+#pragma unroll
+        for (int t = 0; t < GSE_MAX_SHARDS; ++t) s_st.idx[t] = a.shard_idx[t];
+    }
     __syncthreads();
     const int vb = (int)s_vb;
     if (a.trace && tid == 0) { a.trace[8 * vb] = global_timer_ns(); unsigned int smid; asm("mov.u32 %0, %%smid;" : "=r"(smid)); a.trace[8 * vb + 4] = smid; }
@@ -437,17 +504,32 @@ k_resample_fused(const __grid_constant__ FusedArgs a) {
         const uint64_t incl_w = warp_inclusive_scan_u64(part, lane);
         if (lane == 31) s_part[wid][0] = incl_w;
         __syncthreads();
-        uint64_t base = 0;
+        uint64_t base = 0, local_total = 0;
 #pragma unroll
-        for (int w = 0; w < RF_WARPS; ++w) base += (w < wid) ? s_part[w][0] : 0ull;
-        uint64_t run = base + incl_w - part;
+        for (int w = 0; w < RF_WARPS; ++w) { base += (w < wid) ? s_part[w][0] : 0ull; local_total += s_part[w][0]; }
+        uint64_t shard_off = 0, total = local_total;
+        if (SHARDED) {
+            // the shards' totals cross NVLink here: exclusive offset of this shard and the global total
+            if (wid == 0) {
+                unsigned long long r0, r1;
+                mbox_exchange(a.mb, a.rank, a.nshards, a.epoch_totals, local_total, 0ull, lane, r0, r1, a.err);
+                const uint64_t incl = warp_inclusive_scan_u64(r0, lane);
+                const uint64_t mine = __shfl_sync(0xffffffffu, incl - r0, a.rank);
+                const uint64_t all = __shfl_sync(0xffffffffu, incl, a.nshards - 1);
+                if (lane == 0) { s_part[0][1] = mine; s_part[1][1] = all; }
+            }
+            __syncthreads();
+            shard_off = s_part[0][1];
+            total = s_part[1][1];
+        }
+        uint64_t run = shard_off + base + incl_w - part;
         for (int k = 0; k < chunk; ++k) {
             if (i0 + k < nblocks) {
                 st_status(prefix + i0 + k, status_pack(ST_PREFIX, 0u, run));
                 run += ld_status(a.status + i0 + k) & ((1ull << 54) - 1ull);
             }
         }
-        if (tid == RF_THREADS - 1) st_status(prefix + nblocks, status_pack(ST_PREFIX, 0u, run));
+        if (tid == 0) st_status(prefix + nblocks, status_pack(ST_PREFIX, 0u, total));
     }
     if (tid == 0) {
         uint64_t w0_ = ld_status(prefix + vb);
@@ -459,7 +541,7 @@ k_resample_fused(const __grid_constant__ FusedArgs a) {
     }
     __syncthreads();
     const uint64_t excl_u = s_part[0][0], tot_u = s_part[0][1];
-    if (tid == 0 && vb == 0 && a.total_out) *a.total_out = tot_u;
+    if (tid == 0 && vb == 0 && a.total_out) *a.total_out = tot_u;          // (sharded: the GLOBAL total)
     if (a.trace && tid == 0) a.trace[8 * vb + 2] = global_timer_ns();
 
     // ---- phase 3: scan + rank + fill, warp-autonomous ---------------------------------------------------------
@@ -474,7 +556,7 @@ k_resample_fused(const __grid_constant__ FusedArgs a) {
         if (!(a.first_shard && w0 == 0) && !degenerate) carry_rank = rank_of<POW2, false, false>(carry, rc);
         if (degenerate && lane == 0 && vb == 0 && wid == 0) atomicOr(a.err, GSE_ERR_ZERO_WEIGHTS);
         WarpFill wf;
-        wf.begin(carry_rank, a, a.src_row0 + (int)w0 - 1, s_ring[wid], lane);
+        wf.begin(carry_rank, a, a.src_row0 + (int)w0 - 1, s_ring[wid], lane, &s_st);
         float lcur[RF_ITEMS];
         if (HAS_LL && !HAS_BASE) load_loglik(a.loglik, w0 + (int64_t)lane * RF_ITEMS, w1, lcur);
         const int ntiles = (int)((w1 - w0 + RF_TILE - 1) / RF_TILE);
@@ -505,10 +587,10 @@ k_resample_fused(const __grid_constant__ FusedArgs a) {
             int ep = __shfl_up_sync(0xffffffffu, e[RF_ITEMS - 1], 1);
             if (lane == 0) ep = carry_rank;
             const int E1 = __shfl_sync(0xffffffffu, e[RF_ITEMS - 1], 31);
-            wf.tile(e, ep, carry_rank, E1, t * RF_TILE + 1, a, lane);
+            wf.template tile<SHARDED>(e, ep, carry_rank, E1, t * RF_TILE + 1, a, lane);
             carry_rank = E1;
         }
-        wf.finish(carry_rank, a, lane);
+        wf.template finish<SHARDED>(carry_rank, a, lane);
     }
 
     // ---- tail: wait for every CTA, drain the heavy-run queue, reset the launch state --------------------------
@@ -521,11 +603,25 @@ k_resample_fused(const __grid_constant__ FusedArgs a) {
         __threadfence();
     }
     __syncthreads();
-    drain_queue(a, vb, nblocks, lane, wid);
+    drain_queue<SHARDED>(a, &s_st, vb, nblocks, lane, wid);
     __syncthreads();
-    if (tid == 0) s_vb = atomicAdd(a.counters + 3, 1u);
+    if (tid == 0) {
+        __threadfence();
+        s_vb = atomicAdd(a.counters + 3, 1u);
+    }
     __syncthreads();
-    if (s_vb == (unsigned int)nblocks - 1u) {                     // last CTA out: leave everything zero for the next launch
+    if (s_vb == (unsigned int)nblocks - 1u) {                     // last CTA out
+        if (SHARDED) {
+            // every ancestor index this rank sources has been written (into local and peer buffers).  Tell the peers
+            // and wait until they have said the same: when this kernel ends, this shard's index buffer is complete.
+            if (wid == 0) {
+                __threadfence_system();
+                unsigned long long r0, r1;
+                mbox_exchange(a.mb, a.rank, a.nshards, a.epoch_done, 1ull, 0ull, lane, r0, r1, a.err);
+            }
+            __syncthreads();
+        }
+        // leave everything zero for the next launch
         for (int i = tid; i < nblocks; i += RF_THREADS) { a.status[i] = 0ull; a.status[RF_MAX_BLOCKS + i] = 0ull; }
         if (tid == 0) a.status[RF_MAX_BLOCKS + nblocks] = 0ull;
         if (tid < 5) a.counters[tid] = 0u;
@@ -581,16 +677,16 @@ k_resample_search_f64(const __grid_constant__ FusedArgs a, int64_t tiles_per_war
         int ep = __shfl_up_sync(0xffffffffu, e[RF_ITEMS - 1], 1);
         if (lane == 0) ep = carry_rank;
         const int E1 = __shfl_sync(0xffffffffu, e[RF_ITEMS - 1], 31);
-        wf.tile(e, ep, carry_rank, E1, (int)(t0 - w0) + 1, a, lane);
+        wf.template tile<false>(e, ep, carry_rank, E1, (int)(t0 - w0) + 1, a, lane);
         carry_rank = E1;
     }
-    wf.finish(carry_rank, a, lane);
+    wf.template finish<false>(carry_rank, a, lane);
 }
 
 // queued heavy runs of k_resample_search_f64 (its CTAs do not wait for one another): a second, tiny launch
 __global__ void __launch_bounds__(RF_THREADS)
 k_resample_drain(const __grid_constant__ FusedArgs a) {
-    drain_queue(a, blockIdx.x, gridDim.x, threadIdx.x & 31, threadIdx.x >> 5);
+    drain_queue<false>(a, NULL, blockIdx.x, gridDim.x, threadIdx.x & 31, threadIdx.x >> 5);
     __syncthreads();
     __shared__ unsigned int s_done;
     if (threadIdx.x == 0) s_done = atomicAdd(a.counters + 3, 1u);
@@ -617,12 +713,12 @@ static void fill_common(gse_ctx* ctx, FusedArgs& a, double r, int64_t n_total, i
     a.src_row0 = (int)src_row0;
 }
 
-template <bool LL, bool BASE, bool POW2, int MINB>
+template <bool LL, bool BASE, bool POW2, int MINB, bool SHARDED>
 static int launch_fused(gse_ctx* ctx, FusedArgs& a, int variant, cudaStream_t s) {
     // every CTA must be resident at once (phase 2 and the tail wait on the other CTAs)
     if (ctx->fused_resident[variant] == 0) {
         int per_sm = 0;
-        GSE_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_resample_fused<LL, BASE, POW2, MINB>,
+        GSE_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_resample_fused<LL, BASE, POW2, MINB, SHARDED>,
                                                                      RF_THREADS, 0));
         GSE_REQUIRE(per_sm >= 1, "fused resample kernel does not fit an SM");
         ctx->fused_resident[variant] = per_sm * ctx->num_sms;
@@ -633,7 +729,7 @@ static int launch_fused(gse_ctx* ctx, FusedArgs& a, int variant, cudaStream_t s)
     a.rows_per_block = gse_div_up(groups, blocks) * group;
     blocks = gse_div_up(a.n_src, a.rows_per_block);
     GSE_REQUIRE(blocks <= ctx->max_tiles && blocks < RF_MAX_BLOCKS, "workspace too small");
-    k_resample_fused<LL, BASE, POW2, MINB><<<(unsigned)blocks, RF_THREADS, 0, s>>>(a);
+    k_resample_fused<LL, BASE, POW2, MINB, SHARDED><<<(unsigned)blocks, RF_THREADS, 0, s>>>(a);
     GSE_CHECK_LAUNCH(ctx);
     return GSE_OK;
 }
@@ -666,14 +762,72 @@ extern "C" int gse_resample_fused(gse_ctx* ctx, const float* loglik_dev, const d
     const bool pow2 = (n_total & (n_total - 1)) == 0;
 #define FUSED_CASE(LL, BASE, V)                                                           \
     do {                                                                                  \
-        if (pow2 && ctx->fused_minb == 3) return launch_fused<LL, BASE, true, 3>(ctx, a, 6 + (V), s);   \
-        if (pow2) return launch_fused<LL, BASE, true, 4>(ctx, a, 2 * (V), s);             \
-        return launch_fused<LL, BASE, false, 4>(ctx, a, 2 * (V) + 1, s);                  \
+        if (pow2 && ctx->fused_minb == 3) return launch_fused<LL, BASE, true, 3, false>(ctx, a, 6 + (V), s);   \
+        if (pow2) return launch_fused<LL, BASE, true, 4, false>(ctx, a, 2 * (V), s);      \
+        return launch_fused<LL, BASE, false, 4, false>(ctx, a, 2 * (V) + 1, s);           \
     } while (0)
     if (loglik_dev && base_dev) FUSED_CASE(true, true, 0);
     else if (loglik_dev) FUSED_CASE(true, false, 1);
     else FUSED_CASE(false, true, 2);
 #undef FUSED_CASE
+    return GSE_OK;
+}
+
+// Sharded population: the same kernel on every rank, two mailbox exchanges inside it (shard totals after the local
+// scan, "all my writes are out" at the end).  Scan, search, the collectives and the exchange of ancestor indices are ONE
+// launch per rank; nothing goes through the host or NCCL.
+extern "C" int gse_resample_fused_sharded(gse_ctx* ctx, const float* loglik_dev, const double* base_dev,
+                                          const double* stats_dev, double r, const gse_shards* sh,
+                                          void* const mailboxes[GSE_MAX_SHARDS], int rank, unsigned int epoch_totals,
+                                          unsigned int epoch_done, uint64_t* total_dev, void* stream) {
+    GSE_REQUIRE(ctx != NULL && stats_dev != NULL && sh != NULL, "ctx / stats / shards is NULL");
+    GSE_REQUIRE(loglik_dev != NULL || base_dev != NULL, "need loglik or base weights");
+    GSE_REQUIRE(loglik_dev == NULL || aligned32(loglik_dev), "loglik must be 32-byte aligned");
+    GSE_REQUIRE(base_dev == NULL || aligned32(base_dev), "base must be 32-byte aligned");
+    GSE_REQUIRE(sh->nshards >= 1 && sh->nshards <= GSE_MAX_SHARDS && rank >= 0 && rank < sh->nshards, "bad shard table");
+    GSE_REQUIRE(epoch_totals != 0 && epoch_done != 0 && epoch_totals != epoch_done, "bad mailbox epochs");
+    const int64_t n_total = sh->rows[sh->nshards];
+    GSE_REQUIRE(sh->rows[0] == 0 && n_total >= 1 && n_total <= 0x7ffffff0ll, "global row count out of range (int32 index)");
+    const int64_t n_src = sh->rows[rank + 1] - sh->rows[rank];
+    GSE_REQUIRE(n_src >= 1 && n_src <= ctx->n_max, "n_src out of range for this context");
+    // this rank may source every output of the population: the heavy-run queue must hold n_total / 4096 runs in pieces
+    GSE_REQUIRE(n_total / RF_HEAVY_MIN + n_total / RF_PIECE + 2 <= (int64_t)ctx->heavy_queue_cap,
+                "workspace too small (create the context with workspace rows >= global rows)");
+    GSE_REQUIRE(r >= 0.0 && r < 1.0, "r must be in [0, 1)");
+    gse_device_guard guard(ctx->device);
+    FusedArgs a;
+    memset(&a, 0, sizeof(a));
+    a.loglik = loglik_dev;
+    a.base = base_dev;
+    a.stats = stats_dev;
+    a.n_src = n_src;
+    a.first_shard = (rank == 0) ? 1 : 0;
+    a.total_out = total_dev;
+    a.trace = ctx->fused_trace;
+    a.nshards = sh->nshards;
+    a.rank = rank;
+    a.epoch_totals = epoch_totals;
+    a.epoch_done = epoch_done;
+    for (int t = 0; t <= sh->nshards; ++t) a.shard_lo[t] = (int)sh->rows[t];
+    for (int t = 0; t < sh->nshards; ++t) {
+        GSE_REQUIRE(sh->idx_dev[t] != NULL && (((uintptr_t)sh->idx_dev[t]) & 15u) == 0 && sh->rows[t] % 4 == 0,
+                    "shard index buffers must be non-NULL and 16-byte aligned, shards cut at multiples of four rows");
+        a.shard_idx[t] = sh->idx_dev[t];
+    }
+    int rc = gse_build_mailboxes(mailboxes, rank, sh->nshards, &a.mb);
+    if (rc) return rc;
+    fill_common(ctx, a, r, n_total, 0, n_total, sh->idx_dev[rank], sh->rows[rank]);
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool pow2 = (n_total & (n_total - 1)) == 0;
+#define SHARDED_CASE(LL, BASE, V)                                                         \
+    do {                                                                                  \
+        if (pow2) return launch_fused<LL, BASE, true, 4, true>(ctx, a, 9 + 2 * (V), s);   \
+        return launch_fused<LL, BASE, false, 4, true>(ctx, a, 10 + 2 * (V), s);           \
+    } while (0)
+    if (loglik_dev && base_dev) SHARDED_CASE(true, true, 0);
+    else if (loglik_dev) SHARDED_CASE(true, false, 1);
+    else SHARDED_CASE(false, true, 2);
+#undef SHARDED_CASE
     return GSE_OK;
 }
 

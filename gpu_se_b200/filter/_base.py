@@ -136,11 +136,7 @@ class WeightedEnsemble:
         self._loglik_dirty = False
         self._stats = torch.tensor([0.0, float(n), 0.0, 0.0], dtype=torch.float64, device=dev)
         self._stats_uniform = self._stats.clone()
-        if peer:
-            from gpu_se_b200 import _peer
-            self._cumsum, self._peer_bufs["cumsum"] = _peer.peer_zeros(dev, (self._ld,), torch.int64)
-        else:
-            self._cumsum = torch.zeros(self._ld, dtype=torch.int64, device=dev)  # uint64 payload
+        self._cumsum = None            # uint64 cumulative weights: only the two-stage scan / search path materialises them
         self._offtot = torch.zeros(2, dtype=torch.int64, device=dev)             # [offset, total]
         self._mom = torch.zeros(48, dtype=torch.float64, device=dev)
         self._mom_host = torch.zeros(48, dtype=torch.float64).pin_memory()
@@ -309,6 +305,8 @@ class WeightedEnsemble:
     def _scan(self):
         """cumsum of the fixed-point weights -> self._cumsum, total -> self._offtot[1]."""
         n = self.N_particles
+        if self._cumsum is None:
+            self._cumsum = torch.zeros(self._ld, dtype=torch.int64, device=self.device)  # uint64 payload
         ll, base, stats = self._weight_sources()
         _lib.check(_lib.lib.gse_scan_weights(self._ctx.handle, ll, base, stats.data_ptr(), n, self._cumsum.data_ptr(),
                                              self._offtot.data_ptr() + 8, self._stream()))

@@ -18,16 +18,17 @@ _TRI = [(i, j) for i in range(5) for j in range(i + 1)]
 
 class ParallelGaussianSumUnscentedKalmanFilter(WeightedEnsemble):
     """GS-UKF running on the GPU; parameters as the reference (gs_ukf.py:187-221) plus keyword-only
-    ``device``, ``seed`` and ``means`` (initial means instead of ``x0.draw(N)``)."""
+    ``device``, ``seed``, ``means`` (initial means instead of ``x0.draw(N)``) and, for one shard of a larger population,
+    ``index0`` / ``workspace_rows`` / ``peer`` as in ParallelParticleFilter."""
 
     NCOLS = 20
 
     def __init__(self, f, g, N_particles, x0, state_pdf, measurement_pdf, *, device=None, seed=None, means=None,
-                 index0=0, workspace_rows=None):
+                 index0=0, workspace_rows=None, peer=False):
         self.f = f
         self.g = g
         self._model_id = model_id_for(f, g)
-        self._init_ensemble(N_particles, state_pdf, measurement_pdf, device, seed, workspace_rows)
+        self._init_ensemble(N_particles, state_pdf, measurement_pdf, device, seed, workspace_rows, peer)
         self._index0 = int(index0)
         n = self.N_particles
         self._Nx, self._Ny, self._N_sigmas = 5, 2, 11

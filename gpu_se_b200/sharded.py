@@ -1,49 +1,39 @@
-"""Particle filter sharded over the GPUs of one node: one process per GPU (``torch.distributed``,
-NCCL over NVLink 5 / NVSwitch), contiguous shards of the global row index space, and a globally
-consistent systematic resample.
+"""Particle filter / GS-UKF sharded over the GPUs of one node: one process per GPU (``torch.distributed`` for the
+rendezvous), contiguous shards of the global row index space, and a globally consistent systematic resample.
 
 The reference has no multi-GPU path; this is the north-star design:
 
-* ``predict`` / ``update`` / moments touch local rows only.  The Philox stream is keyed by the GLOBAL
-  row index, so a sharded run draws exactly the noise a single-GPU run of the same seed draws.
-* after ``update`` the local ``(M_s, S_s)`` = (max log-likelihood, sum exp(loglik - M_s)) are combined
-  with two tiny all-reduces (max, then sum of S_s * exp(M_s - M)), so that every shard quantises its
-  weights with the same fixed-point scale (csrc/gse_resample.cu) -- the cumulative weights are
-  integers, hence independent of how the rows are split over GPUs.
-* ``resample``: local scan -> all-gather of the G shard totals T_s (uint64) -> exclusive offsets
-  O_s and total T.  Two exchange modes:
+* ``predict`` / ``update`` / moments touch local rows only.  The Philox stream is keyed by the GLOBAL row index, so
+  a sharded run draws exactly the noise a single-GPU run of the same seed draws.
+* after ``update`` the local ``(M_s, S_s)`` = (max log-likelihood, sum exp(loglik - M_s)) are all-gathered and merged
+  so that every shard quantises its weights with the same fixed-point scale -- the cumulative weights are integers,
+  hence independent of how the rows are split over GPUs.
+* ``resample`` (``exchange="peer"``, the default): ONE kernel per rank (``gse_resample_fused_sharded``).  Every rank
+  scans its own rows; the shard totals cross NVLink inside the kernel (peer mailboxes); every rank then ranks its rows
+  against the global total and WRITES the global ancestor row of each output it sources straight into the index
+  buffer of the shard that owns the output slot (peer stores); a second mailbox exchange at the end of the kernel
+  makes every index buffer complete when its kernel completes.  The rows themselves move lazily: the next ``predict``
+  / moments kernel pulls row ``idx[i]`` out of whichever GPU holds it.  No NCCL call, no host synchronisation.
+* estimates: every rank reduces its shard to a 48-double moment block; the blocks are all-gathered through the
+  mailboxes and merged on the device (``gse_peer_allgather_moments``), then one 384-byte read-back.
 
-  ``exchange="peer"`` (default on GPUs with peer access): every rank keeps its state and
-  cumulative-weight buffers in IPC-exportable memory and maps every other rank's once.  Each rank
-  then searches the rows of ALL shards for its own output slots and gathers the ancestors'
-  rows, both kernels reading the other GPUs' memory directly over NVLink / NVSwitch
-  (``gse_resample_search_sharded`` / ``gse_gather_rows_sharded``): the compute kernels ARE the
-  communication.  The offsets stay on the device (all-gather + cumsum on the stream), so a step
-  never synchronises the host; the collectives that every step contains anyway order the
-  buffer reuse between ranks.
+  ``exchange="slabs"`` is the host-planned alternative for GPUs without peer access (and the cross-check of the peer
+  path): all-gather of the totals over NCCL -> closed-form output ranges per source shard
+  (``gse_count_outputs_below``) -> two-stage scan / search per range -> grouped NCCL send/recv of contiguous column
+  slabs received in place.  It needs one device-to-host read per resample.
 
-  ``exchange="slabs"``: host-planned.  Shard s is the *source* of the global outputs
-  ``[a_s, b_s)`` whose sample position falls in ``(O_s, O_s + T_s] / T`` (closed form through the
-  device's exact predicate, ``gse_count_outputs_below``); it runs the search + gather for that
-  range, writes the part it owns itself straight into its own state and ships the rest as
-  contiguous column slabs to the owning shards (grouped NCCL send/recv, received in place).
-  Needs one device-to-host read of the G totals per resample; kept for GPUs without peer
-  access and as the cross-check of the peer path.
+Ordering between ranks in peer mode.  Every rank owns two state buffers X (current) and Y and one ancestor-index
+buffer I.  Peers read X (through I) in ``predict`` / moments and write I in ``resample``.  A rank leaves a mailbox
+exchange only after every peer has entered it, and a peer enters it after everything its stream ran before.  Every
+``resample`` contains two exchanges (totals; done) and every ``update`` one (stats), hence: (1) a peer writes this
+rank's I only after the totals exchange of that resample, which this rank enters after its own earlier readers of I
+(predict, moments, gather) have finished; (2) I is complete when the resample kernel completes (the done exchange);
+(3) this rank's X is overwritten by its predict after next, which follows a resample whose exchanges every peer
+only joins once its own predict -- the last reader of X -- has finished.  No sequence of calls (resample -> resample,
+``set_global_weights(); resample()`` repeated, ...) needs an extra barrier.
 
-Ordering between ranks in peer mode (why no extra barrier is needed).  Every rank owns two state
-buffers X (current) and Y.  A step is: predict (reads the peers' X through the pending index, writes
-its own Y; Y becomes current) -> update -> exchange (a) -> scan (writes the local cumulative
-weights) -> exchange (b) -> search (reads the peers' cumulative weights).  A rank leaves an
-exchange only after every peer has written that exchange's flag, and a peer's flag is written by
-a kernel its stream runs after everything it enqueued before.  Hence: (1) the peers' cumulative
-weights are complete before the search reads them (their scan precedes their flag (b));
-(2) the peers' X is final before predict reads it (written one step earlier) and is next
-overwritten by their predict two resamples later, after exchanges that this rank only joins once
-its own predict has finished; (3) a rank's cumulative weights are rewritten by its next scan,
-which follows exchange (a) of the next step, which every peer joins after its search.
-
-``plan_resample`` and ``exchange_columns`` are pure host / ``torch.distributed`` code and run on
-CPU tensors over ``gloo`` as well (tests/test_sharded_cpu.py).
+``plan_resample`` and ``exchange_columns`` are pure host / ``torch.distributed`` code and run on CPU tensors over
+``gloo`` as well (tests/test_sharded_cpu.py).
 """
 import ctypes
 
@@ -52,6 +42,7 @@ import torch
 import torch.distributed as dist
 
 from gpu_se_b200 import _device, _lib
+from gpu_se_b200.filter.gs_ukf import ParallelGaussianSumUnscentedKalmanFilter
 from gpu_se_b200.filter.particle import ParallelParticleFilter
 
 
@@ -148,92 +139,96 @@ def staging_layout(plan, rank, align=64):
     return offs, width
 
 
-class ShardedParticleFilter:
-    """``ParallelParticleFilter`` over all ranks of ``group``: same constructor and
-    ``predict / update / resample / point_estimate / point_covariance`` calls, every rank calling
-    each method collectively with identical arguments.  ``N_particles`` is the GLOBAL count;
-    ``particles`` / ``weights`` are this rank's shard.  "Collectively" includes the ``particles``
-    attribute: reading it applies a pending resample, which flips the state buffers every rank's
-    kernels read, so all ranks must do it at the same point of the call sequence."""
+class _ShardedEnsemble:
+    """A weighted ensemble (particles, or Gaussian components) over all ranks of ``group``: the constructor and the
+    ``predict / update / resample / point_estimate / point_covariance`` calls of the single-GPU class, every rank
+    calling each method collectively with identical arguments.  ``N_particles`` is the GLOBAL count; the state
+    attributes are this rank's shard.  "Collectively" includes reading the state attributes: that applies a pending
+    resample, which flips the state buffers every rank's kernels read, so all ranks must do it at the same point of
+    the call sequence."""
 
-    def __init__(self, f, g, N_particles, x0, state_pdf, measurement_pdf, *, device=None, seed=0, n_sub=1,
-                 group=None, particles=None, exchange="peer"):
+    LOCAL_CLS = None
+
+    def __init__(self, f, g, N_particles, x0, state_pdf, measurement_pdf, *, device=None, seed=0, group=None,
+                 exchange="peer", **local_kw):
         if not dist.is_initialized():
-            raise RuntimeError("ShardedParticleFilter needs an initialised torch.distributed process group")
+            raise RuntimeError("a sharded filter needs an initialised torch.distributed process group")
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.N_particles = int(N_particles)
         if self.N_particles < self.world:
-            raise ValueError("need at least one particle per shard")
+            raise ValueError("need at least one row per shard")
         self.bounds = shard_bounds(self.N_particles, self.world)
         lo, hi = self.bounds[self.rank]
-        local_particles = None
-        if particles is not None:
-            local_particles = _device.to_numpy(particles)[lo:hi]
         if exchange not in ("peer", "slabs"):
             raise ValueError("exchange must be 'peer' or 'slabs'")
         if self.world > _lib.GSE_MAX_SHARDS:
             raise ValueError("at most %d shards" % _lib.GSE_MAX_SHARDS)
         self.exchange = exchange
-        widest = max(b - a for a, b in self.bounds)
-        self.local = ParallelParticleFilter(f, g, hi - lo, x0, state_pdf, measurement_pdf, device=device, seed=seed,
-                                            n_sub=n_sub, particles=local_particles, index0=lo,
-                                            workspace_rows=max(widest, self.N_particles // 4 + 4096),
-                                            peer=(exchange == "peer"))
+        for key in ("particles", "means"):                    # initial state given for the whole population
+            if local_kw.get(key) is not None:
+                local_kw[key] = _device.to_numpy(local_kw[key])[lo:hi]
+        # the fused resample may source every output of the population from this shard (heavy-run queue)
+        self.local = self.LOCAL_CLS(f, g, hi - lo, x0, state_pdf, measurement_pdf, device=device, seed=seed, index0=lo,
+                                    workspace_rows=self.N_particles, peer=(exchange == "peer"), **local_kw)
         self.device = self.local.device
         self._set_uniform()
+        self._pending = False
         if exchange == "peer":
             self._open_peers()
         self.last_plan = None
         self.exchanged_rows = 0
         self._stage_hook = None
-        self._pending = False
+        self._want_cov = False
 
     # -- peer memory -----------------------------------------------------------------------------
     def _open_peers(self):
-        """Exchange the IPC handles of (state, state_alt, cumsum) and map every other rank's buffers."""
+        """Exchange the IPC handles of (state, state_alt, ancestor index, mailbox) and map every other rank's."""
         from gpu_se_b200 import _peer
         loc = self.local
-        if self.N_particles > 2 ** 31 - 1:
+        if self.N_particles > 2 ** 31 - 17:
             raise ValueError("peer exchange indexes global rows with int32")
         self._mailbox = _peer.PeerBuffer(self.device, _lib.GSE_MAILBOX_BYTES)
-        mine = tuple(loc._peer_bufs[k].handle for k in ("state", "state_alt", "cumsum")) + (loc._ld,
-                                                                                               self._mailbox.handle)
+        self._idx_global, self._idx_buf = _peer.peer_zeros(self.device, (_device.round_up(loc.N_particles, 64),),
+                                                           torch.int32)
+        mine = (loc._peer_bufs["state"].handle, loc._peer_bufs["state_alt"].handle, self._idx_buf.handle, loc._ld,
+                self._mailbox.handle)
         everyone = [None] * self.world
         dist.all_gather_object(everyone, mine, group=self.group)
         self._mappings = []
-        self._peer_ptr = []                  # per rank: (state, state_alt, cumsum) device pointers, ld
+        self._peer_ptr = []                  # per rank: (state, state_alt, idx) device pointers, ld
         boxes = (ctypes.c_void_p * _lib.GSE_MAX_SHARDS)()
-        for s, (h0, h1, hc, ld, hm) in enumerate(everyone):
+        for s, (h0, h1, hi_, ld, hm) in enumerate(everyone):
             if s == self.rank:
-                self._peer_ptr.append((loc._peer_bufs["state"].ptr, loc._peer_bufs["state_alt"].ptr,
-                                       loc._peer_bufs["cumsum"].ptr, ld))
+                self._peer_ptr.append((loc._peer_bufs["state"].ptr, loc._peer_bufs["state_alt"].ptr, self._idx_buf.ptr, ld))
                 boxes[s] = self._mailbox.ptr
             else:
-                maps = [_peer.PeerMapping(self.device, h) for h in (h0, h1, hc, hm)]
+                maps = [_peer.PeerMapping(self.device, h) for h in (h0, h1, hi_, hm)]
                 self._mappings += maps
                 self._peer_ptr.append((maps[0].ptr, maps[1].ptr, maps[2].ptr, ld))
                 boxes[s] = maps[3].ptr
         self._boxes = boxes
         self._epoch = 0                      # mailbox exchanges so far: identical on every rank
         self._parity = 0                     # which of (state, state_alt) is current -- flips on every rank together
-        self._offsets = torch.zeros(self.world + 1, dtype=torch.int64, device=self.device)
-        self._totals = torch.zeros(self.world, dtype=torch.int64, device=self.device)
         self._shards = []
         for parity in (0, 1):
             sh = _lib.gse_shards()
             sh.nshards = self.world
             for s, (a, b) in enumerate(self.bounds):
                 sh.rows[s] = a
-                sh.cumsum_dev[s] = self._peer_ptr[s][2]
                 sh.state_dev[s] = self._peer_ptr[s][parity]
+                sh.idx_dev[s] = self._peer_ptr[s][2]
                 sh.ld[s] = self._peer_ptr[s][3]
             sh.rows[self.world] = self.N_particles
-            sh.offsets_dev = self._offsets.data_ptr()
             self._shards.append(sh)
-        self._idx_global = torch.zeros(_device.round_up(loc.N_particles, 64), dtype=torch.int32, device=self.device)
         dist.barrier(group=self.group)
+
+    def _next_epoch(self):
+        """Sequence number of the next mailbox exchange: 1, 2, ..., 0xFFFFFFFE, 1, ... (never 0; the parity of
+        consecutive numbers alternates across the wrap, which the double-buffered slots rely on)."""
+        self._epoch = self._epoch % 0xFFFFFFFE + 1
+        return self._epoch
 
     def close(self):
         """Unmap the other ranks' buffers (collective: every rank must call it before any frees its own)."""
@@ -245,24 +240,15 @@ class ShardedParticleFilter:
             self._mappings = []
             dist.barrier(group=self.group)
 
+    # -- resample --------------------------------------------------------------------------------
     def _resample_peer(self, r, return_index):
         loc = self.local
-        n_loc = loc.N_particles
-        lo, hi = self.bounds[self.rank]
-        loc._scan()                                               # local cumsum, T_s -> _offtot[1]
-        if self._stage_hook is not None:
-            self._stage_hook("scan")
-        # shard totals -> exclusive offsets + global total, on the device: one single-warp kernel that
-        # all-gathers through the peer mailboxes (gse_peer_allgather_totals)
-        self._epoch += 1
-        _lib.check(_lib.lib.gse_peer_allgather_totals(loc._ctx.handle, self._boxes, self.rank, self.world, self._epoch,
-                                                      loc._offtot.data_ptr() + 8, self._offsets.data_ptr(),
-                                                      loc._stream()))
-        if self._stage_hook is not None:
-            self._stage_hook("offsets")
+        ll, base, stats = loc._weight_sources()
+        e1, e2 = self._next_epoch(), self._next_epoch()
         sh = self._shards[self._parity]
-        _lib.check(_lib.lib.gse_resample_search_sharded(loc._ctx.handle, ctypes.byref(sh), r, lo, n_loc,
-                                                        self._idx_global.data_ptr(), loc._stream()))
+        _lib.check(_lib.lib.gse_resample_fused_sharded(loc._ctx.handle, ll, base, stats.data_ptr(), r, ctypes.byref(sh),
+                                                       self._boxes, self.rank, e1, e2, loc._offtot.data_ptr() + 8,
+                                                       loc._stream()))
         # lazy, as on one GPU: the rows move when the next kernel reads them (predict / moments pull them
         # out of the owning shard's memory through the global ancestor index)
         self._pending = True
@@ -271,11 +257,11 @@ class ShardedParticleFilter:
         self._set_uniform()
         loc._touch()
         self.exchanged_rows = None                                # known on the device only: see rows_from_peers()
-        return self._idx_global[:n_loc].to(torch.int64) if return_index else None
+        return self._idx_global[:loc.N_particles].to(torch.int64) if return_index else None
 
     def _materialise(self):
         """Apply a pending sharded resample: pull the ancestors' rows into this shard's other buffer."""
-        if getattr(self, "_pending", False):
+        if self._pending:
             loc = self.local
             sh = self._shards[self._parity]
             _lib.check(_lib.lib.gse_gather_rows_sharded(loc._ctx.handle, ctypes.byref(sh),
@@ -306,11 +292,6 @@ class ShardedParticleFilter:
         loc._stats.copy_(loc._stats_uniform)
 
     @property
-    def particles(self):
-        self._materialise()
-        return self.local.particles
-
-    @property
     def weights(self):
         return self.local.weights
 
@@ -326,14 +307,13 @@ class ShardedParticleFilter:
         self.local._base_max = full.max()
 
     def _allreduce_stats(self):
-        """Global (M, S) from the shards' (M_s, S_s): one all-gather of a pair + one tiny kernel."""
+        """Global (M, S) from the shards' (M_s, S_s): one all-gather of a pair + the merge, one tiny kernel."""
         loc = self.local
         if self.world == 1:
             return
         if self.exchange == "peer":
-            self._epoch += 1
             _lib.check(_lib.lib.gse_peer_allgather_stats(loc._ctx.handle, self._boxes, self.rank, self.world,
-                                                         self._epoch, loc._stats.data_ptr(), loc._stream()))
+                                                         self._next_epoch(), loc._stats.data_ptr(), loc._stream()))
             return
         if not hasattr(self, "_stat_pairs"):
             self._stat_pairs = torch.zeros(2 * self.world, dtype=torch.float64, device=self.device)
@@ -342,29 +322,24 @@ class ShardedParticleFilter:
                                             loc._stats.data_ptr(), loc._stream()))
 
     # -- the three stages ------------------------------------------------------------------------
+    def _predict_pending(self, u, dt, noise_ptr, ld_noise):
+        raise NotImplementedError
+
+    def _noise_rows(self, noise):
+        raise NotImplementedError
+
     def predict(self, u, dt, noise=None):
         lo, hi = self.bounds[self.rank]
         if noise is not None:
             noise = _device.to_numpy(noise)[lo:hi]
-        if not getattr(self, "_pending", False):
+        if not self._pending:
             self.local.predict(u, dt, noise=noise)
             return
         # pending sharded resample: read row idx[i] out of whichever GPU holds it, write the other buffer
         loc = self.local
-        n = loc.N_particles
-        if noise is None:
-            noise = loc._host_noise(loc.state_pdf, n)
-        nz_ptr, ld_nz, nz = None, 0, None
-        if noise is not None:
-            nz = torch.zeros((5, loc._ld), dtype=torch.float32, device=self.device)
-            nz[:, :n].copy_(torch.as_tensor(numpy.ascontiguousarray(_device.to_numpy(noise), dtype=numpy.float32)
-                                            .reshape(n, 5), device=self.device).t())
-            nz_ptr, ld_nz = nz.data_ptr(), loc._ld
-        sh = self._shards[self._parity]
-        _lib.check(_lib.lib.gse_pf_predict_sharded(loc._ctx.handle, ctypes.byref(sh), self._idx_global.data_ptr(),
-                                                   loc._state_alt.data_ptr(), loc._ld, n, _lib.as_double2(u), float(dt),
-                                                   loc._n_sub, loc._seed, loc._step, loc._index0, nz_ptr, ld_nz,
-                                                   loc._stream()))
+        nz_ptr, ld_nz, keep = self._noise_rows(noise)
+        self._predict_pending(u, dt, nz_ptr, ld_nz)
+        del keep
         loc._step += 1
         self._swap()
 
@@ -382,6 +357,8 @@ class ShardedParticleFilter:
                            group=self.group)
             r = float(rt.item())
         r = float(r)
+        if not (0.0 <= r < 1.0):
+            raise ValueError("r must be in [0, 1)")
         if self.exchange == "peer":
             return self._resample_peer(r, return_index)
         n_loc = loc.N_particles
@@ -428,45 +405,61 @@ class ShardedParticleFilter:
         return idx
 
     # -- estimates -------------------------------------------------------------------------------
+    def _launch_local_moments(self, mean_only):
+        raise NotImplementedError
+
     def _global_moments(self, need_cov=True):
+        """(mom, S0, S1, S2, p, A) of the WHOLE population, identical on every rank."""
         loc = self.local
         if need_cov:
             self._want_cov = True
-        mean_only = not (need_cov or getattr(self, "_want_cov", False))
-        if getattr(self, "_pending", False):
-            sh = self._shards[self._parity]
-            _lib.check(_lib.lib.gse_pf_moments_sharded(
-                loc._ctx.handle, ctypes.byref(sh), self._idx_global.data_ptr(), loc.N_particles, loc._loglik_ptr(),
-                loc._base.data_ptr() if loc._base is not None else None, loc._stats.data_ptr(), int(mean_only),
-                loc._mom.data_ptr(), loc._stream()))
+        mean_only = not (need_cov or self._want_cov)
+        self._launch_local_moments(mean_only)
+        if self.exchange == "peer":
+            # the shards' moment blocks cross NVLink inside one single-warp kernel that also merges them
+            if self.world > 1:
+                _lib.check(_lib.lib.gse_peer_allgather_moments(loc._ctx.handle, self._boxes, self.rank, self.world,
+                                                               self._next_epoch(), loc._mom.data_ptr(), loc._stream()))
+            loc._mom[41:43].copy_(loc._stats[0:2])
+            loc._mom_host.copy_(loc._mom, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            loc._ctx.check_device_errors()
+            mom = loc._mom_host.numpy().copy()
+            S0, S1, S2, p = mom[0], mom[1:6].copy(), loc._unpack_sym(mom[6:21]), mom[21:26].copy()
         else:
-            loc._launch_moments(mean_only=mean_only)
-        loc._mom[41:43].copy_(loc._stats[0:2])
-        allm = [torch.empty_like(loc._mom) for _ in range(self.world)]
-        dist.all_gather(allm, loc._mom, group=self.group)
-        mom = torch.stack(allm).cpu().numpy()
-        p = mom[0, 21:26].copy()                                  # common pivot: rank 0's row 0
-        S0, S1, S2 = 0.0, numpy.zeros(5), numpy.zeros((5, 5))
-        for m in mom:
-            s0, s1, s2 = m[0], m[1:6], loc._unpack_sym(m[6:21])
-            d = m[21:26] - p
-            S2 = S2 + s2 + numpy.outer(s1, d) + numpy.outer(d, s1) + s0 * numpy.outer(d, d)
-            S1 = S1 + s1 + s0 * d
-            S0 = S0 + s0
-        A = loc._base_scale * float(numpy.exp(mom[0, 41]))
-        return S0, S1, S2, p, A
+            loc._mom[41:43].copy_(loc._stats[0:2])
+            allm = [torch.empty_like(loc._mom) for _ in range(self.world)]
+            dist.all_gather(allm, loc._mom, group=self.group)
+            moms = torch.stack(allm).cpu().numpy()
+            loc._ctx.check_device_errors()
+            p = moms[0, 21:26].copy()                             # common pivot: rank 0's row 0
+            S0, S1, S2, X = 0.0, numpy.zeros(5), numpy.zeros((5, 5)), numpy.zeros(15)
+            for m in moms:
+                s0, s1, s2 = m[0], m[1:6], loc._unpack_sym(m[6:21])
+                d = m[21:26] - p
+                S2 = S2 + s2 + numpy.outer(s1, d) + numpy.outer(d, s1) + s0 * numpy.outer(d, d)
+                S1 = S1 + s1 + s0 * d
+                S0 = S0 + s0
+                X = X + m[26:41]
+            mom = moms[0].copy()
+            mom[26:41] = X
+        A = loc._base_scale * float(numpy.exp(mom[41]))
+        return mom, S0, S1, S2, p, A
 
     def point_estimate(self, normalised=False):
-        S0, S1, S2, p, A = self._global_moments(need_cov=False)
+        mom, S0, S1, S2, p, A = self._global_moments(need_cov=False)
         return p + S1 / S0 if normalised else A * (S0 * p + S1)
 
-    def covariance_matrix(self, normalised=False):
-        S0, S1, S2, p, A = self._global_moments()
+    def _scatter(self, normalised):
+        mom, S0, S1, S2, p, A = self._global_moments()
         if normalised:
             d = S1 / S0
-            return S2 / S0 - numpy.outer(d, d)
+            return S2 / S0 - numpy.outer(d, d), mom, 1.0 / S0
         d = A * (S0 * p + S1) - p
-        return A * (S2 - numpy.outer(S1, d) - numpy.outer(d, S1) + S0 * numpy.outer(d, d))
+        return A * (S2 - numpy.outer(S1, d) - numpy.outer(d, S1) + S0 * numpy.outer(d, d)), mom, A
+
+    def covariance_matrix(self, normalised=False):
+        return self._scatter(normalised)[0]
 
     def point_covariance(self, normalised=False):
         return float(numpy.linalg.svd(self.covariance_matrix(normalised), compute_uv=False)[0])
@@ -474,3 +467,111 @@ class ShardedParticleFilter:
     @property
     def _ctx(self):
         return self.local._ctx
+
+
+class ShardedParticleFilter(_ShardedEnsemble):
+    """``ParallelParticleFilter`` (filter/particle.py:151-327) over all ranks of ``group``; ``particles`` / ``weights``
+    are this rank's shard."""
+
+    LOCAL_CLS = ParallelParticleFilter
+
+    def __init__(self, f, g, N_particles, x0, state_pdf, measurement_pdf, *, device=None, seed=0, n_sub=1, group=None,
+                 particles=None, exchange="peer"):
+        super().__init__(f, g, N_particles, x0, state_pdf, measurement_pdf, device=device, seed=seed, group=group,
+                         exchange=exchange, n_sub=n_sub, particles=particles)
+
+    @property
+    def particles(self):
+        self._materialise()
+        return self.local.particles
+
+    def _noise_rows(self, noise):
+        loc = self.local
+        n = loc.N_particles
+        if noise is None:
+            noise = loc._host_noise(loc.state_pdf, n)
+        if noise is None:
+            return None, 0, None
+        nz = torch.zeros((5, loc._ld), dtype=torch.float32, device=self.device)
+        nz[:, :n].copy_(torch.as_tensor(numpy.ascontiguousarray(_device.to_numpy(noise), dtype=numpy.float32)
+                                        .reshape(n, 5), device=self.device).t())
+        return nz.data_ptr(), loc._ld, nz
+
+    def _predict_pending(self, u, dt, nz_ptr, ld_nz):
+        loc = self.local
+        sh = self._shards[self._parity]
+        _lib.check(_lib.lib.gse_pf_predict_sharded(loc._ctx.handle, ctypes.byref(sh), self._idx_global.data_ptr(),
+                                                   loc._state_alt.data_ptr(), loc._ld, loc.N_particles,
+                                                   _lib.as_double2(u), float(dt), loc._n_sub, loc._seed, loc._step,
+                                                   loc._index0, nz_ptr, ld_nz, loc._stream()))
+
+    def _launch_local_moments(self, mean_only):
+        loc = self.local
+        if self._pending:
+            sh = self._shards[self._parity]
+            _lib.check(_lib.lib.gse_pf_moments_sharded(
+                loc._ctx.handle, ctypes.byref(sh), self._idx_global.data_ptr(), loc.N_particles, loc._loglik_ptr(),
+                loc._base.data_ptr() if loc._base is not None else None, loc._stats.data_ptr(), int(mean_only),
+                loc._mom.data_ptr(), loc._stream()))
+        else:
+            loc._launch_moments(mean_only=mean_only)
+
+
+class ShardedGaussianSumUnscentedKalmanFilter(_ShardedEnsemble):
+    """``ParallelGaussianSumUnscentedKalmanFilter`` (filter/gs_ukf.py:223-449) over all ranks of ``group``: the Gaussian
+    components shard like particles do (BASELINE.json north_star); a resampled component's mean and covariance (20
+    floats) are pulled from the owning GPU by the next predict.  ``means`` / ``covariances`` are this rank's shard."""
+
+    LOCAL_CLS = ParallelGaussianSumUnscentedKalmanFilter
+
+    def __init__(self, f, g, N_particles, x0, state_pdf, measurement_pdf, *, device=None, seed=0, group=None, means=None,
+                 exchange="peer"):
+        super().__init__(f, g, N_particles, x0, state_pdf, measurement_pdf, device=device, seed=seed, group=group,
+                         exchange=exchange, means=means)
+
+    @property
+    def means(self):
+        self._materialise()
+        return self.local.means
+
+    @property
+    def covariances(self):
+        self._materialise()
+        return self.local.covariances
+
+    def _noise_rows(self, noise):
+        loc = self.local
+        n = loc.N_particles
+        if noise is None:
+            noise = loc._host_noise(loc.state_pdf, (n, 11))
+        if noise is None:
+            return None, 0, None
+        nz = torch.zeros((55, loc._ld), dtype=torch.float32, device=self.device)
+        host = numpy.ascontiguousarray(_device.to_numpy(noise), dtype=numpy.float32).reshape(n, 55)
+        nz[:, :n].copy_(torch.as_tensor(host, device=self.device).t())
+        return nz.data_ptr(), loc._ld, nz
+
+    def _predict_pending(self, u, dt, nz_ptr, ld_nz):
+        loc = self.local
+        sh = self._shards[self._parity]
+        dst = loc._state_alt
+        _lib.check(_lib.lib.gse_gsf_predict_sharded(loc._ctx.handle, ctypes.byref(sh), self._idx_global.data_ptr(),
+                                                    dst.data_ptr(), dst.data_ptr() + 5 * loc._ld * 4, loc._ld,
+                                                    loc.N_particles, _lib.as_double2(u), float(dt), loc._seed, loc._step,
+                                                    loc._index0, nz_ptr, ld_nz, loc._stream()))
+
+    def _launch_local_moments(self, mean_only):
+        loc = self.local
+        if self._pending:
+            sh = self._shards[self._parity]
+            _lib.check(_lib.lib.gse_gsf_moments_sharded(
+                loc._ctx.handle, ctypes.byref(sh), self._idx_global.data_ptr(), loc.N_particles, loc._loglik_ptr(),
+                loc._base.data_ptr() if loc._base is not None else None, loc._stats.data_ptr(), loc._mom.data_ptr(),
+                loc._stream()))
+        else:
+            loc._launch_moments(mean_only=False)
+
+    def covariance_matrix(self, normalised=False):
+        """cov_cov + cov_mean (gs_ukf.py:442-447)."""
+        cov_mean, mom, A = self._scatter(normalised)
+        return A * self.local._unpack_sym(mom[26:41]) + cov_mean

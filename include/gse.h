@@ -263,6 +263,7 @@ typedef struct gse_shards {
     const float* state_dev[GSE_MAX_SHARDS];
     int64_t ld[GSE_MAX_SHARDS];
     const uint64_t* offsets_dev;
+    int32_t* idx_dev[GSE_MAX_SHARDS];    /* shard s's ancestor-index buffer (rows[s+1] - rows[s] entries, rounded up to 4) */
 } gse_shards;
 
 /* gse_resample_search over the rows of ALL shards for the outputs [out0, out0 + n_out) (this
@@ -271,6 +272,16 @@ typedef struct gse_shards {
  * kernel, nothing is staged and the host never synchronises. */
 int gse_resample_search_sharded(gse_ctx* ctx, const gse_shards* shards, double r, int64_t out0,
                                 int64_t n_out, int32_t* idx_out_dev, void* stream);
+
+/* gse_resample_fused for a sharded population: EVERY rank calls it with its own weights; rank `rank` scans its rows
+ * [rows[rank], rows[rank+1]), the shards' totals are exchanged through the peer mailboxes INSIDE the kernel (sequence
+ * number epoch_totals), every rank ranks its rows against the global total and writes the GLOBAL ancestor row of each
+ * output it sources into shards->idx_dev[t] of the shard t that owns the output slot (NVLink stores for t != rank);
+ * a second mailbox exchange (epoch_done) at the end of the kernel makes every rank's index buffer complete when its
+ * kernel completes.  One launch per rank per resample; total_dev receives the global integer total (NULL to skip). */
+int gse_resample_fused_sharded(gse_ctx* ctx, const float* loglik_dev, const double* base_dev, const double* stats_dev,
+                               double r, const gse_shards* shards, void* const mailboxes[GSE_MAX_SHARDS], int rank,
+                               unsigned int epoch_totals, unsigned int epoch_done, uint64_t* total_dev, void* stream);
 
 /* dst[:, i] = state row idx[i] (global) pulled from the owning shard's memory, ncols SoA columns. */
 int gse_gather_rows_sharded(gse_ctx* ctx, const gse_shards* shards, const int32_t* idx_dev,
@@ -284,12 +295,18 @@ int gse_gather_rows_sharded(gse_ctx* ctx, const gse_shards* shards, const int32_
  *   _stats : in/out stats_dev[0..1] = this shard's (M_s, S_s) -> (max_s M_s, sum_s S_s exp(M_s - M))
  *   _totals: total_dev[0] = this shard's total -> offsets_dev[0..nshards] (exclusive prefix, total last)
  * Every rank of the population must enqueue the same exchanges in the same order. */
-#define GSE_MAILBOX_BYTES (2 * GSE_MAX_SHARDS * 64)
+#define GSE_MAILBOX_BYTES (2 * GSE_MAX_SHARDS * 512)
 int gse_peer_allgather_stats(gse_ctx* ctx, void* const mailboxes[GSE_MAX_SHARDS], int rank, int nshards,
                              unsigned int epoch, double* stats_dev, void* stream);
 int gse_peer_allgather_totals(gse_ctx* ctx, void* const mailboxes[GSE_MAX_SHARDS], int rank, int nshards,
                               unsigned int epoch, const uint64_t* total_dev, uint64_t* offsets_dev,
                               void* stream);
+
+/*   _moments: in/out mom_dev[0..47] = this shard's moment block (gse_pf_moments / gse_gsf_moments layout) -> the
+ *             moments of the whole population about shard 0's pivot, merged in shard order: identical on every rank.
+ * The waits are bounded (4 s): a peer that never arrives sets GSE_ERR_PEER_TIMEOUT in the context's error word. */
+int gse_peer_allgather_moments(gse_ctx* ctx, void* const mailboxes[GSE_MAX_SHARDS], int rank, int nshards,
+                               unsigned int epoch, double* mom_dev, void* stream);
 
 /* stats_dev[0..1] = (max_s M_s, sum_s S_s exp(M_s - M)) from the nshards all-gathered pairs
  * pairs_dev[2 s .. 2 s + 1] = (M_s, S_s) written by each shard's update kernel. */
@@ -328,6 +345,15 @@ int gse_gsf_predict(gse_ctx* ctx, const float* mean_src_dev, const float* cov_sr
                     const int32_t* idx_dev, float* mean_dev, float* cov_dev, int64_t ld, int64_t n,
                     const double u[GSE_NU], double dt, uint64_t seed, uint64_t step,
                     int64_t index0, const float* noise_dev, int64_t ld_noise, void* stream);
+
+/* gse_gsf_predict / gse_gsf_moments of a sharded population: component idx[i] (GLOBAL ancestor row) is read out of the
+ * owning shard's (20, ld) state (5 mean rows + 15 covariance rows) through peer memory. */
+int gse_gsf_predict_sharded(gse_ctx* ctx, const gse_shards* shards, const int32_t* idx_dev, float* mean_dev,
+                            float* cov_dev, int64_t ld, int64_t n, const double u[GSE_NU], double dt, uint64_t seed,
+                            uint64_t step, int64_t index0, const float* noise_dev, int64_t ld_noise, void* stream);
+int gse_gsf_moments_sharded(gse_ctx* ctx, const gse_shards* shards, const int32_t* idx_dev, int64_t n,
+                            const float* loglik_dev, const double* base_dev, const double* stats_dev, double* out_dev,
+                            void* stream);
 
 /* update (gs_ukf.py:105-149 / :369-407): sigma points, g, P_xy, P_yy, K, mean/cov update,
  * loglik_i = loglik_in_i + log pdf_meas(z - g(mean_i)) (loglik_in_dev NULL = zeros);

@@ -1,4 +1,4 @@
-"""-m gpu tests of the sharded particle filter (gpu_se_b200/sharded.py) over NCCL.
+"""-m gpu tests of the sharded particle filter and GS-UKF (gpu_se_b200/sharded.py), one process per GPU.
 
 * world size 1 (always runs): the sharded driver must reproduce the single-GPU filter bit for bit.
 * both exchange modes: "peer" (kernels read the other GPUs' memory over NVLink) and "slabs" (NCCL send/recv)
@@ -24,7 +24,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _run_cycles(pf, n_cycles, seed):
+def _run_cycles(pf, n_cycles, seed, set_weights=None):
     rng = numpy.random.default_rng(seed)
     out = []
     from oracle import bioreactor
@@ -41,10 +41,26 @@ def _run_cycles(pf, n_cycles, seed):
         out.append((est_u, pf.point_estimate(), pf.point_covariance()))      # moments through the pending index
     pf.update(u, z)                           # update straight after a resample: the pending gather is applied first
     out.append((pf.point_estimate(normalised=True), pf.point_estimate(), pf.point_covariance()))
+    # sequences without an update in between (nothing but the resamples themselves orders the ranks):
+    # resample -> resample, assigned weights -> resample twice (the reference's pf_run_seq pattern), resample -> predict
+    pf.resample(r=0.11)
+    pf.resample(r=0.93)
+    out.append((pf.point_estimate(normalised=True), pf.point_estimate(), pf.point_covariance()))
+    if set_weights is not None:
+        for k in range(2):
+            set_weights(pf, k)
+            pf.resample(r=0.5 + 0.25 * k)
+        out.append((pf.point_estimate(normalised=True), pf.point_estimate(), pf.point_covariance()))
+    pf.predict(u, 0.5)
     return out
 
 
-def _worker(rank, world, port, n, exchange, q):
+def _global_weights(n, k):
+    w = numpy.random.default_rng(1000 + k).random(n) ** 6
+    return w / w.sum()
+
+
+def _worker(rank, world, port, n, exchange, kind, q):
     try:
         sys.path.insert(0, ROOT)
         sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -57,22 +73,38 @@ def _worker(rank, world, port, n, exchange, q):
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
         import gpu_se_b200 as g
         from gpu_common import make_pdfs
-        from gpu_se_b200.sharded import ShardedParticleFilter
+        from gpu_se_b200.sharded import ShardedGaussianSumUnscentedKalmanFilter, ShardedParticleFilter
         x0, state, meas = make_pdfs(g)
         f, gg = g.Bioreactor.homeostatic_DEs, g.Bioreactor.static_outputs
-        spf = ShardedParticleFilter(f, gg, n, x0, state, meas, device=dev, seed=77, exchange=exchange)
-        got = _run_cycles(spf, 4, seed=3)
+        gsf = kind == "gsf"
+        sharded_cls = ShardedGaussianSumUnscentedKalmanFilter if gsf else ShardedParticleFilter
+        single_cls = g.GaussianSumUnscentedKalmanFilter if gsf else g.ParticleFilter
+        spf = sharded_cls(f, gg, n, x0, state, meas, device=dev, seed=77, exchange=exchange)
+        got = _run_cycles(spf, 4, seed=3, set_weights=lambda p, k: p.set_global_weights(_global_weights(n, k)))
         exchanged = spf.rows_from_peers()
-        parts = [torch.empty((b - a, 5), dtype=torch.float32, device=dev) for a, b in spf.bounds]
+        ncol = 20 if gsf else 5
+        parts = [torch.empty((b - a, ncol), dtype=torch.float32, device=dev) for a, b in spf.bounds]
         for s in range(world):
             if s == rank:
-                parts[s].copy_(spf.particles)
+                if gsf:
+                    spf.means                                    # applies the pending gather
+                    parts[s].copy_(spf.local._state[:, :spf.local.N_particles].t())
+                else:
+                    parts[s].copy_(spf.particles)
             dist.broadcast(parts[s], src=s)
         full = torch.cat(parts).cpu().numpy()
         if rank == 0:
-            pf = g.ParticleFilter(f, gg, n, x0, state, meas, device=dev, seed=77)
-            ref = _run_cycles(pf, 4, seed=3)
-            assert numpy.array_equal(full, pf.particles.get()), "sharded particles differ from the single-GPU run"
+            pf = single_cls(f, gg, n, x0, state, meas, device=dev, seed=77)
+
+            def assign(p, k):
+                p.weights = _global_weights(n, k)
+            ref = _run_cycles(pf, 4, seed=3, set_weights=assign)
+            if gsf:
+                pf.means
+                want = pf._state[:, :n].t().cpu().numpy()
+            else:
+                want = pf.particles.get()
+            assert numpy.array_equal(full, want), "sharded state differs from the single-GPU run"
             # identical rows and weights; only the float64 summation order of the moments differs
             for (a0, a1, a2), (b0, b1, b2) in zip(got, ref):
                 assert numpy.allclose(a0, b0, rtol=1e-10, atol=1e-10)
@@ -86,12 +118,12 @@ def _worker(rank, world, port, n, exchange, q):
         q.put((rank, "fail", traceback.format_exc() + repr(e)))
 
 
-def _launch(world, n, exchange):
+def _launch(world, n, exchange, kind="pf"):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(rank, world, port, n, exchange, q)) for rank in range(world)]
+    procs = [ctx.Process(target=_worker, args=(rank, world, port, n, exchange, kind, q)) for rank in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=300) for _ in procs]
@@ -108,6 +140,11 @@ def test_world1_equals_single_gpu(n, exchange):
     _launch(1, n, exchange)
 
 
+@pytest.mark.parametrize("exchange,n", [("peer", 5000), ("slabs", 5000), ("peer", 70001)])
+def test_world1_gsukf_equals_single_gpu(n, exchange):
+    _launch(1, n, exchange, kind="gsf")
+
+
 @pytest.mark.parametrize("world,exchange,n", [(2, "peer", 8192), (2, "peer", 1000003), (2, "slabs", 8192),
                                               (2, "slabs", 1000003), (4, "peer", 1000003), (4, "slabs", 100003),
                                               (8, "peer", 2000003)])
@@ -117,3 +154,13 @@ def test_worldN_equals_single_gpu(world, n, exchange):
         pytest.skip("needs %d GPUs" % world)
     results = _launch(world, n, exchange)
     assert any(info > 0 for _, _, info in results), "informative measurement: shards must exchange rows"
+
+
+@pytest.mark.parametrize("world,exchange,n", [(2, "peer", 8192), (2, "peer", 200003), (2, "slabs", 8192), (4, "peer", 200003),
+                                              (8, "peer", 400003)])
+def test_worldN_gsukf_equals_single_gpu(world, n, exchange):
+    """BASELINE.json north_star: "particles and Gaussian components shard naturally across the 8 B200s"."""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    _launch(world, n, exchange, kind="gsf")
