@@ -5,12 +5,11 @@ simulation step, update + resample + point_estimate every control period, point_
 point_covariance logged every step -- and its noise / factory definitions (``get_noise``,
 sim_base.py:117-161; ``get_parts``, :10-114) for the parts that are on the state-estimation path.
 
-Out of scope here: the reference's MPC (controller.py, needs OSQP, which is not
-installable in this image) and LinearModel.  The controller is a plug-in: any callable
-``controller(x_estimate, u_previous, y_measured) -> u`` -- the reference's ``MPC.step`` wrapped in
-its deviation-variable conversions fits -- and the default is a small proportional-integral law on
-the glucose output that keeps the loop closed for timing studies.  The plant is the low-nitrogen
-bioreactor (``Bioreactor.homeostatic_DEs``, the regime the filters model) stepped on the host.
+The controller is the reference's linear MPC (controller.py:9-279 with the internal model of sim_base.py:56-87),
+restated in ``gpu_se_b200/controller.py`` with an ADMM solver in place of OSQP (not installable in this image); any
+callable ``controller(x_estimate, u_previous, y_measured) -> u`` can be plugged in instead (``controller="pi"``: a small
+proportional-integral law for timing studies).  The plant is the low-nitrogen bioreactor
+(``Bioreactor.homeostatic_DEs``, the regime the filters model) stepped on the host.
 """
 import time
 
@@ -64,8 +63,8 @@ class HostBioreactor:
 
 
 class GlucosePI:
-    """Stand-in for the reference's MPC: PI law on the measured glucose concentration (mg/L) that
-    trims the glucose feed around its nominal value.  Not a port of controller.py."""
+    """PI law on the measured glucose concentration (mg/L) that trims the glucose feed around its nominal value: a
+    cheap stand-in for the MPC when only the filter is being timed (``controller="pi"``)."""
 
     def __init__(self, setpoint=280.0, kp=2e-4, ki=2e-5, u_nominal=(0.06, 0.2), limits=(0.0, 0.2)):
         self.setpoint, self.kp, self.ki = setpoint, kp, ki
@@ -93,7 +92,12 @@ class Simulation:
         self.dt = self.ts[1]
         self.dt_control, self.dt_predict = dt_control, dt_predict
         self.bioreactor = HostBioreactor()
-        self.K = controller if controller is not None else GlucosePI()
+        if controller is None or controller == "mpc":           # the reference's closed loop (sim_base.py:75-87)
+            from gpu_se_b200.controller import MPCController
+            controller = MPCController(dt_control)
+        elif controller == "pi":
+            controller = GlucosePI()
+        self.K = controller
         self.f = get_filter(N_particles, pf, device, seed)
         self.state_pdf, self.measurement_pdf = get_noise(device, seed + 100)
         self._rng = numpy.random.default_rng(seed)

@@ -7,7 +7,7 @@ import pytest
 @pytest.mark.parametrize("pf,N", [(True, 1 << 14), (False, 1 << 8)])
 def test_closed_loop_tracks_plant(pf, N):
     from gpu_se_b200.sim_base import Simulation
-    sim = Simulation(N, dt_control=0.1, dt_predict=0.1, end_time=20, pf=pf, seed=3).simulate()
+    sim = Simulation(N, dt_control=0.1, dt_predict=0.1, end_time=20, pf=pf, seed=3, controller="pi").simulate()
     assert sim.predict_count == len(sim.ts) - 1 and sim.update_count >= len(sim.ts) - 2
     assert numpy.isfinite(sim.xs_f).all() and numpy.isfinite(sim.covariance_point_size).all()
     err = numpy.abs(sim.ys_f - sim.ys[:, list(sim.OUTPUTS)])[20:]
@@ -18,6 +18,19 @@ def test_closed_loop_tracks_plant(pf, N):
     assert numpy.median(err[:, 0]) < 3.0 and numpy.median(err[:, 1]) < 6.0
     assert sim.utilisation() < 0.05                                             # 6 s control period
     assert sim.performance >= 0.0
+
+
+@pytest.mark.gpu
+def test_closed_loop_with_the_mpc_reaches_the_set_point():
+    """BASELINE.json configs[4] with the reference's controller (host ADMM in place of OSQP): the filter feeds the MPC,
+    every QP is solved, and the fumaric-acid output heads for its 850 mg/L set point (sim_base.py:80)."""
+    from gpu_se_b200.sim_base import Simulation
+    sim = Simulation(1 << 14, dt_control=1.0, dt_predict=0.1, end_time=150, pf=True, seed=5).simulate()
+    assert sim.K.mpc_frac == 1.0 and sim.update_count >= 149
+    y = sim.ys[:, list(sim.OUTPUTS)]
+    assert abs(y[-100:, 0].mean() - 280.0) < 10.0
+    assert y[-1, 1] > y[0, 1] + 50.0                              # started at 611 mg/L, driven upwards
+    assert (sim.us >= -1e-9).all()
 
 
 def test_performance_is_time_weighted_simpson():
