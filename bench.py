@@ -67,6 +67,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="pf", choices=["pf", "gsf"],
                     help="gsf: GS-UKF components/s at 2^--log2n components (BASELINE configs[3]; give --log2n 16)")
+    ap.add_argument("--no-gsf", action="store_true", help="skip the GS-UKF sub-object of the default line")
     ap.add_argument("--graphs", action="store_true", help="CUDA-graph replay of the cycle (launch-bound sizes)")
     ap.add_argument("--sharded", action="store_true",
                     help="use the sharded driver even on one GPU (profiling the peer-memory kernels under ncu)")
@@ -509,11 +510,111 @@ def run_ours(args):
         "clocks": clocks,
         "last_estimate": [float(v) for v in est],
     }
+    if world == 1 and args.workload == "pf" and not args.no_gsf and not args.sharded:
+        line["gsf"] = gsf_block(g, dev, (x0, state, meas), peak, with_cpu=not args.no_cpu_baseline)
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(args.cpu_log2n + 1) if args.workload == "pf" else cpu_baseline_gsf()
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+# algorithmic bytes per Gaussian component and stage: state = 5 means + 15 covariance entries (lower
+# triangle) in float32, lazy resample (the gather of 80 B rides inside predict through the int32 ancestor index)
+GSF_STAGE_BYTES = {"predict": 4 + 80 + 80, "update": 80 + 80 + 4, "resample": 8}
+
+
+def run_gsf(g, dev, pdfs, log2n, steps, warmup, graphs):
+    """GS-UKF predict -> update -> resample at 2^log2n components (BASELINE.json metric "GSF comps/sec", configs[3]):
+    device-timed components/s and, without graphs, the per-stage times."""
+    import torch
+    x0, state, meas = pdfs
+    n = 1 << log2n
+    f, gg = g.Bioreactor.homeostatic_DEs, g.Bioreactor.static_outputs
+    gf = g.GaussianSumUnscentedKalmanFilter(f, gg, n, x0, state, meas, device=dev, seed=4321)
+    if graphs:
+        gf.enable_graphs()
+    us, zs = trajectory(steps + warmup, seed=17)
+    rs = numpy.random.default_rng(3).random(steps + warmup)
+    stream = torch.cuda.current_stream(dev)
+    events = []
+
+    def hook(label):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(stream)
+        events.append((label, ev))
+
+    for k in range(steps + warmup):
+        if k == warmup:
+            torch.cuda.synchronize(dev)
+            launches0 = gf._ctx.launches
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev0.record(stream)
+        rec = k >= warmup and not graphs
+        if rec:
+            hook("start")
+        gf.predict(us[k], DT)
+        if rec:
+            hook("predict")
+        gf.update(us[k], zs[k])
+        if rec:
+            hook("update")
+        gf.resample(r=float(rs[k]))
+        if rec:
+            hook("resample")
+    gf._materialise()
+    ev1 = torch.cuda.Event(enable_timing=True)
+    ev1.record(stream)
+    torch.cuda.synchronize(dev)
+    ms = ev0.elapsed_time(ev1) / steps
+    est = gf.point_estimate()
+    out = {"components": n, "value": n / (ms * 1e-3), "ms_per_step": ms, "steps": steps, "cuda_graphs": bool(graphs),
+           "gpu_launches": int(gf._ctx.launches - launches0), "last_estimate": [float(v) for v in est]}
+    if events:
+        acc, prev = {}, None
+        for label, ev in events:
+            if label != "start" and prev is not None:
+                acc.setdefault(label, []).append(prev.elapsed_time(ev))
+            prev = ev
+        out["stages"] = {k: round(sum(v) / len(v), 4) for k, v in acc.items()}
+    del gf
+    torch.cuda.empty_cache()
+    return out
+
+
+def gsf_block(g, dev, pdfs, peak, with_cpu):
+    """The "gsf" sub-object of the default bench line: BASELINE configs[3] at its top size (2^16 components, CUDA-graph
+    replay: the sweep is launch-bound) and at 2^20 (out of the launch-bound regime) with the roofline of the step."""
+    small = run_gsf(g, dev, pdfs, 16, 300, 20, graphs=True)
+    small_eager = run_gsf(g, dev, pdfs, 16, 100, 10, graphs=False)
+    big = run_gsf(g, dev, pdfs, 20, 60, 10, graphs=False)
+    n = big["components"]
+    st = big.get("stages", {})
+    hbm_ms = {k: GSF_STAGE_BYTES[k] * n / (peak * 1e9) * 1e3 for k in GSF_STAGE_BYTES}
+    # issue-slot floor: warp-instructions per component measured with ncu (profiles/r2_gsf_2p20_ncu.csv) at one
+    # instruction per SM sub-partition and clock: 148 SMs x 4 x 1.965 GHz
+    issue_ms = {k: GSF_WARP_INSTR_PER_COMPONENT[k] * n / (148 * 4 * 1.965e9) * 1e3 for k in GSF_WARP_INSTR_PER_COMPONENT}
+    bound_ms = {k: max(hbm_ms[k], issue_ms.get(k, 0.0)) for k in hbm_ms}
+    block = {"metric": "GSF comps/sec (predict+update+resample)", "unit": "components/s",
+             "config": {"workload": "gsf_openloop predict+update+resample, BioreactorModel, dt=1.0, in-kernel Philox noise",
+                        "sizes": "2^16 components (configs[3] top size; CUDA-graph replay and eager), 2^20 components (eager)"},
+             "2p16_cuda_graphs": small, "2p16_eager": small_eager, "2p20": big,
+             "roofline": {"at": "2^20 components", "bytes_per_component": GSF_STAGE_BYTES,
+                          "hbm_floor_ms": {k: round(v, 4) for k, v in hbm_ms.items()},
+                          "issue_floor_ms": {k: round(v, 4) for k, v in issue_ms.items()},
+                          "warp_instructions_per_component": GSF_WARP_INSTR_PER_COMPONENT,
+                          "bound": {k: ("issue" if issue_ms.get(k, 0.0) > hbm_ms[k] else "hbm") for k in hbm_ms},
+                          "frac_of_bound": {k: round(bound_ms[k] / st[k], 4) for k in bound_ms if k in st},
+                          "step_frac_of_bound": round(sum(bound_ms.values()) / big["ms_per_step"], 4),
+                          "step_frac_of_hbm": round(sum(hbm_ms.values()) / big["ms_per_step"], 4), "peak_gbs": peak}}
+    if with_cpu:
+        block["cpu_baseline"] = cpu_baseline_gsf()
+    return block
+
+
+# warp-instructions executed per component (smsp__inst_executed.sum / components, ncu at 2^20): filled from
+# profiles/r2_gsf_2p20_ncu.csv
+GSF_WARP_INSTR_PER_COMPONENT = {"predict": 84.0, "update": 40.0}
 
 
 def sharded_parity(g, dev, world, rank, n=(1 << 20) + 8):
