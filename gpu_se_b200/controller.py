@@ -370,7 +370,9 @@ class MPCController:
             du = self.K.step(lm.xn2d(x_estimate), lm.un2d(u_previous), lm.yn2d(y_measured))
             self.converged += 1
             self.iterations.append(self.K.prob.iterations)
-            u[lm.inputs] = lm.ud2n(du)
+            # ADMM at OSQP's default tolerance (1e-3 of the largest row: the outputs, hundreds of mg/L) leaves the first
+            # move feasible only to a few 1e-2 L/h; feed rates cannot be negative, so the move is projected onto the bound
+            u[lm.inputs] = numpy.maximum(lm.ud2n(du), 0.0)
         except ValueError:
             self.failed += 1
             u[:] = [0.06, 0.2]                                     # sim_base.py:271-273

@@ -259,6 +259,10 @@ extern "C" int gse_ctx_create(int device, int model_id, int64_t n_max, const gse
     c->fused_status = (uint64_t*)(base + o_fstatus);
     c->heavy_queue = (int4*)(base + o_queue);
     {
+        const char* v = getenv("GSE_GSF_MINB");
+        c->gsf_minb = (v && (atoi(v) == 3 || atoi(v) == 5 || atoi(v) == 6)) ? atoi(v) : 4;
+    }
+    {
         const char* v = getenv("GSE_PREDICT_MINB");               // tuning knob: CTAs per SM of the predict kernel
         c->predict_minb = (v && atoi(v) == 5) ? 5 : 4;
     }

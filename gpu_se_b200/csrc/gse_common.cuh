@@ -109,6 +109,7 @@ struct gse_ctx {
     int4* heavy_queue;        // fused resample: runs of one heavy source handed to the whole grid (start, end, ancestor)
     int heavy_queue_cap;
     int fused_resident[16];   // co-resident CTAs of each k_resample_fused instantiation (0: not queried yet)
+    int gsf_minb;             // CTAs (of 128 threads) per SM the GS-UKF kernels are compiled for (4; GSE_GSF_MINB = 3 / 5 / 6)
     int predict_minb;         // CTAs per SM of the benchmark's predict specialisation (4; GSE_PREDICT_MINB=5: the 48-register build)
     unsigned long long* fused_trace;   // GSE_FUSED_TRACE=1: per-CTA phase time stamps of the last fused resample (debugging)
     int fused_minb;           // CTAs per SM the fused kernel is compiled for (3; GSE_FUSED_MINB=4 to compare)
@@ -249,38 +250,10 @@ __device__ __forceinline__ float box_muller_cos(uint32_t a, uint32_t b) {
     return box_muller_radius(a) * __cosf(th);
 }
 
-// Five state-noise values for row `index` at `step`, subsequence pair (sub, sub+1).
-// Draw layout (restated in oracle/philox.py):
-//   A = philox(index_lo, index_hi, step, 2*sub)    -> (z0, z1) = BM(A.x, A.y), (z2, z3) = BM(A.z, A.w)
-//   B = philox(index_lo, index_hi, step, 2*sub+1)  -> (z4, _ ) = BM(B.x, B.y), component from B.z
+// mixture sample from five standard normals z and the component selector uc: mean[c] + L[c] z
 template <bool DIAG, int ND>      // ND = 0: component count read from the sampler at run time
-__device__ __forceinline__ void draw_mixture5(const MixSampler5& sp, uint64_t index, uint32_t step,
-                                              uint32_t sub, uint32_t k0, uint32_t k1, float out[5]) {
-    const Philox4 A = philox4x32_10((uint32_t)index, (uint32_t)(index >> 32), step, 2u * sub, k0, k1);
-    const Philox4 B = philox4x32_10((uint32_t)index, (uint32_t)(index >> 32), step, 2u * sub + 1u, k0, k1);
-    float z[5];
-    box_muller(A.x, A.y, z[0], z[1]);
-    box_muller(A.z, A.w, z[2], z[3]);
-    z[4] = box_muller_cos(B.x, B.y);
+__device__ __forceinline__ void mix_apply(const MixSampler5& sp, const float z[5], float uc, float out[5]) {
     const int dg[5] = {0, 2, 5, 9, 14};
-    if (ND == 1) {
-#pragma unroll
-        for (int j = 0; j < 5; ++j) {
-            if (DIAG) out[j] = fmaf(sp.L[0][dg[j]], z[j], sp.mean[0][j]);
-        }
-        if (!DIAG) {
-            int t = 0;
-#pragma unroll
-            for (int j = 0; j < 5; ++j) {
-                float acc = sp.mean[0][j];
-#pragma unroll
-                for (int m = 0; m <= j; ++m) acc = fmaf(sp.L[0][t++], z[m], acc);
-                out[j] = acc;
-            }
-        }
-        return;
-    }
-    const float uc = u32_to_unit(B.z);
     if (ND == 2 && DIAG) {
         const bool second = uc > sp.cdf[0];
 #pragma unroll
@@ -289,9 +262,11 @@ __device__ __forceinline__ void draw_mixture5(const MixSampler5& sp, uint64_t in
         return;
     }
     int comp = 0;
+    if (ND != 1) {
 #pragma unroll
-    for (int d = 0; d < GSE_MAX_ND - 1; ++d)
-        comp += (d < sp.nd - 1 && uc > sp.cdf[d]) ? 1 : 0;
+        for (int d = 0; d < GSE_MAX_ND - 1; ++d)
+            comp += ((ND == 0 ? d < sp.nd - 1 : d < ND - 1) && uc > sp.cdf[d]) ? 1 : 0;
+    }
     if (DIAG) {
 #pragma unroll
         for (int j = 0; j < 5; ++j) out[j] = fmaf(sp.L[comp][dg[j]], z[j], sp.mean[comp][j]);
@@ -306,6 +281,56 @@ __device__ __forceinline__ void draw_mixture5(const MixSampler5& sp, uint64_t in
         }
     }
 }
+
+// Five state-noise values for row `index` at `step`, subsequence pair (sub, sub+1).
+// Draw layout (restated in oracle/philox.py):
+//   A = philox(index_lo, index_hi, step, 2*sub)    -> (z0, z1) = BM(A.x, A.y), (z2, z3) = BM(A.z, A.w)
+//   B = philox(index_lo, index_hi, step, 2*sub+1)  -> (z4, _ ) = BM(B.x, B.y), component from B.z
+template <bool DIAG, int ND>      // ND = 0: component count read from the sampler at run time
+__device__ __forceinline__ void draw_mixture5(const MixSampler5& sp, uint64_t index, uint32_t step,
+                                              uint32_t sub, uint32_t k0, uint32_t k1, float out[5]) {
+    const Philox4 A = philox4x32_10((uint32_t)index, (uint32_t)(index >> 32), step, 2u * sub, k0, k1);
+    const Philox4 B = philox4x32_10((uint32_t)index, (uint32_t)(index >> 32), step, 2u * sub + 1u, k0, k1);
+    float z[5];
+    box_muller(A.x, A.y, z[0], z[1]);
+    box_muller(A.z, A.w, z[2], z[3]);
+    z[4] = box_muller_cos(B.x, B.y);
+    mix_apply<DIAG, ND>(sp, z, u32_to_unit(B.z), out);
+}
+
+// State noise of the ELEVEN sigma points of one Gaussian component (GS-UKF predict, gs_ukf.py:99) from 17 Philox calls
+// instead of 22: 55 normals + 11 selectors = 66 of 68 words.
+//   P_j = philox(ctr = (i_lo, i_hi, step, 0x40000000 + j), key),  j = 0..16;  words w[4 j + {0,1,2,3}] = P_j.{x,y,z,w}
+//   (n[2 p], n[2 p + 1]) = BM(w[2 p], w[2 p + 1]),  p = 0..27;  sigma point s takes n[5 s .. 5 s + 4] and selector w[56 + s]
+// Consumed as a stream (four normals and four selector words live at a time); restated in oracle/philox.py
+// (sigma_grouped_normals).
+struct SigmaNoise {
+    float q[4];
+    uint32_t sel[4];
+    uint32_t lo, hi, step, k0, k1;
+    __device__ __forceinline__ SigmaNoise(uint64_t index, uint32_t step_, uint32_t k0_, uint32_t k1_)
+        : lo((uint32_t)index), hi((uint32_t)(index >> 32)), step(step_), k0(k0_), k1(k1_) {}
+    // S = sigma point (compile-time after unrolling)
+    template <bool DIAG, int ND>
+    __device__ __forceinline__ void draw(int S, const MixSampler5& sp, float out[5]) {
+        float z[5];
+#pragma unroll
+        for (int t = 0; t < 5; ++t) {
+            const int k = 5 * S + t;                              // index of the normal in the component's stream
+            if ((k & 3) == 0) {
+                const Philox4 P = philox4x32_10(lo, hi, step, 0x40000000u + (uint32_t)(k >> 2), k0, k1);
+                box_muller(P.x, P.y, q[0], q[1]);
+                box_muller(P.z, P.w, q[2], q[3]);
+            }
+            z[t] = q[k & 3];
+        }
+        if ((S & 3) == 0) {
+            const Philox4 P = philox4x32_10(lo, hi, step, 0x40000000u + 14u + (uint32_t)(S >> 2), k0, k1);
+            sel[0] = P.x; sel[1] = P.y; sel[2] = P.z; sel[3] = P.w;
+        }
+        mix_apply<DIAG, ND>(sp, z, u32_to_unit(sel[S & 3]), out);
+    }
+};
 
 // State noise of FOUR consecutive rows (a group: global rows 4 g .. 4 g + 3) from six Philox calls instead
 // of eight: 20 normals = 10 Box-Muller pairs (words 0..19) and 4 component selectors (words 20..23).
@@ -625,27 +650,43 @@ __device__ __forceinline__ unsigned int ld_status32(const unsigned int* p) {
     return v;
 }
 
-// The shard table arrives as a kernel parameter; indexing a parameter array with a run-time index makes the compiler
-// copy the whole struct to local memory.  Kernels that look shards up copy the table to shared memory once per CTA
-// (call before any early return) and index that.
-__device__ __forceinline__ void stage_shards(GatherShards* s_dst, const GatherShards& src) {
-    const unsigned int* w = reinterpret_cast<const unsigned int*>(&src);
-    unsigned int* d = reinterpret_cast<unsigned int*>(s_dst);
-    for (unsigned int i = threadIdx.x; i < sizeof(GatherShards) / 4; i += blockDim.x) d[i] = w[i];
-    __syncthreads();
-}
-
-__device__ __forceinline__ int shard_of(const GatherShards& g, int64_t k) {
-    int s = 0;
+// The shard table arrives as a kernel parameter.  Indexing a parameter array with a run-time index makes the compiler
+// copy the whole struct to local memory, and staging it in shared memory puts a block barrier in front of every
+// short-lived CTA (measured: +30 us on the 2^24-row predict); so the owner of a row is SELECTED with compile-time
+// indices -- seven predicated moves per field.
+struct ShardRef {
+    const float* state;    // column 0, row 0 of the owning shard's buffer
+    int64_t ld;
+    int64_t row0, row1;    // the shard holds global rows [row0, row1)
+};
+__device__ __forceinline__ ShardRef shard_ref(const GatherShards& g, int64_t k) {
+    ShardRef r;
+    r.state = g.state[0]; r.ld = g.ld[0]; r.row0 = g.seg_row[0]; r.row1 = g.seg_row[1];
 #pragma unroll
-    for (int t = 1; t < GSE_MAX_SHARDS; ++t) s += (t < g.nseg && k >= g.seg_row[t]) ? 1 : 0;
-    return s;
+    for (int t = 1; t < GSE_MAX_SHARDS; ++t) {
+        if (t < g.nseg && k >= g.seg_row[t]) {
+            r.state = g.state[t]; r.ld = g.ld[t]; r.row0 = g.seg_row[t]; r.row1 = g.seg_row[t + 1];
+        }
+    }
+    return r;
 }
 // column 0 of global row k and the leading dimension of the shard that owns it
 __device__ __forceinline__ const float* shard_row(const GatherShards& g, int64_t k, int64_t& ld) {
-    const int s = shard_of(g, k);
-    ld = g.ld[s];
-    return g.state[s] + (k - g.seg_row[s]);
+    const ShardRef r = shard_ref(g, k);
+    ld = r.ld;
+    return r.state + (k - r.row0);
+}
+
+// four rows with non-decreasing global indices: one look-up serves all four unless they straddle a shard boundary
+__device__ __forceinline__ void shard_rows4(const GatherShards& g, const int id[4], const float* q[4], int64_t l[4]) {
+    const ShardRef own = shard_ref(g, id[0]);
+    if (id[3] < own.row1) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { q[r] = own.state + (id[r] - own.row0); l[r] = own.ld; }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) q[r] = shard_row(g, id[r], l[r]);
+    }
 }
 
 // streaming 128-bit accesses for touch-once columns

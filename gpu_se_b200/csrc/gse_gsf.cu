@@ -126,16 +126,14 @@ extern "C" int gse_gsf_sigma_points(gse_ctx* ctx, const float* mean_dev, const f
 // ------------------------------------------------------------------------------------------------
 // SHARDED: idx holds GLOBAL ancestor rows of a multi-GPU population; the (20, ld) state of the owning shard is read
 // through peer memory (rows 0-4 the mean, 5-19 the covariance triangle)
-template <bool DIAG, bool HOST_NOISE, bool SHARDED>
-__global__ void __launch_bounds__(GSF_THREADS)
+template <bool DIAG, bool HOST_NOISE, bool SHARDED, int ND, int MINB>
+__global__ void __launch_bounds__(GSF_THREADS, MINB)
 k_gsf_predict(const float* mean_src, const float* cov_src, int64_t lds, const int32_t* __restrict__ idx,
               const __grid_constant__ GatherShards shards_arg, float* mean, float* cov, int64_t ld, int64_t n, ModelInputs in_arg,
               const __grid_constant__ MixSampler5 sp, uint32_t k0, uint32_t k1, uint32_t step, int64_t index0,
               const float* __restrict__ noise, int64_t ldn, const gse_step_params* __restrict__ params,
               unsigned int* err) {
-    __shared__ GatherShards s_shards;
-    if (SHARDED) stage_shards(&s_shards, shards_arg);
-    const GatherShards& shards = SHARDED ? s_shards : shards_arg;
+    const GatherShards& shards = shards_arg;
     const int64_t i = (int64_t)blockIdx.x * GSF_THREADS + threadIdx.x;
     if (i >= n) return;
     const ModelInputs in = model_inputs(in_arg, params, 1);
@@ -159,6 +157,7 @@ k_gsf_predict(const float* mean_src, const float* cov_src, int64_t lds, const in
 
     float sg[GSE_NSIGMA][5];
     double msum[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    SigmaNoise stream((uint64_t)(index0 + i), step, k0, k1);
 #pragma unroll
     for (int s = 0; s < GSE_NSIGMA; ++s) {
         float x[5], d[5], e[5];
@@ -168,7 +167,7 @@ k_gsf_predict(const float* mean_src, const float* cov_src, int64_t lds, const in
 #pragma unroll
             for (int j = 0; j < 5; ++j) e[j] = noise[(s * 5 + j) * ldn + i];
         } else {
-            draw_mixture5<DIAG, 0>(sp, (uint64_t)(index0 + i), step, (uint32_t)s, k0, k1, e);   // :99
+            stream.template draw<DIAG, ND>(s, sp, e);                // an independent draw per sigma point  (:99)
         }
         const double w = (double)(s == 0 ? W_SIGMA_0 : W_SIGMA_I);
 #pragma unroll
@@ -224,20 +223,27 @@ static int launch_gsf_predict(gse_ctx* ctx, const float* mean_src_dev, const flo
     GatherShards none;
     memset(&none, 0, sizeof(none));
     const GatherShards& sh = shards ? *shards : none;
-#define LAUNCH_G1(DIAG, HOST, SH)                                                                                   \
-    k_gsf_predict<DIAG, HOST, SH><<<blocks, GSF_THREADS, 0, s>>>(mean_src_dev, cov_src_dev, ld_src, idx_dev, sh, mean_dev, \
-                                                                 cov_dev, ld, n, in, ctx->state_sampler, k0, k1,     \
-                                                                 (uint32_t)step, index0, noise_dev, ld_noise,       \
-                                                                 ctx->step_params, ctx->err_dev)
+#define LAUNCH_G1M(DIAG, HOST, SH, ND, MB)                                                                          \
+    k_gsf_predict<DIAG, HOST, SH, ND, MB><<<blocks, GSF_THREADS, 0, s>>>(mean_src_dev, cov_src_dev, ld_src, idx_dev, sh, \
+                                                                         mean_dev, cov_dev, ld, n, in, ctx->state_sampler, \
+                                                                         k0, k1, (uint32_t)step, index0, noise_dev,      \
+                                                                         ld_noise, ctx->step_params, ctx->err_dev)
+#define LAUNCH_G1(DIAG, HOST, SH) LAUNCH_G1M(DIAG, HOST, SH, 0, 4)
     if (shards) {
         if (noise_dev) LAUNCH_G1(true, true, true);
         else if (ctx->state_sampler.diag) LAUNCH_G1(true, false, true);
         else LAUNCH_G1(false, false, true);
     } else {
         if (noise_dev) LAUNCH_G1(true, true, false);
-        else if (ctx->state_sampler.diag) LAUNCH_G1(true, false, false);
+        else if (ctx->state_sampler.diag && ctx->state_sampler.nd == 2) {       // the benchmark's noise; GSE_GSF_MINB tunes
+            if (ctx->gsf_minb == 5) LAUNCH_G1M(true, false, false, 2, 5);
+            else if (ctx->gsf_minb == 6) LAUNCH_G1M(true, false, false, 2, 6);
+            else if (ctx->gsf_minb == 3) LAUNCH_G1M(true, false, false, 2, 3);
+            else LAUNCH_G1M(true, false, false, 2, 4);
+        } else if (ctx->state_sampler.diag) LAUNCH_G1(true, false, false);
         else LAUNCH_G1(false, false, false);
     }
+#undef LAUNCH_G1M
 #undef LAUNCH_G1
     GSE_CHECK_LAUNCH(ctx);
     return GSE_OK;
@@ -270,7 +276,8 @@ extern "C" int gse_gsf_predict_sharded(gse_ctx* ctx, const gse_shards* shards, c
 // G2: update (gs_ukf.py:105-149).  The reference evaluates this stage in float64 (etas is a
 // float64 array, :118), so the Kalman algebra here is float64 too; storage stays float32.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(GSF_THREADS)
+template <int MINB>
+__global__ void __launch_bounds__(GSF_THREADS, MINB)
 k_gsf_update(float* __restrict__ mean, float* __restrict__ cov, int64_t ld, int64_t n, const float* loglik_in,
              float* loglik, double z0, double z1, const __grid_constant__ MixDensity2 md, float* block_max, float* block_sum,
              unsigned int* ticket, double* stats, const gse_step_params* __restrict__ params, unsigned int* err) {
@@ -286,40 +293,55 @@ k_gsf_update(float* __restrict__ mean, float* __restrict__ cov, int64_t ld, int6
         for (int j = 0; j < 15; ++j) P[j] = cov[j * ld + i];
         cholesky5_retry(P, L, err);
         constexpr double inv_wsum = 1.0 / ((double)W_SIGMA_0 + 10.0 * (double)W_SIGMA_I);
-        // pass 1: eta mean (:126)
-        double eta[GSE_NSIGMA][2];
-        double em0 = 0.0, em1 = 0.0;
+        constexpr double w0 = (double)W_SIGMA_0, wi = (double)W_SIGMA_I;
+        // The sigma points are m and m +- L[:, j] (float32 adds, :76-78) and g reads rows 0 and 2 only (:251-253), so
+        // most of the 11 x (5 + 2) values the reference forms coincide or vanish:
+        //   eta[0] differs from g(m)[0] only for column 0 (L is lower triangular), eta[1] only for columns 0, 1, 2;
+        //   sigma - m is zero above the diagonal: 15 non-zero deviations per sign instead of 55.
+        // Every value that IS formed is the reference's (float32 sigma point, float32 output, float64 from there on).
+        const double g0 = (double)output_glucose(m[0]), g1 = (double)output_fa(m[2]);                 // eta of sigma point 0
+        const double g0p = (double)output_glucose(__fadd_rn(m[0], L[tri(0, 0)]));
+        const double g0m = (double)output_glucose(__fadd_rn(m[0], -L[tri(0, 0)]));
+        double g1p[3], g1m[3];
 #pragma unroll
-        for (int s = 0; s < GSE_NSIGMA; ++s) {
-            float x[5];
-            sigma_point(m, L, s, x);
-            eta[s][0] = (double)output_glucose(x[0]);                 // :118-123
-            eta[s][1] = (double)output_fa(x[2]);
-            const double w = (double)(s == 0 ? W_SIGMA_0 : W_SIGMA_I);
-            em0 = fma(w, eta[s][0], em0);
-            em1 = fma(w, eta[s][1], em1);
+        for (int j = 0; j < 3; ++j) {
+            g1p[j] = (double)output_fa(__fadd_rn(m[2], L[tri(2, j)]));
+            g1m[j] = (double)output_fa(__fadd_rn(m[2], -L[tri(2, j)]));
         }
+        // eta mean (:126): numpy.average over the 11 points
+        double em0 = fma(wi, (g0p + g0m) + 8.0 * g0, w0 * g0);
+        double em1 = fma(wi, ((g1p[0] + g1m[0]) + (g1p[1] + g1m[1])) + ((g1p[2] + g1m[2]) + 4.0 * g1), w0 * g1);
         em0 *= inv_wsum;
         em1 *= inv_wsum;
-        // pass 2: P_xy (5x2), P_yy (2x2)  (:127-131)
-        double pxy[5][2], pyy00 = 0.0, pyy01 = 0.0, pyy11 = 0.0;
+        // deviations of the outputs (:128)
+        const double d0 = g0 - em0, d0p = g0p - em0, d0m = g0m - em0;
+        const double d1 = g1 - em1;
+        double d1p[3], d1m[3];
 #pragma unroll
-        for (int a = 0; a < 5; ++a) { pxy[a][0] = 0.0; pxy[a][1] = 0.0; }
+        for (int j = 0; j < 3; ++j) { d1p[j] = g1p[j] - em1; d1m[j] = g1m[j] - em1; }
+        // P_yy (:130-131)
+        double pyy00 = fma(wi, fma(d0p, d0p, d0m * d0m), (w0 + 8.0 * wi) * (d0 * d0));
+        double pyy11 = (w0 + 4.0 * wi) * (d1 * d1);
+        double pyy01 = fma(wi, fma(d0p, d1p[0], d0m * d1m[0]), (w0 + 4.0 * wi) * (d0 * d1));
 #pragma unroll
-        for (int s = 0; s < GSE_NSIGMA; ++s) {
-            float x[5];
-            sigma_point(m, L, s, x);
-            const double w = (double)(s == 0 ? W_SIGMA_0 : W_SIGMA_I);
-            const double d0 = eta[s][0] - em0, d1 = eta[s][1] - em1;
-            pyy00 = fma(w * d0, d0, pyy00);
-            pyy01 = fma(w * d0, d1, pyy01);
-            pyy11 = fma(w * d1, d1, pyy11);
+        for (int j = 0; j < 3; ++j) pyy11 = fma(wi, fma(d1p[j], d1p[j], d1m[j] * d1m[j]), pyy11);
+        pyy01 = fma(wi * d0, (d1p[1] + d1m[1]) + (d1p[2] + d1m[2]), pyy01);
+        // P_xy (:127-129): row a collects the columns j <= a
+        double pxy[5][2];
 #pragma unroll
-            for (int a = 0; a < 5; ++a) {
-                const double ds = (double)__fsub_rn(x[a], m[a]);        // sigmas -= means  (:127)
-                pxy[a][0] = fma(w * ds, d0, pxy[a][0]);
-                pxy[a][1] = fma(w * ds, d1, pxy[a][1]);
+        for (int a = 0; a < 5; ++a) {
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int j = 0; j <= a; ++j) {
+                const double dsp = (double)__fsub_rn(__fadd_rn(m[a], L[tri(a, j)]), m[a]);      // sigmas -= means  (:127)
+                const double dsm = (double)__fsub_rn(__fadd_rn(m[a], -L[tri(a, j)]), m[a]);
+                const double e0p = j == 0 ? d0p : d0, e0m = j == 0 ? d0m : d0;
+                const double e1p = j < 3 ? d1p[j < 3 ? j : 0] : d1, e1m = j < 3 ? d1m[j < 3 ? j : 0] : d1;
+                s0 = fma(dsp, e0p, fma(dsm, e0m, s0));
+                s1 = fma(dsp, e1p, fma(dsm, e1m, s1));
             }
+            pxy[a][0] = wi * s0;
+            pxy[a][1] = wi * s1;
         }
         // K = P_xy pinv(P_yy) (:132-133).  P_yy is symmetric positive semi-definite 2x2: closed-form inverse; when its
         // smaller eigenvalue is below numpy.linalg.pinv's cut-off (1e-15 of the larger) the pseudo-inverse of the
@@ -360,9 +382,9 @@ k_gsf_update(float* __restrict__ mean, float* __restrict__ cov, int64_t ld, int6
 #pragma unroll
         for (int j = 0; j < 15; ++j) cov[j * ld + i] = P[j];
         // global update: weights *= pdf(z - g(mean))  (:141-149)
-        const double g0 = z0 - (double)output_glucose(mn[0]);
-        const double g1 = z1 - (double)output_fa(mn[2]);
-        vals[0] = (float)((loglik_in ? (double)loglik_in[i] : 0.0) + meas_logpdf(md, g0, g1));
+        const double ge0 = z0 - (double)output_glucose(mn[0]);
+        const double ge1 = z1 - (double)output_fa(mn[2]);
+        vals[0] = (float)((loglik_in ? (double)loglik_in[i] : 0.0) + meas_logpdf(md, ge0, ge1));
         valid[0] = true;
         loglik[i] = vals[0];
     }
@@ -378,9 +400,16 @@ extern "C" int gse_gsf_update(gse_ctx* ctx, float* mean_dev, float* cov_dev, int
     (void)u;
     const unsigned blocks = (unsigned)gse_div_up(n, GSF_THREADS);
     GSE_REQUIRE((int64_t)blocks <= ctx->max_blocks, "workspace too small");
-    k_gsf_update<<<blocks, GSF_THREADS, 0, (cudaStream_t)stream>>>(mean_dev, cov_dev, ld, n, loglik_in_dev, loglik_dev, z[0], z[1],
-                                                                   ctx->meas_density, ctx->block_max, ctx->block_sum,
-                                                                   ctx->ticket, stats_dev, ctx->step_params, ctx->err_dev);
+#define LAUNCH_G2(MB)                                                                                              \
+    k_gsf_update<MB><<<blocks, GSF_THREADS, 0, (cudaStream_t)stream>>>(mean_dev, cov_dev, ld, n, loglik_in_dev, loglik_dev, \
+                                                                       z[0], z[1], ctx->meas_density, ctx->block_max,      \
+                                                                       ctx->block_sum, ctx->ticket, stats_dev,             \
+                                                                       ctx->step_params, ctx->err_dev)
+    if (ctx->gsf_minb == 5) LAUNCH_G2(5);
+    else if (ctx->gsf_minb == 6) LAUNCH_G2(6);
+    else if (ctx->gsf_minb == 3) LAUNCH_G2(3);
+    else LAUNCH_G2(4);
+#undef LAUNCH_G2
     GSE_CHECK_LAUNCH(ctx);
     return GSE_OK;
 }

@@ -75,9 +75,7 @@ k_pf_predict(const float* xs, int64_t lds, const int32_t* __restrict__ idx, cons
              ModelInputs in_arg, int n_sub, const __grid_constant__ MixSampler5 sp, uint32_t k0, uint32_t k1,
              uint32_t step, int64_t index0, const float* __restrict__ noise, int64_t ldn,
              const gse_step_params* __restrict__ params) {
-    __shared__ GatherShards s_shards;
-    if (GMODE == 2) stage_shards(&s_shards, shards_arg);
-    const GatherShards& shards = GMODE == 2 ? s_shards : shards_arg;
+    const GatherShards& shards = shards_arg;
     const int64_t g = (int64_t)blockIdx.x * PF_THREADS + threadIdx.x;
     const int64_t row0 = g * ROWS_PER_THREAD;
     if (row0 >= n) return;
@@ -90,10 +88,10 @@ k_pf_predict(const float* xs, int64_t lds, const int32_t* __restrict__ idx, cons
                            (row0 + 3 < n) ? id4.w : id4.x};
         // idx is non-decreasing: when the first and the last ancestor sit in one shard (all but a
         // handful of threads) one look-up serves the four rows
-        const int s0 = shard_of(shards, id[0]);
-        if (id[3] < shards.seg_row[s0 + 1]) {
-            const int64_t ld0 = shards.ld[s0];
-            const float* base = shards.state[s0] - shards.seg_row[s0];
+        const ShardRef own = shard_ref(shards, id[0]);
+        if (id[3] < own.row1) {
+            const int64_t ld0 = own.ld;
+            const float* base = own.state - own.row0;
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
 #pragma unroll
@@ -561,9 +559,7 @@ k_moments(const float* __restrict__ x, const float* __restrict__ extra, int64_t 
           const int32_t* __restrict__ idx, const __grid_constant__ GatherShards shards_arg,
           const float* __restrict__ loglik, const double* __restrict__ base,
           const double* __restrict__ stats, double* partials, unsigned int* ticket, double* out) {
-    __shared__ GatherShards s_shards;
-    if (GMODE == 2) stage_shards(&s_shards, shards_arg);
-    const GatherShards& shards = GMODE == 2 ? s_shards : shards_arg;
+    const GatherShards& shards = shards_arg;
     constexpr bool MEAN = NEXTRA < 0;
     constexpr int NV = MEAN ? 6 : 21 + NEXTRA;
     const float M = (float)stats[0];
@@ -593,8 +589,7 @@ k_moments(const float* __restrict__ x, const float* __restrict__ extra, int64_t 
             id[0] = id4.x; id[1] = (row0 + 1 < n) ? id4.y : id4.x; id[2] = (row0 + 2 < n) ? id4.z : id4.x;
             id[3] = (row0 + 3 < n) ? id4.w : id4.x;
             if (GMODE == 2) {
-#pragma unroll
-                for (int r = 0; r < 4; ++r) qs[r] = shard_row(shards, id[r], ls[r]);
+                shard_rows4(shards, id, qs, ls);
 #pragma unroll
                 for (int j = 0; j < 5; ++j)
                     c[j] = make_float4(qs[0][j * ls[0]], qs[1][j * ls[1]], qs[2][j * ls[2]], qs[3][j * ls[3]]);
@@ -680,13 +675,11 @@ k_moments(const float* __restrict__ x, const float* __restrict__ extra, int64_t 
 // float64 summation order.
 // ------------------------------------------------------------------------------------------------
 template <int GMODE>
-__global__ void __launch_bounds__(MOM_THREADS)
+__global__ void __launch_bounds__(MOM_THREADS, GMODE == 2 ? 3 : 4)
 k_means(const float* __restrict__ x, int64_t ld, int64_t n, const int32_t* __restrict__ idx,
         const __grid_constant__ GatherShards shards_arg, const float* __restrict__ loglik,
         const double* __restrict__ stats, double* partials, unsigned int* ticket, double* out) {
-    __shared__ GatherShards s_shards;
-    if (GMODE == 2) stage_shards(&s_shards, shards_arg);
-    const GatherShards& shards = GMODE == 2 ? s_shards : shards_arg;
+    const GatherShards& shards = shards_arg;
     constexpr int NV = 6;
     const float M = (float)stats[0];
     double acc[NV];
@@ -701,13 +694,11 @@ k_means(const float* __restrict__ x, int64_t ld, int64_t n, const int32_t* __res
             const int id[4] = {id4.x, (row0 + 1 < n) ? id4.y : id4.x, (row0 + 2 < n) ? id4.z : id4.x,
                                (row0 + 3 < n) ? id4.w : id4.x};
             if (GMODE == 2) {
-                int64_t l0, l1, l2, l3;
-                const float* q0 = shard_row(shards, id[0], l0);
-                const float* q1 = shard_row(shards, id[1], l1);
-                const float* q2 = shard_row(shards, id[2], l2);
-                const float* q3 = shard_row(shards, id[3], l3);
+                const float* q[4];
+                int64_t l[4];
+                shard_rows4(shards, id, q, l);
 #pragma unroll
-                for (int j = 0; j < 5; ++j) c[j] = make_float4(q0[j * l0], q1[j * l1], q2[j * l2], q3[j * l3]);
+                for (int j = 0; j < 5; ++j) c[j] = make_float4(q[0][j * l[0]], q[1][j * l[1]], q[2][j * l[2]], q[3][j * l[3]]);
             } else {
 #pragma unroll
                 for (int j = 0; j < 5; ++j) {

@@ -863,20 +863,18 @@ template <bool VEC>
 __global__ void __launch_bounds__(GR_THREADS)
 k_gather_rows_sharded(const __grid_constant__ GatherShards g_arg, const int32_t* __restrict__ idx, int64_t n_out,
                       float* __restrict__ dst, int64_t ld_dst, int ncols) {
-    __shared__ GatherShards g;
-    stage_shards(&g, g_arg);
+    const GatherShards& g = g_arg;
     if (VEC) {
         const int64_t row0 = ((int64_t)blockIdx.x * GR_THREADS + threadIdx.x) * 4;
         if (row0 >= n_out) return;
         if (row0 + 4 <= n_out) {
-            const int4 id = *reinterpret_cast<const int4*>(idx + row0);
-            int64_t l0, l1, l2, l3;
-            const float* p0 = shard_row(g, id.x, l0);
-            const float* p1 = shard_row(g, id.y, l1);
-            const float* p2 = shard_row(g, id.z, l2);
-            const float* p3 = shard_row(g, id.w, l3);
+            const int4 id4 = *reinterpret_cast<const int4*>(idx + row0);
+            const int id[4] = {id4.x, id4.y, id4.z, id4.w};
+            const float* p[4];
+            int64_t l[4];
+            shard_rows4(g, id, p, l);
             for (int c = 0; c < ncols; ++c)
-                st_stream4(dst + c * ld_dst + row0, make_float4(p0[c * l0], p1[c * l1], p2[c * l2], p3[c * l3]));
+                st_stream4(dst + c * ld_dst + row0, make_float4(p[0][c * l[0]], p[1][c * l[1]], p[2][c * l[2]], p[3][c * l[3]]));
             return;
         }
         for (int64_t i = row0; i < n_out; ++i) {

@@ -90,6 +90,31 @@ def grouped_normals5(index, step, seed):
     return normals, u32_to_unit(w[rows, 20 + lane])
 
 
+def sigma_grouped_normals(index, step, seed):
+    """(n, 11, 5) float64 standard normals and (n, 11) float32 component uniforms of the layout the GS-UKF predict kernel
+    uses for the eleven sigma points of component ``index`` (csrc/gse_common.cuh: SigmaNoise): 17 Philox calls
+    P_j = philox(ctr=(i_lo, i_hi, step, 0x40000000 + j)), j = 0..16; words w[4j..4j+3] = P_j; normals
+    (n[2p], n[2p+1]) = BM(w[2p], w[2p+1]) for p = 0..27; sigma point s takes n[5s..5s+4] and the selector word w[56 + s]."""
+    index = numpy.asarray(index, dtype=numpy.uint64)
+    lo, hi = index & MASK, index >> numpy.uint64(32)
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    words = []
+    for j in range(17):
+        words += list(philox4x32_10(lo, hi, numpy.uint64(step & 0xFFFFFFFF), numpy.uint64(0x40000000 + j), k0, k1))
+    w = numpy.stack(words, axis=-1)                                   # (n, 68)
+    z = numpy.empty((len(index), 56))
+    for p in range(28):
+        z[:, 2 * p], z[:, 2 * p + 1] = box_muller(w[:, 2 * p], w[:, 2 * p + 1])
+    return z[:, :55].reshape(len(index), 11, 5), u32_to_unit(w[:, 56:67])
+
+
+def draw_mixture5_sigma(means, covariances, weights, index, step, seed):
+    """(n, 11, 5) float64 state-noise samples of the GS-UKF predict kernel (one independent draw per sigma point)."""
+    z, uc = sigma_grouped_normals(index, step, seed)
+    out = [_mix(means, covariances, weights, z[:, s, :], uc[:, s])[0] for s in range(11)]
+    return numpy.stack(out, axis=1)
+
+
 def draw_mixture5_grouped(means, covariances, weights, index, step, seed):
     """As draw_mixture5, with the grouped layout of the predict kernel."""
     return _mix(means, covariances, weights, *grouped_normals5(index, step, seed))

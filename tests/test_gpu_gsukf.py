@@ -127,7 +127,7 @@ def test_same_cpu_gpu_like_the_reference_test(g, noise_pdfs):
 
 
 def test_philox_sigma_noise_matches_specification(g):
-    """Every sigma point gets an independent draw keyed by (index, step, sigma) (gs_ukf.py:99)."""
+    """Every sigma point gets an independent draw from the component's (index, step) stream (gs_ukf.py:99)."""
     N = 512
     seed = 77
     gf = make_gsf(g, N, seed=seed)
@@ -137,8 +137,7 @@ def test_philox_sigma_noise_matches_specification(g):
     gf.predict(u, 0.1)
     from oracle import bioreactor
     stepped = (sig.astype(numpy.float64) + bioreactor.increment(sig, u, 0.1)).astype(numpy.float32).astype(numpy.float64)
-    noise = numpy.stack([philox.draw_mixture5(mixture.STATE_MEANS, mixture.STATE_COVS, mixture.STATE_WEIGHTS,
-                                              numpy.arange(N), 0, s, seed)[0] for s in range(11)], axis=1)
+    noise = philox.draw_mixture5_sigma(mixture.STATE_MEANS, mixture.STATE_COVS, mixture.STATE_WEIGHTS, numpy.arange(N), 0, seed)
     sg = (stepped + noise).astype(numpy.float32).astype(numpy.float64)
     w = gs_ukf.sigma_weights().astype(numpy.float64)
     mean = numpy.einsum("nsj,s->nj", sg, w) / w.sum()

@@ -21,6 +21,10 @@ import torch  # noqa: E402
 import bench  # noqa: E402  (trajectory, peak)
 
 
+PF_STEP_BYTES = bench.STAGE_BYTES["predict"] + bench.STAGE_BYTES["update"] + bench.STAGE_BYTES["resample"]     # 64 B
+GSF_STEP_BYTES = sum(bench.GSF_STAGE_BYTES.values())                                                            # 336 B
+
+
 def build(kind, n, dev):
     import gpu_se_b200 as g
     from gpu_se_b200.model.BioreactorModel import X_STEADY
@@ -84,10 +88,10 @@ def main():
     torch.cuda.set_device(dev)
     peak, src = bench.measured_peak_gbs()
     res = {"hbm_peak_gbs": peak, "peak_source": src, "runs": a.runs, "dt": 1.0, "pf": [], "gsf": [], "cuda_graphs": a.graphs,
-           "pf_bytes_per_particle_step": bench.STEP_BYTES, "gsf_bytes_per_comp_step": 80 + 80 + 84 + 84 + 12 + 12 + 4}
+           "pf_bytes_per_particle_step": PF_STEP_BYTES, "gsf_bytes_per_comp_step": GSF_STEP_BYTES}
     for p in range(10, a.pf_max + 1, 2):
         r = time_filter("pf", 1 << p, a.runs, dev, 1.0, a.graphs)
-        r["hbm_frac"] = bench.STEP_BYTES * r["N"] / (r["step_ms_median"] * 1e-3) / 1e9 / peak
+        r["hbm_frac"] = PF_STEP_BYTES * r["N"] / (r["step_ms_median"] * 1e-3) / 1e9 / peak
         res["pf"].append(r)
         print(json.dumps(r), flush=True)
     for p in list(range(8, min(a.gsf_max, 16) + 1, 2)) + ([18, 20] if a.gsf_max >= 20 else []):
