@@ -260,7 +260,7 @@ extern "C" int gse_ctx_create(int device, int model_id, int64_t n_max, const gse
     c->heavy_queue = (int4*)(base + o_queue);
     {
         const char* v = getenv("GSE_GSF_MINB");
-        c->gsf_minb = (v && (atoi(v) == 3 || atoi(v) == 5 || atoi(v) == 6)) ? atoi(v) : 4;
+        c->gsf_minb = (v && (atoi(v) == 3 || atoi(v) == 4 || atoi(v) == 5 || atoi(v) == 6)) ? atoi(v) : 0;    // 0: per-kernel defaults
     }
     {
         const char* v = getenv("GSE_PREDICT_MINB");               // tuning knob: CTAs per SM of the predict kernel

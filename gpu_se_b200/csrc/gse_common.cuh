@@ -109,7 +109,7 @@ struct gse_ctx {
     int4* heavy_queue;        // fused resample: runs of one heavy source handed to the whole grid (start, end, ancestor)
     int heavy_queue_cap;
     int fused_resident[16];   // co-resident CTAs of each k_resample_fused instantiation (0: not queried yet)
-    int gsf_minb;             // CTAs (of 128 threads) per SM the GS-UKF kernels are compiled for (4; GSE_GSF_MINB = 3 / 5 / 6)
+    int gsf_minb;             // GSE_GSF_MINB = 3..6: CTAs (of 128 threads) per SM for both GS-UKF kernels; 0: predict 5, update 6
     int predict_minb;         // CTAs per SM of the benchmark's predict specialisation (4; GSE_PREDICT_MINB=5: the 48-register build)
     unsigned long long* fused_trace;   // GSE_FUSED_TRACE=1: per-CTA phase time stamps of the last fused resample (debugging)
     int fused_minb;           // CTAs per SM the fused kernel is compiled for (3; GSE_FUSED_MINB=4 to compare)

@@ -236,10 +236,11 @@ static int launch_gsf_predict(gse_ctx* ctx, const float* mean_src_dev, const flo
     } else {
         if (noise_dev) LAUNCH_G1(true, true, false);
         else if (ctx->state_sampler.diag && ctx->state_sampler.nd == 2) {       // the benchmark's noise; GSE_GSF_MINB tunes
-            if (ctx->gsf_minb == 5) LAUNCH_G1M(true, false, false, 2, 5);
+            // measured at 2^20 components (us): 3 CTAs/SM 113, 4: 110, 5: 109 (96 registers), 6: 117 (80, spills)
+            if (ctx->gsf_minb == 4) LAUNCH_G1M(true, false, false, 2, 4);
             else if (ctx->gsf_minb == 6) LAUNCH_G1M(true, false, false, 2, 6);
             else if (ctx->gsf_minb == 3) LAUNCH_G1M(true, false, false, 2, 3);
-            else LAUNCH_G1M(true, false, false, 2, 4);
+            else LAUNCH_G1M(true, false, false, 2, 5);
         } else if (ctx->state_sampler.diag) LAUNCH_G1(true, false, false);
         else LAUNCH_G1(false, false, false);
     }
@@ -405,10 +406,11 @@ extern "C" int gse_gsf_update(gse_ctx* ctx, float* mean_dev, float* cov_dev, int
                                                                        z[0], z[1], ctx->meas_density, ctx->block_max,      \
                                                                        ctx->block_sum, ctx->ticket, stats_dev,             \
                                                                        ctx->step_params, ctx->err_dev)
+    // measured at 2^20 components (us): 3 CTAs/SM 95, 4: 82, 5: 76, 6: 71 (80 registers)
     if (ctx->gsf_minb == 5) LAUNCH_G2(5);
-    else if (ctx->gsf_minb == 6) LAUNCH_G2(6);
+    else if (ctx->gsf_minb == 4) LAUNCH_G2(4);
     else if (ctx->gsf_minb == 3) LAUNCH_G2(3);
-    else LAUNCH_G2(4);
+    else LAUNCH_G2(6);
 #undef LAUNCH_G2
     GSE_CHECK_LAUNCH(ctx);
     return GSE_OK;
