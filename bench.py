@@ -426,6 +426,7 @@ def run_ours(args):
         step(k, True)
     pf._materialise()                           # the last resample's pending gather belongs to the timed region
     ev1.record(stream)
+    t_issued = time.perf_counter()              # host side done issuing: close to the device time = launch-bound
     barrier()
     t_wall1 = time.perf_counter()
     launches = pf._ctx.launches - launches0
@@ -505,6 +506,7 @@ def run_ours(args):
                 "h2d_bytes_per_step": 48, "d2h_bytes_per_step": 48 * 8,
                 "note": "u, z are host arrays passed per call; particles stay resident (as in the reference's GPU "
                         "class); point_estimate() read back every step"},
+        "host_issue_ms_per_step": (t_issued - t_wall0) * 1e3 / K,
         "gpu_launches": int(lsum[0]),
         "sharded_parity": parity,
         "clocks": clocks,

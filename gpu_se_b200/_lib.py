@@ -9,7 +9,7 @@ import os
 
 GSE_NX, GSE_NU, GSE_NY, GSE_NSIGMA, GSE_NCOV, GSE_MAX_ND = 5, 2, 2, 11, 15, 8
 GSE_MODEL_BIOREACTOR = 1
-GSE_ABI_VERSION = 5
+GSE_ABI_VERSION = 6
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgse_b200.so")
 
@@ -38,7 +38,7 @@ class gse_shards(ctypes.Structure):
     _fields_ = [("nshards", ctypes.c_int32), ("rows", ctypes.c_int64 * (GSE_MAX_SHARDS + 1)),
                 ("cumsum_dev", ctypes.c_void_p * GSE_MAX_SHARDS), ("state_dev", ctypes.c_void_p * GSE_MAX_SHARDS),
                 ("ld", ctypes.c_int64 * GSE_MAX_SHARDS), ("offsets_dev", ctypes.c_void_p),
-                ("idx_dev", ctypes.c_void_p * GSE_MAX_SHARDS)]
+                ("idx_dev", ctypes.c_void_p * GSE_MAX_SHARDS), ("rank", ctypes.c_int32)]
 
 
 class gse_step_params(ctypes.Structure):
@@ -66,9 +66,10 @@ SIGNATURES = {
     "gse_weights_linear": (c_int, [c_vp, c_vp, c_vp, c_i64, c_dbl, c_vp, c_vp]),
     "gse_scan_weights": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "gse_resample_search": (c_int, [c_vp, c_vp, c_i64, c_vp, c_dbl, c_i64, c_i64, c_i64, c_vp, c_vp]),
-    "gse_resample_fused": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_dbl, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "gse_resample_fused": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_dbl, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_i64,
+                                   c_vp, c_int, c_vp]),
     "gse_resample_fused_sharded": (c_int, [c_vp, c_vp, c_vp, c_vp, c_dbl, c_shards_p, ctypes.POINTER(c_vp), c_int,
-                                           ctypes.c_uint, ctypes.c_uint, c_vp, c_vp]),
+                                           ctypes.c_uint, ctypes.c_uint, c_vp, c_vp, c_i64, c_vp, c_int, c_vp]),
     "gse_resample_search_f64": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_dbl, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "gse_ctx_errors": (ctypes.c_uint, [c_vp, c_int]),
     "gse_gather_rows": (c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_vp]),

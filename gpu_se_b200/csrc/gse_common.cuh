@@ -108,7 +108,7 @@ struct gse_ctx {
     uint64_t* fused_status;   // fused resample: one aggregate word per CTA, zero between launches
     int4* heavy_queue;        // fused resample: runs of one heavy source handed to the whole grid (start, end, ancestor)
     int heavy_queue_cap;
-    int fused_resident[16];   // co-resident CTAs of each k_resample_fused instantiation (0: not queried yet)
+    int fused_resident[24];   // co-resident CTAs of each k_resample_fused instantiation (0: not queried yet)
     int gsf_minb;             // GSE_GSF_MINB = 3..6: CTAs (of 128 threads) per SM for both GS-UKF kernels; 0: predict 5, update 6
     int predict_minb;         // CTAs per SM of the benchmark's predict specialisation (4; GSE_PREDICT_MINB=5: the 48-register build)
     unsigned long long* fused_trace;   // GSE_FUSED_TRACE=1: per-CTA phase time stamps of the last fused resample (debugging)
@@ -156,6 +156,10 @@ struct GatherShards {
     int64_t seg_row[GSE_MAX_SHARDS + 1];
     const float* state[GSE_MAX_SHARDS];
     int64_t ld[GSE_MAX_SHARDS];
+    // the calling rank's own shard once more, as scalars: nearly every ancestor is local (the shards' weight totals
+    // are balanced), and these fields are read without any look-up
+    const float* home_state;
+    int64_t home_ld, home_row0, home_row1;
 };
 
 static inline int gse_build_gather_shards(const gse_shards* sh, const void* dst, GatherShards* g) {
@@ -168,6 +172,11 @@ static inline int gse_build_gather_shards(const gse_shards* sh, const void* dst,
         g->state[t] = sh->state_dev[t];
         g->ld[t] = sh->ld[t];
     }
+    const int home = (sh->rank >= 0 && sh->rank < sh->nshards) ? sh->rank : 0;
+    g->home_state = g->state[home];
+    g->home_ld = g->ld[home];
+    g->home_row0 = g->seg_row[home];
+    g->home_row1 = g->seg_row[home + 1];
     return GSE_OK;
 }
 
@@ -661,6 +670,8 @@ struct ShardRef {
 };
 __device__ __forceinline__ ShardRef shard_ref(const GatherShards& g, int64_t k) {
     ShardRef r;
+    r.state = g.home_state; r.ld = g.home_ld; r.row0 = g.home_row0; r.row1 = g.home_row1;
+    if (k >= r.row0 && k < r.row1) return r;                      // local: two compares, no look-up
     r.state = g.state[0]; r.ld = g.ld[0]; r.row0 = g.seg_row[0]; r.row1 = g.seg_row[1];
 #pragma unroll
     for (int t = 1; t < GSE_MAX_SHARDS; ++t) {

@@ -90,12 +90,13 @@ k_pf_predict(const float* xs, int64_t lds, const int32_t* __restrict__ idx, cons
         // handful of threads) one look-up serves the four rows
         const ShardRef own = shard_ref(shards, id[0]);
         if (id[3] < own.row1) {
+            // (same access pattern as GMODE 1: read-only loads, one column at a time)
             const int64_t ld0 = own.ld;
             const float* base = own.state - own.row0;
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
+            for (int j = 0; j < 5; ++j) {
 #pragma unroll
-                for (int j = 0; j < 5; ++j) v[j][r] = base[j * ld0 + id[r]];
+                for (int r = 0; r < 4; ++r) v[j][r] = __ldg(base + j * ld0 + id[r]);
             }
         } else {
 #pragma unroll

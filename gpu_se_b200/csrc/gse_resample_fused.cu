@@ -35,6 +35,7 @@
 #define RF_PIECE 65536           // queued runs are cut into pieces of at most this many outputs (one warp each)
 
 #define RF_TWO52 4503599627370496.0
+#define RF_NMEAN 6               // MEAN kernels: sum of c_k x_k (5 columns) and of c_k
 #define RF_MAX_BLOCKS 4096       // status words: [0, 4096) CTA aggregates, [4096, 8192] exclusive prefixes + total
 
 struct FusedArgs {
@@ -61,13 +62,21 @@ struct FusedArgs {
     int first_shard;           // local row 0 is the first row of the whole population (e_{-1} = 0)
     int normalise;             // f64 entry: divide by cumsum[n_src - 1] on the fly (`cumsum /= cumsum[-1]`, :90)
     uint64_t* total_out;       // receives the integer total (NULL to skip)
+    double* stats_reset;       // weights are uniform after a resample: (M, S) <- (0, n_total) when the kernel is done (NULL to skip)
     // sharded population (SHARDED kernels): every rank ranks its OWN rows against the global total and writes the
     // ancestor of every output it sources straight into the index buffer of the shard that owns the output slot
     int nshards, rank;
+    int out_home_lo, out_home_hi;              // this rank's own output slots (idx_out is its buffer)
     unsigned int epoch_totals, epoch_done;     // mailbox sequence numbers of the two exchanges inside the kernel
     int shard_lo[GSE_MAX_SHARDS + 1];          // shard t owns the output slots [shard_lo[t], shard_lo[t + 1])
     int32_t* shard_idx[GSE_MAX_SHARDS];        // shard t's index buffer (its local slot 0), peer memory for t != rank
     MailboxTable mb;
+    // MEAN kernels: the post-resample estimate sum_k c_k x_k (c_k = offspring of row k) falls out of the ranks -- only the
+    // few rows that have offspring are read
+    const float* mean_state;   // SoA state of the source rows, 5 columns `mean_ld` apart
+    int64_t mean_ld;
+    double* mean_partials;     // 6 doubles per CTA
+    double* mean_out;          // moment block: [0] S0 = outputs sourced here, [1..5] S1, [21..25] pivot (0)
     unsigned long long* trace; // GSE_FUSED_TRACE: 8 words per CTA (globaltimer at start / phase 1 / 2 / 3 done, SM id, ...), or NULL
 };
 
@@ -222,6 +231,8 @@ __device__ __forceinline__ void ranks_of(double C0, const double (&q)[RF_ITEMS],
 // the whole argument struct into local memory)
 struct ShardTable {
     int nshards;
+    int home_lo, home_hi;          // the calling rank's own slots: most windows land there
+    int32_t* home_idx;
     int lo[GSE_MAX_SHARDS + 1];
     int32_t* idx[GSE_MAX_SHARDS];
 };
@@ -286,8 +297,16 @@ struct WarpFill {
         if (SHARDED) {
             // the window usually lies inside one shard's slots: two coalesced 128-bit stores into that shard's buffer
             // (over NVLink when it is a peer's); windows across a shard boundary or the sub-run's ends go element-wise
+            const bool whole = wb >= mlo && wb + RF_WIN <= mhi;
+            if (whole && wb >= st->home_lo && wb + RF_WIN <= st->home_hi) {
+                int32_t* o = st->home_idx + (wb - st->home_lo) + 4 * lane;
+                *reinterpret_cast<int4*>(o) = a;
+                *reinterpret_cast<int4*>(o + 128) = b;
+                wb += RF_WIN;
+                return;
+            }
             const int t0 = shard_of_output(*st, wb), t1 = shard_of_output(*st, wb + RF_WIN - 1);
-            if (t0 == t1 && wb >= mlo && wb + RF_WIN <= mhi) {
+            if (t0 == t1 && whole) {
                 int32_t* o = st->idx[t0] + (wb - st->lo[t0]) + 4 * lane;
                 *reinterpret_cast<int4*>(o) = a;
                 *reinterpret_cast<int4*>(o + 128) = b;
@@ -424,10 +443,12 @@ __device__ __forceinline__ void drain_queue(const FusedArgs& a, const ShardTable
     }
 }
 
-template <bool HAS_LL, bool HAS_BASE, bool POW2, int MINB, bool SHARDED>
+template <bool HAS_LL, bool HAS_BASE, bool POW2, int MINB, bool SHARDED, bool MEAN>
 __global__ void __launch_bounds__(RF_THREADS, MINB)
 k_resample_fused(const __grid_constant__ FusedArgs a) {
     __shared__ __align__(16) int s_ring[RF_WARPS][RF_RING];
+    __shared__ int2 s_list[MEAN ? RF_WARPS : 1][MEAN ? RF_TILE : 1];     // (row, offspring) of the tile's rows that have any
+    __shared__ double s_mean[MEAN ? RF_WARPS : 1][RF_NMEAN];
     __shared__ double s_wsum[RF_WARPS];
     __shared__ uint64_t s_part[RF_WARPS][2];
     __shared__ unsigned int s_vb;
@@ -437,6 +458,9 @@ k_resample_fused(const __grid_constant__ FusedArgs a) {
     if (tid == 0) s_vb = atomicAdd(a.counters, 1u);               // CTAs are numbered in the order they start
     if (SHARDED && tid == 32) {
         s_st.nshards = a.nshards;
+        s_st.home_lo = a.out_home_lo;
+        s_st.home_hi = a.out_home_hi;
+        s_st.home_idx = a.idx_out;
 #pragma unroll
         for (int t = 0; t <= GSE_MAX_SHARDS; ++t) s_st.lo[t] = a.shard_lo[t];
 #pragma unroll
@@ -551,6 +575,9 @@ k_resample_fused(const __grid_constant__ FusedArgs a) {
     double carry = __ull2double_rn(excl_u);
 #pragma unroll
     for (int w = 0; w < RF_WARPS; ++w) carry += (w < wid) ? s_wsum[w] : 0.0;
+    double macc[RF_NMEAN];
+#pragma unroll
+    for (int c = 0; c < RF_NMEAN; ++c) macc[c] = 0.0;
     if (w0 < w1) {
         int carry_rank = 0;
         if (!(a.first_shard && w0 == 0) && !degenerate) carry_rank = rank_of<POW2, false, false>(carry, rc);
@@ -587,15 +614,57 @@ k_resample_fused(const __grid_constant__ FusedArgs a) {
             int ep = __shfl_up_sync(0xffffffffu, e[RF_ITEMS - 1], 1);
             if (lane == 0) ep = carry_rank;
             const int E1 = __shfl_sync(0xffffffffu, e[RF_ITEMS - 1], 31);
+            if (MEAN) {
+                // list the rows with offspring (about one in twenty once the weights have spread), then the whole warp reads
+                // them at once: a lane that read its own rows one after the other would wait out a memory round trip for each
+                int2* const list = s_list[wid];
+                const unsigned int below = (1u << lane) - 1u;
+                int prev = ep, cnt = 0;
+#pragma unroll
+                for (int k = 0; k < RF_ITEMS; ++k) {
+                    const int c = e[k] - prev;
+                    prev = e[k];
+                    const unsigned int m = __ballot_sync(0xffffffffu, c > 0);
+                    if (c > 0) list[cnt + __popc(m & below)] = make_int2((int)row0 + k, c);
+                    cnt += __popc(m);
+                }
+                __syncwarp();
+                for (int i = lane; i < cnt; i += 32) {
+                    const int2 en = list[i];
+                    const float* const xr = a.mean_state + en.x;
+                    const double cd = (double)en.y;
+                    float xv[5];
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) xv[c] = __ldg(xr + c * a.mean_ld);
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) macc[c] = fma(cd, (double)xv[c], macc[c]);     // exact products
+                    macc[5] += cd;
+                }
+                __syncwarp();
+            }
             wf.template tile<SHARDED>(e, ep, carry_rank, E1, t * RF_TILE + 1, a, lane);
             carry_rank = E1;
         }
         wf.template finish<SHARDED>(carry_rank, a, lane);
     }
+    if (MEAN) {
+#pragma unroll
+        for (int c = 0; c < RF_NMEAN; ++c) {
+            const double v = warp_sum_f64(macc[c]);
+            if (lane == 0) s_mean[wid][c] = v;
+        }
+    }
 
     // ---- tail: wait for every CTA, drain the heavy-run queue, reset the launch state --------------------------
     __syncthreads();
     if (a.trace && tid == 0) a.trace[8 * vb + 3] = global_timer_ns();
+    if (MEAN && tid >= 32 && tid < 32 + RF_NMEAN) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < RF_WARPS; ++w) t += s_mean[w][tid - 32];
+        a.mean_partials[(size_t)vb * RF_NMEAN + (tid - 32)] = t;
+        __threadfence();                                          // read by the last CTA out, two barriers from here
+    }
     if (tid == 0) {
         __threadfence();
         atomicAdd(a.counters + 1, 1u);
@@ -621,6 +690,18 @@ k_resample_fused(const __grid_constant__ FusedArgs a) {
             }
             __syncthreads();
         }
+        if (MEAN) {
+            __threadfence();
+            if (wid < RF_NMEAN) {                                 // fixed summation order: the estimate is reproducible
+                double t = 0.0;
+                for (int b = lane; b < nblocks; b += 32) t += __ldcg(a.mean_partials + (size_t)b * RF_NMEAN + wid);
+                t = warp_sum_f64(t);
+                if (lane == 0) a.mean_out[wid == 5 ? 0 : 1 + wid] = t;
+                if (lane == 1 && wid < 5) a.mean_out[21 + wid] = 0.0;
+            }
+            if (tid == 0) { a.mean_out[41] = 0.0; a.mean_out[42] = a.n_total; }      // (M, S) of the uniform weights
+        }
+        if (a.stats_reset && tid == 0) { a.stats_reset[0] = 0.0; a.stats_reset[1] = a.n_total; }
         // leave everything zero for the next launch
         for (int i = tid; i < nblocks; i += RF_THREADS) { a.status[i] = 0ull; a.status[RF_MAX_BLOCKS + i] = 0ull; }
         if (tid == 0) a.status[RF_MAX_BLOCKS + nblocks] = 0ull;
@@ -713,12 +794,12 @@ static void fill_common(gse_ctx* ctx, FusedArgs& a, double r, int64_t n_total, i
     a.src_row0 = (int)src_row0;
 }
 
-template <bool LL, bool BASE, bool POW2, int MINB, bool SHARDED>
+template <bool LL, bool BASE, bool POW2, int MINB, bool SHARDED, bool MEAN = false>
 static int launch_fused(gse_ctx* ctx, FusedArgs& a, int variant, cudaStream_t s) {
     // every CTA must be resident at once (phase 2 and the tail wait on the other CTAs)
     if (ctx->fused_resident[variant] == 0) {
         int per_sm = 0;
-        GSE_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_resample_fused<LL, BASE, POW2, MINB, SHARDED>,
+        GSE_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_resample_fused<LL, BASE, POW2, MINB, SHARDED, MEAN>,
                                                                      RF_THREADS, 0));
         GSE_REQUIRE(per_sm >= 1, "fused resample kernel does not fit an SM");
         ctx->fused_resident[variant] = per_sm * ctx->num_sms;
@@ -729,15 +810,19 @@ static int launch_fused(gse_ctx* ctx, FusedArgs& a, int variant, cudaStream_t s)
     a.rows_per_block = gse_div_up(groups, blocks) * group;
     blocks = gse_div_up(a.n_src, a.rows_per_block);
     GSE_REQUIRE(blocks <= ctx->max_tiles && blocks < RF_MAX_BLOCKS, "workspace too small");
-    k_resample_fused<LL, BASE, POW2, MINB, SHARDED><<<(unsigned)blocks, RF_THREADS, 0, s>>>(a);
+    k_resample_fused<LL, BASE, POW2, MINB, SHARDED, MEAN><<<(unsigned)blocks, RF_THREADS, 0, s>>>(a);
     GSE_CHECK_LAUNCH(ctx);
     return GSE_OK;
 }
 
 extern "C" int gse_resample_fused(gse_ctx* ctx, const float* loglik_dev, const double* base_dev, const double* stats_dev,
                                   int64_t n_src, double r, int64_t n_total, int64_t out0, int64_t n_out,
-                                  int64_t src_row0, int32_t* idx_out_dev, uint64_t* total_dev, void* stream) {
+                                  int64_t src_row0, int32_t* idx_out_dev, uint64_t* total_dev, const float* state_dev,
+                                  int64_t ld, double* moments_dev, int reset_stats, void* stream) {
     GSE_REQUIRE(ctx != NULL && stats_dev != NULL && idx_out_dev != NULL, "ctx / stats / idx is NULL");
+    GSE_REQUIRE(moments_dev == NULL || (state_dev != NULL && ld >= n_src && loglik_dev != NULL && base_dev == NULL &&
+                                        out0 == 0 && n_out == n_total),
+                "the in-kernel estimate needs the state, log-likelihood weights and the whole output range");
     GSE_REQUIRE(loglik_dev != NULL || base_dev != NULL, "need loglik or base weights");
     GSE_REQUIRE(loglik_dev == NULL || aligned32(loglik_dev), "loglik must be 32-byte aligned");
     GSE_REQUIRE(base_dev == NULL || aligned32(base_dev), "base must be 32-byte aligned");
@@ -756,15 +841,24 @@ extern "C" int gse_resample_fused(gse_ctx* ctx, const float* loglik_dev, const d
     a.n_src = n_src;
     a.first_shard = (src_row0 == 0) ? 1 : 0;
     a.total_out = total_dev;
+    a.stats_reset = reset_stats ? const_cast<double*>(stats_dev) : NULL;
     a.trace = ctx->fused_trace;
     fill_common(ctx, a, r, n_total, out0, n_out, idx_out_dev, src_row0);
     cudaStream_t s = (cudaStream_t)stream;
     const bool pow2 = (n_total & (n_total - 1)) == 0;
+    if (moments_dev) {
+        a.mean_state = state_dev;
+        a.mean_ld = ld;
+        a.mean_partials = ctx->red_partials;
+        a.mean_out = moments_dev;
+        if (pow2) return launch_fused<true, false, true, 3, false, true>(ctx, a, 16, s);
+        return launch_fused<true, false, false, 3, false, true>(ctx, a, 17, s);
+    }
 #define FUSED_CASE(LL, BASE, V)                                                           \
     do {                                                                                  \
         if (pow2 && ctx->fused_minb == 3) return launch_fused<LL, BASE, true, 3, false>(ctx, a, 6 + (V), s);   \
         if (pow2) return launch_fused<LL, BASE, true, 4, false>(ctx, a, 2 * (V), s);      \
-        return launch_fused<LL, BASE, false, 4, false>(ctx, a, 2 * (V) + 1, s);           \
+        return launch_fused<LL, BASE, false, 3, false>(ctx, a, 2 * (V) + 1, s);           \
     } while (0)
     if (loglik_dev && base_dev) FUSED_CASE(true, true, 0);
     else if (loglik_dev) FUSED_CASE(true, false, 1);
@@ -779,8 +873,11 @@ extern "C" int gse_resample_fused(gse_ctx* ctx, const float* loglik_dev, const d
 extern "C" int gse_resample_fused_sharded(gse_ctx* ctx, const float* loglik_dev, const double* base_dev,
                                           const double* stats_dev, double r, const gse_shards* sh,
                                           void* const mailboxes[GSE_MAX_SHARDS], int rank, unsigned int epoch_totals,
-                                          unsigned int epoch_done, uint64_t* total_dev, void* stream) {
+                                          unsigned int epoch_done, uint64_t* total_dev, const float* state_dev,
+                                          int64_t ld, double* moments_dev, int reset_stats, void* stream) {
     GSE_REQUIRE(ctx != NULL && stats_dev != NULL && sh != NULL, "ctx / stats / shards is NULL");
+    GSE_REQUIRE(moments_dev == NULL || (state_dev != NULL && loglik_dev != NULL && base_dev == NULL),
+                "the in-kernel estimate needs the state and log-likelihood weights");
     GSE_REQUIRE(loglik_dev != NULL || base_dev != NULL, "need loglik or base weights");
     GSE_REQUIRE(loglik_dev == NULL || aligned32(loglik_dev), "loglik must be 32-byte aligned");
     GSE_REQUIRE(base_dev == NULL || aligned32(base_dev), "base must be 32-byte aligned");
@@ -803,6 +900,7 @@ extern "C" int gse_resample_fused_sharded(gse_ctx* ctx, const float* loglik_dev,
     a.n_src = n_src;
     a.first_shard = (rank == 0) ? 1 : 0;
     a.total_out = total_dev;
+    a.stats_reset = reset_stats ? const_cast<double*>(stats_dev) : NULL;
     a.trace = ctx->fused_trace;
     a.nshards = sh->nshards;
     a.rank = rank;
@@ -817,12 +915,23 @@ extern "C" int gse_resample_fused_sharded(gse_ctx* ctx, const float* loglik_dev,
     int rc = gse_build_mailboxes(mailboxes, rank, sh->nshards, &a.mb);
     if (rc) return rc;
     fill_common(ctx, a, r, n_total, 0, n_total, sh->idx_dev[rank], sh->rows[rank]);
+    a.out_home_lo = (int)sh->rows[rank];
+    a.out_home_hi = (int)sh->rows[rank + 1];
     cudaStream_t s = (cudaStream_t)stream;
     const bool pow2 = (n_total & (n_total - 1)) == 0;
+    if (moments_dev) {
+        GSE_REQUIRE(ld >= n_src, "ld < n_src");
+        a.mean_state = state_dev;
+        a.mean_ld = ld;
+        a.mean_partials = ctx->red_partials;
+        a.mean_out = moments_dev;
+        if (pow2) return launch_fused<true, false, true, 3, true, true>(ctx, a, 18, s);
+        return launch_fused<true, false, false, 3, true, true>(ctx, a, 19, s);
+    }
 #define SHARDED_CASE(LL, BASE, V)                                                         \
     do {                                                                                  \
-        if (pow2) return launch_fused<LL, BASE, true, 4, true>(ctx, a, 9 + 2 * (V), s);   \
-        return launch_fused<LL, BASE, false, 4, true>(ctx, a, 10 + 2 * (V), s);           \
+        if (pow2) return launch_fused<LL, BASE, true, 3, true>(ctx, a, 9 + 2 * (V), s);   \
+        return launch_fused<LL, BASE, false, 3, true>(ctx, a, 10 + 2 * (V), s);           \
     } while (0)
     if (loglik_dev && base_dev) SHARDED_CASE(true, true, 0);
     else if (loglik_dev) SHARDED_CASE(true, false, 1);

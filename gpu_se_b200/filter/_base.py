@@ -143,6 +143,12 @@ class WeightedEnsemble:
         self._mom_valid = False
         self._mom_full = False         # the cached moments include the second moments
         self._want_cov = False         # a caller asked for point_covariance before: compute both in one pass
+        # point_estimate() straight after resample() -- every filter loop of the reference -- is folded into the resample
+        # kernel once the filter has seen the pattern (it needs no second pass over the ancestor index)
+        self._est_hint = False         # the caller reads the estimate of the resampled population
+        self._fresh_resample = False   # nothing has touched the population since the last resample
+        self._mom_from_resample = False    # self._mom holds that estimate (device side)
+        self._mom_unused = False       # ... and nobody has asked for it yet
         self._seed = int(seed) if seed is not None else int(numpy.random.randint(0, 2 ** 31 - 1))
         self._step = 0
         self.last_sample_index = None
@@ -196,7 +202,8 @@ class WeightedEnsemble:
         p.r = r
         p.step = self._step
         _lib.check(_lib.lib.gse_ctx_upload_step_params(self._ctx.handle, ctypes.byref(p), self._stream()))
-        key = self._state.data_ptr()
+        want_mean = self._mean_in_resample()
+        key = (self._state.data_ptr(), want_mean)
         g = self._graphs.get(key)
         if g is None:
             # capture: the eager code path runs once into the capture stream (its host-side state
@@ -219,6 +226,8 @@ class WeightedEnsemble:
             self._state, self._state_alt = self._state_alt, self._state
             self._step += 1
             self._touch()
+            self._fresh_resample = True
+            self._mom_from_resample = self._mom_unused = want_mean
         self.graph_replays += 1
 
     # -- helpers -------------------------------------------------------------------------
@@ -227,6 +236,8 @@ class WeightedEnsemble:
 
     def _touch(self):
         self._mom_valid = False
+        self._fresh_resample = False
+        self._mom_from_resample = False
 
     def _idx_ptr(self):
         return self._idx.data_ptr() if self._pending else None
@@ -289,12 +300,14 @@ class WeightedEnsemble:
         self._stats[1] = self._base.sum()
         self._touch()
 
-    def _reset_uniform(self):
+    def _reset_uniform(self, stats_done=False):
+        """Uniform weights; ``stats_done``: the resample kernel has already stored (M, S) = (0, N)."""
         self._base = None
         self._base_max = None
         self._base_scale = 1.0 / self.N_particles
         self._loglik_dirty = False
-        self._stats.copy_(self._stats_uniform)
+        if not stats_done:
+            self._stats.copy_(self._stats_uniform)
 
     def _after_update(self):
         self._loglik_dirty = True
@@ -339,15 +352,27 @@ class WeightedEnsemble:
         return (self._ensure_loglik_buffer() if use_loglik else None,
                 self._base.data_ptr() if self._base is not None else None, stats)
 
+    def _mean_in_resample(self):
+        """Should the next resample also produce the estimate of the resampled population?  Yes once a caller has asked
+        for ``point_estimate()`` right after a resample, until an estimate computed that way goes unread."""
+        if self._mom_unused:
+            self._est_hint = False
+        return (FUSED_RESAMPLE and self.MEAN_ONLY_KERNEL and self._est_hint and not self._want_cov
+                and self._base is None)
+
     def _resample_now(self, r, return_index):
         n = self.N_particles
         self._materialise()                       # a second resample without a predict in between
+        want_mean = stats_done = False
         if FUSED_RESAMPLE:
             # scan + rank + fill in one launch: the cumulative weights never reach HBM (csrc/gse_resample_fused.cu)
+            want_mean = self._mean_in_resample()
             ll, base, stats = self._weight_sources()
+            stats_done = stats is self._stats     # the kernel leaves (M, S) = (0, N) behind: no launch for that
             _lib.check(_lib.lib.gse_resample_fused(
                 self._ctx.handle, ll, base, stats.data_ptr(), n, r, n, 0, n, 0, self._idx.data_ptr(),
-                self._offtot.data_ptr() + 8, self._stream()))
+                self._offtot.data_ptr() + 8, self._state.data_ptr() if want_mean else None, self._ld,
+                self._mom.data_ptr() if want_mean else None, int(stats_done), self._stream()))
         else:
             self._scan()
             if self._stage_hook is not None:
@@ -357,8 +382,10 @@ class WeightedEnsemble:
                 self._idx.data_ptr(), self._stream()))
         self._pending = True
         self._loglik_zero = True                  # weights = 1/N  (:103 / :316)
-        self._reset_uniform()
+        self._reset_uniform(stats_done)
         self._touch()
+        self._fresh_resample = True
+        self._mom_from_resample = self._mom_unused = want_mean
         idx = self._idx[:n].to(torch.int64) if return_index else None
         self.last_sample_index = idx
         return idx
@@ -385,9 +412,14 @@ class WeightedEnsemble:
             self._want_cov = True
         if not self._mom_valid or (need_cov and not self._mom_full):
             full = need_cov or self._want_cov or not self.MEAN_ONLY_KERNEL
-            self._launch_moments(mean_only=not full)
+            if self._fresh_resample and not full:
+                self._est_hint = True
+            if self._mom_from_resample and not full:
+                self._mom_unused = False                    # the resample kernel left the estimate (and M, S) in self._mom
+            else:
+                self._launch_moments(mean_only=not full)
+                self._mom[41:43].copy_(self._stats[0:2])    # M, S ride along in the same read-back
             self._mom_full = full
-            self._mom[41:43].copy_(self._stats[0:2])        # M, S ride along in the same read-back
             self._mom_host.copy_(self._mom, non_blocking=True)
             torch.cuda.current_stream(self.device).synchronize()
             self._ctx.check_device_errors()

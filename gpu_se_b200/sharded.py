@@ -173,7 +173,7 @@ class _ShardedEnsemble:
         self.local = self.LOCAL_CLS(f, g, hi - lo, x0, state_pdf, measurement_pdf, device=device, seed=seed, index0=lo,
                                     workspace_rows=self.N_particles, peer=(exchange == "peer"), **local_kw)
         self.device = self.local.device
-        self._set_uniform()
+        self._set_uniform(init=True)
         self._pending = False
         if exchange == "peer":
             self._open_peers()
@@ -215,6 +215,7 @@ class _ShardedEnsemble:
         for parity in (0, 1):
             sh = _lib.gse_shards()
             sh.nshards = self.world
+            sh.rank = self.rank
             for s, (a, b) in enumerate(self.bounds):
                 sh.rows[s] = a
                 sh.state_dev[s] = self._peer_ptr[s][parity]
@@ -243,19 +244,25 @@ class _ShardedEnsemble:
     # -- resample --------------------------------------------------------------------------------
     def _resample_peer(self, r, return_index):
         loc = self.local
+        want_mean = loc._mean_in_resample()      # the estimate of the resampled population out of the same kernel
         ll, base, stats = loc._weight_sources()
+        stats_done = stats is loc._stats
         e1, e2 = self._next_epoch(), self._next_epoch()
         sh = self._shards[self._parity]
         _lib.check(_lib.lib.gse_resample_fused_sharded(loc._ctx.handle, ll, base, stats.data_ptr(), r, ctypes.byref(sh),
                                                        self._boxes, self.rank, e1, e2, loc._offtot.data_ptr() + 8,
+                                                       loc._state.data_ptr() if want_mean else None, loc._ld,
+                                                       loc._mom.data_ptr() if want_mean else None, int(stats_done),
                                                        loc._stream()))
         # lazy, as on one GPU: the rows move when the next kernel reads them (predict / moments pull them
         # out of the owning shard's memory through the global ancestor index)
         self._pending = True
         loc._loglik_zero = True
-        loc._reset_uniform()
+        loc._reset_uniform(stats_done)
         self._set_uniform()
         loc._touch()
+        loc._fresh_resample = True
+        loc._mom_from_resample = loc._mom_unused = want_mean
         self.exchanged_rows = None                                # known on the device only: see rows_from_peers()
         return self._idx_global[:loc.N_particles].to(torch.int64) if return_index else None
 
@@ -285,11 +292,13 @@ class _ShardedEnsemble:
         return int(((idx < lo) | (idx >= hi)).sum().item())
 
     # -- weights ---------------------------------------------------------------------------------
-    def _set_uniform(self):
+    def _set_uniform(self, init=False):
+        """Uniform weights over the WHOLE population (the local class's reset has just assumed its own row count)."""
         loc = self.local
         loc._base_scale = 1.0 / self.N_particles
-        loc._stats_uniform[1] = float(self.N_particles)
-        loc._stats.copy_(loc._stats_uniform)
+        if init:
+            loc._stats_uniform[1] = float(self.N_particles)       # from here on loc._reset_uniform() copies the global S
+            loc._stats.copy_(loc._stats_uniform)
 
     @property
     def weights(self):
@@ -414,7 +423,14 @@ class _ShardedEnsemble:
         if need_cov:
             self._want_cov = True
         mean_only = not (need_cov or self._want_cov)
-        self._launch_local_moments(mean_only)
+        loc._want_cov = self._want_cov
+        if loc._fresh_resample and mean_only and loc.MEAN_ONLY_KERNEL:
+            loc._est_hint = True
+        if loc._mom_from_resample and mean_only:
+            loc._mom_unused = False          # this rank's block (the outputs it sources) came out of the resample kernel
+            loc._mom_from_resample = False   # ... and the merge below overwrites it
+        else:
+            self._launch_local_moments(mean_only)
         if self.exchange == "peer":
             # the shards' moment blocks cross NVLink inside one single-warp kernel that also merges them
             if self.world > 1:

@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define GSE_ABI_VERSION 5
+#define GSE_ABI_VERSION 6
 
 #define GSE_NX 5        /* states  (Cg, Cx, Cfa, Ce, Ch)   model/BioreactorModel.py:191 */
 #define GSE_NU 2        /* inputs  (Fg_in, Fm_in)          model/BioreactorModel.py:195 */
@@ -215,10 +215,19 @@ int gse_resample_search(gse_ctx* ctx, const uint64_t* cumsum_dev, int64_t n_src,
  * -- the same indices as gse_scan_weights + gse_resample_search, bit for bit, without the cumulative weights ever
  * reaching HBM.  Outputs j in [out0, out0 + n_out) are written to idx_out_dev[j - out0] (int32 global ancestor row);
  * a single-GPU population passes out0 = 0, n_out = n_total = n_src, src_row0 = 0.  total_dev receives the integer
- * total (NULL to skip).  The kernel's CTAs wait on one another: the grid is one wave of co-resident CTAs. */
+ * total (NULL to skip).  The kernel's CTAs wait on one another: the grid is one wave of co-resident CTAs.
+ *   moments_dev != NULL additionally yields the estimate of the RESAMPLED population (point_estimate straight after
+ * resample, particle.py:105-108, the pattern of every filter loop of the reference) without reading the ancestor index
+ * back: sum_k c_k x_k over the source rows, c_k = e_k - e_{k-1} the offspring of row k, taken from state_dev (5 SoA
+ * columns ld apart).  Written as a moment block like gse_pf_moments(mean_only): [0] = outputs sourced, [1..5] = the
+ * column sums, [21..25] = pivot (0), [41..42] = (0, n_total).  Needs log-likelihood weights (base_dev NULL) and the
+ * whole output range.
+ *   reset_stats != 0: when the kernel is done it stores (M, S) = (0, n_total) -- the uniform weights a resample leaves
+ * (particle.py:103 / :316) -- into stats_dev[0..1], which saves the caller a launch. */
 int gse_resample_fused(gse_ctx* ctx, const float* loglik_dev, const double* base_dev, const double* stats_dev,
                        int64_t n_src, double r, int64_t n_total, int64_t out0, int64_t n_out, int64_t src_row0,
-                       int32_t* idx_out_dev, uint64_t* total_dev, void* stream);
+                       int32_t* idx_out_dev, uint64_t* total_dev, const float* state_dev, int64_t ld,
+                       double* moments_dev, int reset_stats, void* stream);
 
 /* `resample_from_cumsum` (contract (ii)): systematic resample fed the CALLER'S float64
  * cumulative sum -- e.g. the reference's own numpy.cumsum / torch.cumsum array (particle.py:89-90 / :301-304).
@@ -264,6 +273,7 @@ typedef struct gse_shards {
     int64_t ld[GSE_MAX_SHARDS];
     const uint64_t* offsets_dev;
     int32_t* idx_dev[GSE_MAX_SHARDS];    /* shard s's ancestor-index buffer (rows[s+1] - rows[s] entries, rounded up to 4) */
+    int32_t rank;                        /* the caller's own shard (its rows are looked up without a search) */
 } gse_shards;
 
 /* gse_resample_search over the rows of ALL shards for the outputs [out0, out0 + n_out) (this
@@ -278,10 +288,15 @@ int gse_resample_search_sharded(gse_ctx* ctx, const gse_shards* shards, double r
  * number epoch_totals), every rank ranks its rows against the global total and writes the GLOBAL ancestor row of each
  * output it sources into shards->idx_dev[t] of the shard t that owns the output slot (NVLink stores for t != rank);
  * a second mailbox exchange (epoch_done) at the end of the kernel makes every rank's index buffer complete when its
- * kernel completes.  One launch per rank per resample; total_dev receives the global integer total (NULL to skip). */
+ * kernel completes.  One launch per rank per resample; total_dev receives the global integer total (NULL to skip).
+ * moments_dev / state_dev / ld as in gse_resample_fused: this rank's block covers the outputs it SOURCES (whichever
+ * shard owns their slots); the blocks of all ranks add up to the moments of the resampled population
+ * (gse_peer_allgather_moments). */
 int gse_resample_fused_sharded(gse_ctx* ctx, const float* loglik_dev, const double* base_dev, const double* stats_dev,
                                double r, const gse_shards* shards, void* const mailboxes[GSE_MAX_SHARDS], int rank,
-                               unsigned int epoch_totals, unsigned int epoch_done, uint64_t* total_dev, void* stream);
+                               unsigned int epoch_totals, unsigned int epoch_done, uint64_t* total_dev,
+                               const float* state_dev, int64_t ld, double* moments_dev, int reset_stats,
+                               void* stream);
 
 /* dst[:, i] = state row idx[i] (global) pulled from the owning shard's memory, ncols SoA columns. */
 int gse_gather_rows_sharded(gse_ctx* ctx, const gse_shards* shards, const int32_t* idx_dev,

@@ -12,7 +12,7 @@ int main(void) {
     F(gse_mixture, nd); F(gse_mixture, nx); F(gse_mixture, weights); F(gse_mixture, means); F(gse_mixture, covs);
     printf("\"sizeof.gse_shards\": %zu,\n", sizeof(gse_shards));
     F(gse_shards, nshards); F(gse_shards, rows); F(gse_shards, cumsum_dev); F(gse_shards, state_dev);
-    F(gse_shards, ld); F(gse_shards, offsets_dev); F(gse_shards, idx_dev);
+    F(gse_shards, ld); F(gse_shards, offsets_dev); F(gse_shards, idx_dev); F(gse_shards, rank);
     printf("\"sizeof.gse_step_params\": %zu,\n", sizeof(gse_step_params));
     F(gse_step_params, u); F(gse_step_params, dt); F(gse_step_params, z); F(gse_step_params, r);
     F(gse_step_params, step); F(gse_step_params, reserved);

@@ -226,7 +226,83 @@ def test_fused_abi_output_subrange(g, N, out0, n_out):
     idx = torch.full((n_out + 64,), -7, dtype=torch.int32, device=pf.device)
     ll, base, stats = pf._weight_sources()
     _lib.check(_lib.lib.gse_resample_fused(pf._ctx.handle, ll, base, stats.data_ptr(), N, r, N, out0, n_out, 0,
-                                           idx.data_ptr(), None, pf._stream()))
+                                           idx.data_ptr(), None, None, 0, None, 0, pf._stream()))
     got = idx.cpu().numpy()
     assert numpy.array_equal(got[:n_out], expect)
     assert (got[n_out:] == -7).all()           # nothing written past the range
+
+
+# ---- the estimate of the resampled population out of the resample kernel --------------------------------------
+def _cycle(pf, rng, with_estimate=True):
+    u = numpy.array([rng.uniform(0.03, 0.09), rng.uniform(0.1, 0.3)])
+    pf.predict(u, 0.5)
+    pf.update(u, consistent_measurement(u, 0.5, rng))
+    pf.resample(r=float(rng.uniform()))
+    return pf.point_estimate() if with_estimate else None
+
+
+@pytest.mark.parametrize("n", [1000, 4096, 100003, 1 << 20, (1 << 21) + 12])
+def test_estimate_inside_the_resample_kernel(g, n):
+    """point_estimate() straight after resample() (particle.py:105-108 after :85-103, every filter loop of the
+    reference): from the second cycle on the resample kernel itself leaves sum_k offspring_k x_k behind.  It must equal
+    the mean of the gathered rows -- the products are exact in float64, only the summation order differs -- and the
+    filter must go on exactly as one that never asked for an estimate."""
+    pf, plain = make_pf(g, n, seed=5), make_pf(g, n, seed=5)
+    rng, rng2 = numpy.random.default_rng(8), numpy.random.default_rng(8)
+    for c in range(4):
+        est = _cycle(pf, rng)
+        _cycle(plain, rng2, with_estimate=False)
+        in_kernel = pf._mom_valid and not pf._mom_unused and pf._est_hint and c > 0
+        assert in_kernel == (c > 0)
+        rows = pf.particles.get().astype(numpy.float64)               # materialises the pending gather
+        # (the first estimate comes from k_means: float32 sums of four rows, then float64)
+        assert numpy.allclose(est, rows.mean(axis=0), rtol=1e-12 if c > 0 else 1e-6, atol=0)
+        assert numpy.array_equal(plain.particles.get(), rows.astype(numpy.float32))
+    # the caller stops reading estimates: one unread estimate later the kernel is the plain one again
+    _cycle(pf, rng, with_estimate=False)
+    assert pf._mom_unused
+    _cycle(pf, rng, with_estimate=False)
+    assert not pf._est_hint and not pf._mom_from_resample
+    # the covariance needs the second moments: the separate moments kernel takes over
+    est = _cycle(pf, rng)
+    cov = pf.point_covariance()
+    rows = pf.particles.get().astype(numpy.float64)
+    assert numpy.allclose(est, rows.mean(axis=0), rtol=1e-6)
+    assert cov == pytest.approx(numpy.linalg.svd(numpy.cov(rows.T, bias=True), compute_uv=False)[0], rel=1e-6)
+    est = _cycle(pf, rng)
+    assert not pf._mom_from_resample
+    assert numpy.allclose(est, pf.particles.get().astype(numpy.float64).mean(axis=0), rtol=1e-6)
+
+
+def test_estimate_inside_the_resample_kernel_one_heavy_row(g):
+    """All outputs descend from one row (heavy-run queue): its offspring count is the whole population."""
+    from oracle import bioreactor
+    n = 1 << 16
+    rng = numpy.random.default_rng(2)
+    rows0 = bioreactor.X_STEADY[None, :] * (1.0 + 1e-3 * rng.normal(size=(n, 5)))
+    rows0[12345, 0] += 2.0                                   # glucose far from everyone else's: 360 apart in the output
+    pf = make_pf(g, n, seed=3, particles=rows0)
+    pf.resample(r=0.5)                                       # uniform weights: the identity
+    pf.point_estimate()                                      # ... and the pattern the filter looks for
+    assert pf._est_hint
+    u = numpy.array([0.06, 0.2])
+    pf.predict(u, 0.5)
+    x = pf.particles.get()
+    pf.update(u, numpy.array([x[12345, 0] * 180.0 + 0.1, x[12345, 2] * 116.0]))
+    idx = pf.resample(r=0.37, return_index=True).cpu().numpy()
+    est = pf.point_estimate()
+    assert pf._mom_valid and not pf._mom_unused
+    assert (idx == 12345).all()
+    assert numpy.allclose(est, x[12345].astype(numpy.float64), rtol=1e-12, atol=0)
+
+
+def test_estimate_inside_the_resample_kernel_graph_replay(g):
+    n = 1 << 14
+    pf, eager = make_pf(g, n, seed=9), make_pf(g, n, seed=9)
+    pf.enable_graphs()
+    rng, rng2 = numpy.random.default_rng(4), numpy.random.default_rng(4)
+    for c in range(6):
+        a, b = _cycle(pf, rng), _cycle(eager, rng2)
+        assert numpy.allclose(a, b, rtol=1e-12 if c > 0 else 1e-6, atol=0)
+    assert pf.graph_replays >= 4
+    assert numpy.array_equal(pf.particles.get(), eager.particles.get())
