@@ -39,9 +39,11 @@ U_NOMINAL = numpy.array([0.06, 0.2])
 #   predict 4 R idx + 20 R + 20 W, update 8 R + 4 W, scan 4 R + 8 W, search 8 R + 4 W
 #   fused resample: 4 R loglik + 4 W ancestor index (the cumulative weights stay on chip); two-stage (GSE_RESAMPLE=unfused and
 #   the sharded path): scan 4 R + 8 W, search 8 R + 4 W
-STAGE_BYTES = {"predict": 44, "update": 12, "resample": 8, "scan": 12, "search": 12}
+#   predict + update as one kernel (the default when update() directly follows predict()): predict's 44 + 4 W loglik -- the
+#   two measured columns are not read back
+STAGE_BYTES = {"predict": 44, "update": 12, "predict+update": 48, "resample": 8, "scan": 12, "search": 12}
 # sharded run: the same, plus the all-gather of the shard totals ("offsets", no HBM traffic to speak of)
-STAGE_BYTES_SHARDED = {"predict": 44, "update": 12, "resample": 8}
+STAGE_BYTES_SHARDED = {"predict": 44, "update": 12, "predict+update": 48, "resample": 8}
 
 
 def workload_name(log2n):
@@ -69,6 +71,8 @@ def parse_args():
                     help="gsf: GS-UKF components/s at 2^--log2n components (BASELINE configs[3]; give --log2n 16)")
     ap.add_argument("--no-gsf", action="store_true", help="skip the GS-UKF sub-object of the default line")
     ap.add_argument("--graphs", action="store_true", help="CUDA-graph replay of the cycle (launch-bound sizes)")
+    ap.add_argument("--peer-buffers", action="store_true",
+                    help="single-GPU filter with its state in IPC-exportable memory (diagnostic for the sharded path)")
     ap.add_argument("--sharded", action="store_true",
                     help="use the sharded driver even on one GPU (profiling the peer-memory kernels under ncu)")
     return ap.parse_args()
@@ -370,7 +374,7 @@ def run_ours(args):
     elif args.workload == "gsf":
         pf = g.GaussianSumUnscentedKalmanFilter(f, gg, n_total, x0, state, meas, device=dev, seed=1234)
     else:
-        pf = g.ParticleFilter(f, gg, n_total, x0, state, meas, device=dev, seed=1234)
+        pf = g.ParticleFilter(f, gg, n_total, x0, state, meas, device=dev, seed=1234, peer=args.peer_buffers)
     if args.graphs:
         pf.enable_graphs()
     from gpu_se_b200.filter import _base
@@ -395,16 +399,18 @@ def run_ours(args):
         ev.record(stream)
         stage_events.append((label, ev))
 
+    fused_update = bool(pf._fuses_update())      # predict() is recorded and runs inside update()'s kernel
+
     def step(k, record):
         record = record and not args.graphs     # a graph replay is one launch: only the whole step can be timed
         if record:
             hook("start")
         pf.predict(us[k], DT)
-        if record:
+        if record and not fused_update:
             hook("predict")
         pf.update(us[k], zs[k])
         if record:
-            hook("update")
+            hook("predict+update" if fused_update else "update")
         pf._stage_hook = hook if record else None
         pf.resample(r=float(rs[k]))
         pf._stage_hook = None

@@ -79,6 +79,11 @@ SIGNATURES = {
     "gse_peer_close": (c_int, [c_int, c_vp]),
     "gse_resample_search_sharded": (c_int, [c_vp, c_shards_p, c_dbl, c_i64, c_i64, c_vp, c_vp]),
     "gse_gather_rows_sharded": (c_int, [c_vp, c_shards_p, c_vp, c_i64, c_vp, c_i64, c_int, c_vp]),
+    "gse_pf_can_fuse_update": (c_int, [c_vp, c_int, c_i64]),
+    "gse_pf_predict_update": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_dbl_p, c_dbl, c_int, c_u64, c_u64,
+                                      c_i64, c_dbl_p, c_vp, c_vp, c_vp, c_vp]),
+    "gse_pf_predict_update_sharded": (c_int, [c_vp, c_shards_p, c_vp, c_vp, c_i64, c_i64, c_dbl_p, c_dbl, c_int, c_u64,
+                                              c_u64, c_i64, c_dbl_p, c_vp, c_vp, c_vp, c_vp]),
     "gse_pf_predict_sharded": (c_int, [c_vp, c_shards_p, c_vp, c_vp, c_i64, c_i64, c_dbl_p, c_dbl, c_int, c_u64, c_u64,
                                        c_i64, c_vp, c_i64, c_vp]),
     "gse_pf_moments_sharded": (c_int, [c_vp, c_shards_p, c_vp, c_i64, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]),

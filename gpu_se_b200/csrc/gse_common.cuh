@@ -659,26 +659,28 @@ __device__ __forceinline__ unsigned int ld_status32(const unsigned int* p) {
     return v;
 }
 
-// The shard table arrives as a kernel parameter.  Indexing a parameter array with a run-time index makes the compiler
-// copy the whole struct to local memory, and staging it in shared memory puts a block barrier in front of every
-// short-lived CTA (measured: +30 us on the 2^24-row predict); so the owner of a row is SELECTED with compile-time
-// indices -- seven predicated moves per field.
+// The shard table arrives as a kernel parameter (__grid_constant__: its address can be taken).  Nearly every ancestor a
+// rank reads is one of its own rows -- the shards' weight totals are balanced -- so the table's "home" fields are tested
+// first (two compares); the search through the other shards sits in a function of its own so that it costs the hot path
+// no instructions and no registers.  (Inlined as a chain of selects it cost every thread ~60 instructions: +18 us on
+// the 2^24-row predict.  Indexing the parameter array in line makes the compiler copy the struct to local memory;
+// staging it in shared memory puts a block barrier in front of every short-lived CTA: +30 us.)
 struct ShardRef {
     const float* state;    // column 0, row 0 of the owning shard's buffer
     int64_t ld;
     int64_t row0, row1;    // the shard holds global rows [row0, row1)
 };
+static __device__ __noinline__ ShardRef shard_ref_search(const GatherShards* g, int64_t k) {
+    int t = 0;
+    for (int u = 1; u < g->nseg; ++u) t += (k >= g->seg_row[u]) ? 1 : 0;
+    ShardRef r;
+    r.state = g->state[t]; r.ld = g->ld[t]; r.row0 = g->seg_row[t]; r.row1 = g->seg_row[t + 1];
+    return r;
+}
 __device__ __forceinline__ ShardRef shard_ref(const GatherShards& g, int64_t k) {
     ShardRef r;
     r.state = g.home_state; r.ld = g.home_ld; r.row0 = g.home_row0; r.row1 = g.home_row1;
-    if (k >= r.row0 && k < r.row1) return r;                      // local: two compares, no look-up
-    r.state = g.state[0]; r.ld = g.ld[0]; r.row0 = g.seg_row[0]; r.row1 = g.seg_row[1];
-#pragma unroll
-    for (int t = 1; t < GSE_MAX_SHARDS; ++t) {
-        if (t < g.nseg && k >= g.seg_row[t]) {
-            r.state = g.state[t]; r.ld = g.ld[t]; r.row0 = g.seg_row[t]; r.row1 = g.seg_row[t + 1];
-        }
-    }
+    if (k < r.row0 || k >= r.row1) r = shard_ref_search(&g, k);
     return r;
 }
 // column 0 of global row k and the leading dimension of the shard that owns it

@@ -68,17 +68,35 @@ extern "C" int gse_mixture_draw(gse_ctx* ctx, const gse_mixture* mix, float* x_d
 // index into the shards of a multi-GPU population (peer memory)
 // ALIGNED: global row index0 + row0 of every thread is a multiple of four (one grouped draw serves the thread's rows);
 // always the case except for a shard that starts off a multiple of four
-template <bool DIAG, bool HOST_NOISE, bool ONE_STEP, int ND, int GMODE, bool ALIGNED, int MINB>
+// FUSE_ND >= 0: predict() immediately followed by update() (the filter loop of the reference, particle.py:265-294) as ONE
+// pass: the new rows are still in registers when their likelihood is evaluated, so the update neither re-reads the
+// two measured columns nor costs a launch.  The arithmetic is k_pf_update's, on the same float32 values it would read
+// back.  FUSE_ND = number of components of the measurement mixture (0: run-time loop).
+struct FusedUpdate {
+    float z0h, z0l, z1h, z1l;       // z split into float32 head and tail (gse_pf_update)
+    const float* loglik_in;         // accumulated log-likelihood, NULL: all zero (fresh resample)
+    float* loglik;
+    float* block_max;
+    float* block_sum;
+    unsigned int* ticket;
+    double* stats;
+};
+
+template <bool DIAG, bool HOST_NOISE, bool ONE_STEP, int ND, int GMODE, bool ALIGNED, int MINB, int FUSE_ND = -1>
 __global__ void __launch_bounds__(PF_THREADS, MINB)
 k_pf_predict(const float* xs, int64_t lds, const int32_t* __restrict__ idx, const __grid_constant__ GatherShards shards_arg,
              float* xd, int64_t ldd, int64_t n,
              ModelInputs in_arg, int n_sub, const __grid_constant__ MixSampler5 sp, uint32_t k0, uint32_t k1,
              uint32_t step, int64_t index0, const float* __restrict__ noise, int64_t ldn,
-             const gse_step_params* __restrict__ params) {
+             const gse_step_params* __restrict__ params, const __grid_constant__ FusedUpdate fu,
+             const __grid_constant__ MixDensity2f md) {
+    constexpr bool FUSE = FUSE_ND >= 0;
     const GatherShards& shards = shards_arg;
     const int64_t g = (int64_t)blockIdx.x * PF_THREADS + threadIdx.x;
-    const int64_t row0 = g * ROWS_PER_THREAD;
-    if (row0 >= n) return;
+    // (fused: every thread reaches the block reduction; a thread past the end recomputes the last group and stores nothing)
+    const bool active = g * ROWS_PER_THREAD < n;
+    if (!FUSE && !active) return;
+    const int64_t row0 = active ? g * ROWS_PER_THREAD : ((n - 1) >> 2) * ROWS_PER_THREAD;
     const ModelInputs in = model_inputs(in_arg, params, ONE_STEP ? 1 : n_sub);
     if (params) step = (uint32_t)params->step;
     float v[5][4];
@@ -171,15 +189,101 @@ k_pf_predict(const float* xs, int64_t lds, const int32_t* __restrict__ idx, cons
 #pragma unroll
         for (int j = 0; j < 5; ++j) v[j][r] = __fadd_rn(xv[j], e[j]);      // particles += draw(N)   (:67)
     }
+    if (!FUSE || active) {
 #pragma unroll
-    for (int j = 0; j < 5; ++j)
-        st_stream4(xd + j * ldd + row0, make_float4(v[j][0], v[j][1], v[j][2], v[j][3]));
+        for (int j = 0; j < 5; ++j)
+            st_stream4(xd + j * ldd + row0, make_float4(v[j][0], v[j][1], v[j][2], v[j][3]));
+    }
+    if (FUSE) {
+        float z0h = fu.z0h, z0l = fu.z0l, z1h = fu.z1h, z1l = fu.z1l;
+        if (params) {
+            z0h = (float)params->z[0];
+            z1h = (float)params->z[1];
+            z0l = (float)(params->z[0] - (double)z0h);
+            z1l = (float)(params->z[1] - (double)z1h);
+        }
+        float4 lw = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (fu.loglik_in) lw = ld_stream4(fu.loglik_in + row0);
+        const float l[4] = {lw.x, lw.y, lw.z, lw.w};
+        float vals[4];
+        bool valid[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const float e0 = __fadd_rn(__fsub_rn(z0h, output_glucose(v[0][r])), z0l);   // e = z - y   (:82)
+            const float e1 = __fadd_rn(__fsub_rn(z1h, output_fa(v[2][r])), z1l);
+            vals[r] = l[r] + meas_logpdf32<(FUSE ? FUSE_ND : 0)>(md, e0, e1);           // weights[i] *= pdf(e)  (:83)
+            valid[r] = active && row0 + r < n;
+        }
+        if (active) st_stream4(fu.loglik + row0, make_float4(vals[0], vals[1], vals[2], vals[3]));
+        // (max, sum exp) of the CTA's 1024 rows -> block_max / block_sum; k_merge_block_stats folds them into stats.
+        // No ticket here: a CTA lives for a few microseconds, and waiting out an atomic's round trip at the end of
+        // each (the way the persistent update kernel finds its last block) cost 25 % of the kernel.
+        MaxSumExp acc;
+        acc.add<4>(vals, valid);
+        __shared__ float s_m[PF_THREADS / 32], s_s[PF_THREADS / 32];
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        const float wm = warp_max(acc.m);
+        const float ws = warp_sum(acc.m > -INFINITY ? acc.s * fast_exp(acc.m - wm) : 0.0f);
+        if (lane == 0) { s_m[wid] = wm; s_s[wid] = ws; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float bm = s_m[0];
+#pragma unroll
+            for (int w = 1; w < PF_THREADS / 32; ++w) bm = fmaxf(bm, s_m[w]);
+            float bs = 0.0f;
+#pragma unroll
+            for (int w = 0; w < PF_THREADS / 32; ++w) bs += s_m[w] > -INFINITY ? s_s[w] * fast_exp(s_m[w] - bm) : 0.0f;
+            fu.block_max[blockIdx.x] = bm;
+            fu.block_sum[blockIdx.x] = bs;
+        }
+    }
+}
+
+// stats[0..1] = (M, S) from nblocks (max, sum exp) pairs: fixed order per thread, then a fixed tree, in float64
+__global__ void __launch_bounds__(1024)
+k_merge_block_stats(const float* __restrict__ block_max, const float* __restrict__ block_sum, unsigned int nblocks,
+                    double* stats) {
+    __shared__ float s_red[32];
+    __shared__ double s_dred[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float gm = -INFINITY;
+    for (unsigned int b = threadIdx.x; b < nblocks; b += 1024) gm = fmaxf(gm, block_max[b]);
+    gm = warp_max(gm);
+    if (lane == 0) s_red[wid] = gm;
+    __syncthreads();
+    float M = s_red[lane];
+    M = warp_max(M);
+    double acc = 0.0;
+    for (unsigned int b = threadIdx.x; b < nblocks; b += 1024) {
+        const float bmx = block_max[b];
+        if (bmx > -INFINITY) acc += (double)block_sum[b] * (double)fast_exp(bmx - M);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) s_dred[wid] = acc;
+    __syncthreads();
+    if (wid == 0) {
+        double t = s_dred[lane];
+        t = warp_sum(t);
+        if (lane == 0) { stats[0] = (double)M; stats[1] = t; }
+    }
+}
+
+// Can predict + update run as one pass?  Only the benchmark's specialisation is built fused: diagonal two-component state
+// noise from the in-kernel Philox stream, one Euler step, a shard that starts at a multiple of four rows, two-component
+// measurement mixture.
+static bool can_fuse_update(const gse_ctx* ctx, int n_sub, int64_t index0) {
+    return ctx->state_sampler.diag && ctx->state_sampler.nd == 2 && n_sub == 1 && (index0 & 3) == 0 &&
+           ctx->meas_density32.nd == 2 && ctx->predict_minb == 4;
+}
+
+extern "C" int gse_pf_can_fuse_update(const gse_ctx* ctx, int n_sub, int64_t index0) {
+    return (ctx != NULL && can_fuse_update(ctx, n_sub, index0)) ? 1 : 0;
 }
 
 static int launch_predict(gse_ctx* ctx, const float* x_src_dev, int64_t ld_src, const int32_t* idx_dev,
                           const GatherShards* shards, bool sharded, float* x_dst_dev, int64_t ld_dst, int64_t n,
                           const double u[GSE_NU], double dt, int n_sub, uint64_t seed, uint64_t step, int64_t index0,
-                          const float* noise_dev, int64_t ld_noise, void* stream) {
+                          const float* noise_dev, int64_t ld_noise, void* stream, const FusedUpdate* fuse = NULL) {
     GSE_REQUIRE(ctx != NULL && u != NULL, "ctx / u is NULL");
     gse_device_guard guard(ctx->device);
     GSE_REQUIRE(n >= 0 && n <= ctx->n_max, "n out of range for this context");
@@ -203,10 +307,28 @@ static int launch_predict(gse_ctx* ctx, const float* x_src_dev, int64_t ld_src, 
     const unsigned blocks = (unsigned)gse_div_up(groups, PF_THREADS);
     cudaStream_t s = (cudaStream_t)stream;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    FusedUpdate fu_none;
+    memset(&fu_none, 0, sizeof(fu_none));
+    if (fuse) {
+        GSE_REQUIRE(noise_dev == NULL && can_fuse_update(ctx, n_sub, index0), "this configuration has no fused predict + update");
+        GSE_REQUIRE((int64_t)blocks <= ctx->max_blocks, "workspace too small");
+#define LAUNCH_FUSED(GMODE)                                                                                      \
+    k_pf_predict<true, false, true, 2, GMODE, true, 4, 2><<<blocks, PF_THREADS, 0, s>>>(                         \
+        x_src_dev, ld_src, idx_dev, *shards, x_dst_dev, ld_dst, n, in, n_sub, ctx->state_sampler, k0, k1,        \
+        (uint32_t)step, index0, noise_dev, ld_noise, ctx->step_params, *fuse, ctx->meas_density32)
+        if (sharded) LAUNCH_FUSED(2);
+        else if (idx_dev) LAUNCH_FUSED(1);
+        else LAUNCH_FUSED(0);
+#undef LAUNCH_FUSED
+        GSE_CHECK_LAUNCH(ctx);
+        k_merge_block_stats<<<1, 1024, 0, s>>>(fuse->block_max, fuse->block_sum, blocks, fuse->stats);
+        GSE_CHECK_LAUNCH(ctx);
+        return GSE_OK;
+    }
 #define LAUNCH_PREDICT_GAM(DIAG, HOST, ONE, ND, GMODE, AL, MB)                                                   \
     k_pf_predict<DIAG, HOST, ONE, ND, GMODE, AL, MB><<<blocks, PF_THREADS, 0, s>>>(                              \
         x_src_dev, ld_src, idx_dev, *shards, x_dst_dev, ld_dst, n, in, n_sub, ctx->state_sampler, k0, k1,        \
-        (uint32_t)step, index0, noise_dev, ld_noise, ctx->step_params)
+        (uint32_t)step, index0, noise_dev, ld_noise, ctx->step_params, fu_none, ctx->meas_density32)
 // The benchmark's specialisation (diagonal two-component noise, one Euler step, aligned rows) runs at 4 CTAs per SM
 // (64 registers): measured at 2^24 rows 132 us against 139 us at 5 CTAs (48 registers) and 143 us at 6 (40, spills);
 // GSE_PREDICT_MINB=5 selects the 48-register build for comparison.  (Tying the gather addresses to the first Philox call
@@ -262,6 +384,53 @@ extern "C" int gse_pf_predict_sharded(gse_ctx* ctx, const gse_shards* shards, co
     if (rc) return rc;
     return launch_predict(ctx, NULL, 0, idx_dev, &g, true, x_dst_dev, ld_dst, n, u, dt, n_sub, seed, step, index0,
                           noise_dev, ld_noise, stream);
+}
+
+static int fill_fused_update(gse_ctx* ctx, int64_t n, const double z[GSE_NY], const float* loglik_in_dev, float* loglik_dev,
+                             double* stats_dev, FusedUpdate* fu) {
+    GSE_REQUIRE(ctx != NULL && z != NULL && stats_dev != NULL, "ctx / z / stats is NULL");
+    GSE_REQUIRE(n >= 1, "n out of range for this context");
+    GSE_REQUIRE(loglik_dev != NULL && aligned16(loglik_dev), "loglik must be 16-byte aligned");
+    GSE_REQUIRE(loglik_in_dev == NULL || aligned16(loglik_in_dev), "loglik_in must be 16-byte aligned");
+    fu->z0h = (float)z[0];
+    fu->z1h = (float)z[1];
+    fu->z0l = (float)(z[0] - (double)fu->z0h);
+    fu->z1l = (float)(z[1] - (double)fu->z1h);
+    fu->loglik_in = loglik_in_dev;
+    fu->loglik = loglik_dev;
+    fu->block_max = ctx->block_max;
+    fu->block_sum = ctx->block_sum;
+    fu->ticket = ctx->ticket;
+    fu->stats = stats_dev;
+    return GSE_OK;
+}
+
+extern "C" int gse_pf_predict_update(gse_ctx* ctx, const float* x_src_dev, int64_t ld_src, const int32_t* idx_dev,
+                                     float* x_dst_dev, int64_t ld_dst, int64_t n, const double u[GSE_NU], double dt,
+                                     int n_sub, uint64_t seed, uint64_t step, int64_t index0, const double z[GSE_NY],
+                                     const float* loglik_in_dev, float* loglik_dev, double* stats_dev, void* stream) {
+    FusedUpdate fu;
+    int rc = fill_fused_update(ctx, n, z, loglik_in_dev, loglik_dev, stats_dev, &fu);
+    if (rc) return rc;
+    GatherShards none;
+    memset(&none, 0, sizeof(none));
+    return launch_predict(ctx, x_src_dev, ld_src, idx_dev, &none, false, x_dst_dev, ld_dst, n, u, dt, n_sub, seed, step,
+                          index0, NULL, 0, stream, &fu);
+}
+
+extern "C" int gse_pf_predict_update_sharded(gse_ctx* ctx, const gse_shards* shards, const int32_t* idx_dev,
+                                             float* x_dst_dev, int64_t ld_dst, int64_t n, const double u[GSE_NU],
+                                             double dt, int n_sub, uint64_t seed, uint64_t step, int64_t index0,
+                                             const double z[GSE_NY], const float* loglik_in_dev, float* loglik_dev,
+                                             double* stats_dev, void* stream) {
+    FusedUpdate fu;
+    int rc = fill_fused_update(ctx, n, z, loglik_in_dev, loglik_dev, stats_dev, &fu);
+    if (rc) return rc;
+    GatherShards g;
+    rc = gse_build_gather_shards(shards, x_dst_dev, &g);
+    if (rc) return rc;
+    return launch_predict(ctx, NULL, 0, idx_dev, &g, true, x_dst_dev, ld_dst, n, u, dt, n_sub, seed, step, index0, NULL, 0,
+                          stream, &fu);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -167,8 +167,18 @@ class WeightedEnsemble:
             self._params = _lib.gse_step_params()
         self._graph_mode = bool(enable)
 
+    def _fuses_update(self):
+        """predict() directly followed by update() runs as ONE kernel (the rows never leave the registers in between)."""
+        return False
+
+    def _predict_update_now(self, u, dt, z):
+        raise NotImplementedError
+
     def predict(self, u, dt, noise=None):
-        if self._graph_mode and noise is None and not self._deferred and not hasattr(self.state_pdf, "draw_host"):
+        # recorded, not run: the call that follows decides whether it becomes part of a fused predict + update kernel
+        # (or of a graph replay); anything else first runs it on its own (_flush)
+        if ((self._graph_mode or self._fuses_update()) and noise is None and not self._deferred
+                and not hasattr(self.state_pdf, "draw_host")):
             self._deferred = [("predict", (float(u[0]), float(u[1])), float(dt))]      # values, not references
             return
         self._flush()
@@ -178,6 +188,10 @@ class WeightedEnsemble:
         if self._graph_mode and len(self._deferred) == 1:
             self._deferred.append(("update", (float(u[0]), float(u[1])), (float(z[0]), float(z[1]))))
             return
+        if len(self._deferred) == 1 and self._fuses_update():
+            (_, up, dt), self._deferred = self._deferred[0], []
+            self._predict_update_now(up, dt, (float(z[0]), float(z[1])))
+            return
         self._flush()
         self._update_now(u, z)
 
@@ -185,6 +199,9 @@ class WeightedEnsemble:
         """Run the recorded calls eagerly (something other than the graphed cycle is happening)."""
         if self._deferred:
             ops, self._deferred = self._deferred, []
+            if len(ops) == 2 and self._fuses_update():
+                self._predict_update_now(ops[0][1], ops[0][2], ops[1][2])
+                return
             for op in ops:
                 if op[0] == "predict":
                     self._predict_now(op[1], op[2], None)
@@ -212,8 +229,11 @@ class WeightedEnsemble:
             g = torch.cuda.CUDAGraph()
             try:
                 with torch.cuda.graph(g):
-                    self._predict_now(u, dt, None)
-                    self._update_now(u, z)
+                    if self._fuses_update():
+                        self._predict_update_now(u, dt, z)
+                    else:
+                        self._predict_now(u, dt, None)
+                        self._update_now(u, z)
                     self._resample_now(r, False)
             finally:
                 _lib.check(_lib.lib.gse_ctx_use_step_params(self._ctx.handle, 0))

@@ -7,6 +7,8 @@ hand-written sm_100a kernels in csrc/ (through the C ABI of include/gse.h).
 Particles live on the device as SoA float32 columns ``(5, ld)``; the ``particles`` attribute is the
 ``(N, 5)`` transposed view.  See filter/_base.py for the weight representation.
 """
+import os
+
 import numpy
 import torch
 
@@ -39,6 +41,7 @@ class ParallelParticleFilter(WeightedEnsemble):
         self._init_ensemble(N_particles, state_pdf, measurement_pdf, device, seed, workspace_rows, peer)
         self._index0 = int(index0)     # global index of local row 0 (sharded runs): keys the Philox stream
         self._n_sub = int(n_sub)
+        self._fuse = None              # predict + update as one kernel: asked of the library on first use
         n = self.N_particles
         if particles is not None:
             self.particles = particles
@@ -95,6 +98,32 @@ class ParallelParticleFilter(WeightedEnsemble):
             self._pending = False
         self._step += 1
         self._touch()
+
+    def _fuses_update(self):
+        """predict + update as one kernel.  Built, tested bit-identical to the two kernels, and OFF by default: at 2^24
+        rows it takes 177 us + a 4 us merge against 136 + 47 us for the two -- the update is bound by instruction issue
+        (log-pdf, max / sum-exp), which fusing does not remove, and predict has no issue slots to spare (DESIGN.md
+        section 4).  GSE_FUSE_UPDATE=1 turns it on (it saves the re-read of the two measured columns: 8 B per row)."""
+        if self._fuse is None:
+            self._fuse = os.environ.get("GSE_FUSE_UPDATE", "0") == "1" and self.can_fuse_update()
+        return self._fuse
+
+    def can_fuse_update(self):
+        return bool(_lib.lib.gse_pf_can_fuse_update(self._ctx.handle, self._n_sub, self._index0))
+
+    def _predict_update_now(self, u, dt, z):
+        """predict (particle.py:265-277) and update (:279-294) in one pass over the rows."""
+        n = self.N_particles
+        dst = self._state_alt if self._pending else self._state
+        _lib.check(_lib.lib.gse_pf_predict_update(
+            self._ctx.handle, self._state.data_ptr(), self._ld, self._idx_ptr(), dst.data_ptr(), self._ld, n,
+            _lib.as_double2(u), float(dt), self._n_sub, self._seed, self._step, self._index0, _lib.as_double2(z),
+            self._loglik_ptr(), self._loglik.data_ptr(), self._stats.data_ptr(), self._stream()))
+        if self._pending:
+            self._state, self._state_alt = self._state_alt, self._state
+            self._pending = False
+        self._step += 1
+        self._after_update()
 
     def _update_now(self, u, z):
         """particle.py:279-294."""

@@ -181,6 +181,7 @@ class _ShardedEnsemble:
         self.exchanged_rows = 0
         self._stage_hook = None
         self._want_cov = False
+        self._deferred_predict = None        # (u, dt) of a predict that may still fuse with the update that follows
 
     # -- peer memory -----------------------------------------------------------------------------
     def _open_peers(self):
@@ -233,6 +234,7 @@ class _ShardedEnsemble:
 
     def close(self):
         """Unmap the other ranks' buffers (collective: every rank must call it before any frees its own)."""
+        self._flush()
         if getattr(self, "_mappings", None):
             torch.cuda.synchronize(self.device)
             dist.barrier(group=self.group)
@@ -268,6 +270,7 @@ class _ShardedEnsemble:
 
     def _materialise(self):
         """Apply a pending sharded resample: pull the ancestors' rows into this shard's other buffer."""
+        self._flush()
         if self._pending:
             loc = self.local
             sh = self._shards[self._parity]
@@ -302,10 +305,12 @@ class _ShardedEnsemble:
 
     @property
     def weights(self):
+        self._flush()
         return self.local.weights
 
     def set_global_weights(self, w):
         """Assign weights from the full (N,) global array (every rank passes the same array)."""
+        self._flush()
         lo, hi = self.bounds[self.rank]
         w = numpy.ascontiguousarray(_device.to_numpy(w), dtype=numpy.float64).reshape(-1)
         if w.size != self.N_particles:
@@ -337,15 +342,35 @@ class _ShardedEnsemble:
     def _noise_rows(self, noise):
         raise NotImplementedError
 
+    def _fuses_update(self):
+        return False
+
+    def _predict_update_pending(self, u, dt, z):
+        raise NotImplementedError
+
+    def _flush(self):
+        """Run a recorded predict on its own: something other than ``update`` followed it."""
+        d, self._deferred_predict = self._deferred_predict, None
+        if d is not None:
+            self._predict_now(d[0], d[1], None)
+
     def predict(self, u, dt, noise=None):
+        self._flush()
+        if noise is None and self._fuses_update() and not hasattr(self.local.state_pdf, "draw_host"):
+            self._deferred_predict = ((float(u[0]), float(u[1])), float(dt))
+            return
+        self._predict_now(u, dt, noise)
+
+    def _predict_now(self, u, dt, noise):
         lo, hi = self.bounds[self.rank]
         if noise is not None:
             noise = _device.to_numpy(noise)[lo:hi]
+        loc = self.local
         if not self._pending:
-            self.local.predict(u, dt, noise=noise)
+            loc._flush()
+            loc._predict_now(u, dt, noise)
             return
         # pending sharded resample: read row idx[i] out of whichever GPU holds it, write the other buffer
-        loc = self.local
         nz_ptr, ld_nz, keep = self._noise_rows(noise)
         self._predict_pending(u, dt, nz_ptr, ld_nz)
         del keep
@@ -353,12 +378,27 @@ class _ShardedEnsemble:
         self._swap()
 
     def update(self, u, z):
-        self._materialise()
-        self.local.update(u, z)
+        d, self._deferred_predict = self._deferred_predict, None
+        loc = self.local
+        if d is not None:
+            # predict + update in one pass over the rows (through the pending ancestor index, if there is one)
+            if self._pending:
+                self._predict_update_pending(d[0], d[1], z)
+                loc._step += 1
+                self._swap()
+                loc._after_update()
+            else:
+                loc._flush()
+                loc._predict_update_now(d[0], d[1], (float(z[0]), float(z[1])))
+        else:
+            self._materialise()
+            loc._flush()
+            loc._update_now(u, z)
         self._allreduce_stats()
 
     def resample(self, r=None, return_index=False):
         loc = self.local
+        self._flush()
         self._materialise()
         if r is None:
             rt = torch.tensor([numpy.random.rand()], dtype=torch.float64, device=self.device)
@@ -420,6 +460,7 @@ class _ShardedEnsemble:
     def _global_moments(self, need_cov=True):
         """(mom, S0, S1, S2, p, A) of the WHOLE population, identical on every rank."""
         loc = self.local
+        self._flush()
         if need_cov:
             self._want_cov = True
         mean_only = not (need_cov or self._want_cov)
@@ -520,6 +561,17 @@ class ShardedParticleFilter(_ShardedEnsemble):
                                                    loc._state_alt.data_ptr(), loc._ld, loc.N_particles,
                                                    _lib.as_double2(u), float(dt), loc._n_sub, loc._seed, loc._step,
                                                    loc._index0, nz_ptr, ld_nz, loc._stream()))
+
+    def _fuses_update(self):
+        return self.exchange == "peer" and self.local._fuses_update()
+
+    def _predict_update_pending(self, u, dt, z):
+        loc = self.local
+        sh = self._shards[self._parity]
+        _lib.check(_lib.lib.gse_pf_predict_update_sharded(
+            loc._ctx.handle, ctypes.byref(sh), self._idx_global.data_ptr(), loc._state_alt.data_ptr(), loc._ld,
+            loc.N_particles, _lib.as_double2(u), float(dt), loc._n_sub, loc._seed, loc._step, loc._index0,
+            _lib.as_double2(z), loc._loglik_ptr(), loc._loglik.data_ptr(), loc._stats.data_ptr(), loc._stream()))
 
     def _launch_local_moments(self, mean_only):
         loc = self.local

@@ -327,6 +327,24 @@ int gse_peer_allgather_moments(gse_ctx* ctx, void* const mailboxes[GSE_MAX_SHARD
  * pairs_dev[2 s .. 2 s + 1] = (M_s, S_s) written by each shard's update kernel. */
 int gse_merge_stats(gse_ctx* ctx, const double* pairs_dev, int nshards, double* stats_dev, void* stream);
 
+/* predict() directly followed by update() -- the filter loop of the reference, particle.py:265-294 -- as ONE pass:
+ * gse_pf_predict's arguments, then gse_pf_update's (z, loglik_in_dev or NULL when the accumulated log-likelihood is all
+ * zero, loglik_dev, stats_dev).  The new rows are still in registers when their likelihood is evaluated; rows and
+ * log-likelihoods are bit-identical to the two separate calls, stats_dev[1] differs in the last float32 bits (other
+ * partition of the sum).  Built for the benchmark's specialisation only: gse_pf_can_fuse_update() says whether this
+ * context / n_sub / index0 has it (diagonal two-component state noise, one Euler step, index0 a multiple of four,
+ * two-component measurement mixture); callers fall back to the two calls otherwise. */
+int gse_pf_can_fuse_update(const gse_ctx* ctx, int n_sub, int64_t index0);
+int gse_pf_predict_update(gse_ctx* ctx, const float* x_src_dev, int64_t ld_src, const int32_t* idx_dev, float* x_dst_dev,
+                          int64_t ld_dst, int64_t n, const double u[GSE_NU], double dt, int n_sub, uint64_t seed,
+                          uint64_t step, int64_t index0, const double z[GSE_NY], const float* loglik_in_dev,
+                          float* loglik_dev, double* stats_dev, void* stream);
+/* ... reading its rows through the global ancestor index of a sharded population (gse_pf_predict_sharded) */
+int gse_pf_predict_update_sharded(gse_ctx* ctx, const gse_shards* shards, const int32_t* idx_dev, float* x_dst_dev,
+                                  int64_t ld_dst, int64_t n, const double u[GSE_NU], double dt, int n_sub, uint64_t seed,
+                                  uint64_t step, int64_t index0, const double z[GSE_NY], const float* loglik_in_dev,
+                                  float* loglik_dev, double* stats_dev, void* stream);
+
 /* gse_pf_predict / gse_pf_moments reading row idx[i] (GLOBAL ancestor row from
  * gse_resample_search_sharded) straight out of the owning shard's memory: the lazy resample of a
  * sharded population -- the rows cross NVLink inside the kernel that consumes them. */

@@ -97,6 +97,9 @@ def _worker(rank, world, port, n, exchange, kind, q):
         sharded_cls = ShardedGaussianSumUnscentedKalmanFilter if gsf else ShardedParticleFilter
         single_cls = g.GaussianSumUnscentedKalmanFilter if gsf else g.ParticleFilter
         spf = sharded_cls(f, gg, n, x0, state, meas, device=dev, seed=77, exchange=exchange)
+        if kind == "pf_fused":                 # predict + update as one kernel through the global ancestor index
+            assert spf.local.can_fuse_update()
+            spf.local._fuse = True
         est_only = kind == "pf_estimates"
         if est_only:
             got = _run_estimates(spf, 5, seed=3)
@@ -167,6 +170,19 @@ def _launch(world, n, exchange, kind="pf"):
 @pytest.mark.parametrize("n", [4096, 100003])
 def test_world1_equals_single_gpu(n, exchange):
     _launch(1, n, exchange)
+
+
+@pytest.mark.parametrize("n", [4096, 300007])
+def test_world1_fused_predict_update(n):
+    _launch(1, n, "peer", kind="pf_fused")
+
+
+@pytest.mark.parametrize("world,n", [(2, 1000003), (4, 1000003)])
+def test_worldN_fused_predict_update(world, n):
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    _launch(world, n, "peer", kind="pf_fused")
 
 
 @pytest.mark.parametrize("n", [4096, 300007])
