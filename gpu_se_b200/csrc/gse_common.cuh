@@ -160,6 +160,8 @@ struct GatherShards {
     // are balanced), and these fields are read without any look-up
     const float* home_state;
     int64_t home_ld, home_row0, home_row1;
+    const float* home_base;        // home_state - home_row0: row k of the home shard is home_base[k] (k a GLOBAL index)
+    int home_lo, home_hi;          // home_row0 / home_row1 as int32 (ancestor indices are int32)
 };
 
 static inline int gse_build_gather_shards(const gse_shards* sh, const void* dst, GatherShards* g) {
@@ -177,6 +179,9 @@ static inline int gse_build_gather_shards(const gse_shards* sh, const void* dst,
     g->home_ld = g->ld[home];
     g->home_row0 = g->seg_row[home];
     g->home_row1 = g->seg_row[home + 1];
+    g->home_base = (const float*)((uintptr_t)g->home_state - (uintptr_t)g->home_row0 * sizeof(float));
+    g->home_lo = (int)g->home_row0;
+    g->home_hi = (int)g->home_row1;
     return GSE_OK;
 }
 
@@ -692,10 +697,9 @@ __device__ __forceinline__ const float* shard_row(const GatherShards& g, int64_t
 
 // four rows with non-decreasing global indices: one look-up serves all four unless they straddle a shard boundary
 __device__ __forceinline__ void shard_rows4(const GatherShards& g, const int id[4], const float* q[4], int64_t l[4]) {
-    const ShardRef own = shard_ref(g, id[0]);
-    if (id[3] < own.row1) {
+    if (id[0] >= g.home_lo && id[3] < g.home_hi) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) { q[r] = own.state + (id[r] - own.row0); l[r] = own.ld; }
+        for (int r = 0; r < 4; ++r) { q[r] = g.home_base + id[r]; l[r] = g.home_ld; }
     } else {
 #pragma unroll
         for (int r = 0; r < 4; ++r) q[r] = shard_row(g, id[r], l[r]);

@@ -99,30 +99,54 @@ k_pf_predict(const float* xs, int64_t lds, const int32_t* __restrict__ idx, cons
     const int64_t row0 = active ? g * ROWS_PER_THREAD : ((n - 1) >> 2) * ROWS_PER_THREAD;
     const ModelInputs in = model_inputs(in_arg, params, ONE_STEP ? 1 : n_sub);
     if (params) step = (uint32_t)params->step;
+    // process noise of the four rows: one grouped draw (six Philox calls) when the rows are a whole group of
+    // the global index space -- always, unless a shard starts off a multiple of four
+    float e4[4][5];
+    if (!HOST_NOISE) {
+        const uint64_t r0g = (uint64_t)(index0 + row0);
+        if (ALIGNED) {
+            draw_mixture5_x4<DIAG, ND>(sp, r0g >> 2, step, k0, k1, e4);
+        } else {
+            // (fully unrolled: a loop over r would index e4 dynamically and push it into local memory)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                float g4[4][5];
+                draw_mixture5_x4<DIAG, ND>(sp, (r0g + r) >> 2, step, k0, k1, g4);
+                const int l = (int)((r0g + r) & 3ull);
+#pragma unroll
+                for (int j = 0; j < 5; ++j) e4[r][j] = l == 0 ? g4[0][j] : (l == 1 ? g4[1][j] : (l == 2 ? g4[2][j] : g4[3][j]));
+            }
+        }
+    }
     float v[5][4];
     if (GMODE == 2) {
         const int4 id4 = *reinterpret_cast<const int4*>(idx + row0);
         const int id[4] = {id4.x, (row0 + 1 < n) ? id4.y : id4.x, (row0 + 2 < n) ? id4.z : id4.x,
                            (row0 + 3 < n) ? id4.w : id4.x};
-        // idx is non-decreasing: when the first and the last ancestor sit in one shard (all but a
-        // handful of threads) one look-up serves the four rows
-        const ShardRef own = shard_ref(shards, id[0]);
-        if (id[3] < own.row1) {
-            // (same access pattern as GMODE 1: read-only loads, one column at a time)
-            const int64_t ld0 = own.ld;
-            const float* base = own.state - own.row0;
+        // idx is non-decreasing, and nearly every ancestor is one of this rank's own rows (two int32 compares).  The home
+        // shard is read WITHOUT a branch -- the very loads of GMODE 1, home_base indexed by the GLOBAL row, clamped to a
+        // valid row for the few threads whose ancestors live elsewhere -- so that the compiler schedules them, like GMODE
+        // 1's, after the Philox rounds that hide the latency of the index load.  (With the loads behind a branch on the
+        // index every warp sat out that latency: +18 us at 2^24 rows.)  The other threads then fetch their rows through
+        // the shard table, out of line.
+        const bool home = id[0] >= shards.home_lo && id[3] < shards.home_hi;
+        {
+            const float* base = shards.home_base;
+            const int64_t ld0 = shards.home_ld;
 #pragma unroll
             for (int j = 0; j < 5; ++j) {
 #pragma unroll
-                for (int r = 0; r < 4; ++r) v[j][r] = __ldg(base + j * ld0 + id[r]);
+                for (int r = 0; r < 4; ++r) v[j][r] = __ldg(base + j * ld0 + (home ? id[r] : shards.home_lo));
             }
-        } else {
+        }
+        if (!home) {
+            // (fully unrolled: a loop over r would index id[] dynamically and park it in local memory for EVERY thread)
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-                int64_t ld;
-                const float* p = shard_row(shards, id[r], ld);
+                const ShardRef own = shard_ref_search(&shards, id[r]);
+                const float* p = own.state + (id[r] - own.row0);
 #pragma unroll
-                for (int j = 0; j < 5; ++j) v[j][r] = p[j * ld];
+                for (int j = 0; j < 5; ++j) v[j][r] = p[j * own.ld];
             }
         }
     } else if (GMODE == 1) {
@@ -148,25 +172,6 @@ k_pf_predict(const float* xs, int64_t lds, const int32_t* __restrict__ idx, cons
     if (HOST_NOISE) {
 #pragma unroll
         for (int j = 0; j < 5; ++j) nz[j] = ld_stream4(noise + j * ldn + row0);
-    }
-    // process noise of the four rows: one grouped draw (six Philox calls) when the rows are a whole group of
-    // the global index space -- always, unless a shard starts off a multiple of four
-    float e4[4][5];
-    if (!HOST_NOISE) {
-        const uint64_t r0g = (uint64_t)(index0 + row0);
-        if (ALIGNED) {
-            draw_mixture5_x4<DIAG, ND>(sp, r0g >> 2, step, k0, k1, e4);
-        } else {
-            // (fully unrolled: a loop over r would index e4 dynamically and push it into local memory)
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                float g4[4][5];
-                draw_mixture5_x4<DIAG, ND>(sp, (r0g + r) >> 2, step, k0, k1, g4);
-                const int l = (int)((r0g + r) & 3ull);
-#pragma unroll
-                for (int j = 0; j < 5; ++j) e4[r][j] = l == 0 ? g4[0][j] : (l == 1 ? g4[1][j] : (l == 2 ? g4[2][j] : g4[3][j]));
-            }
-        }
     }
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
@@ -371,6 +376,16 @@ extern "C" int gse_pf_predict(gse_ctx* ctx, const float* x_src_dev, int64_t ld_s
                               int64_t ld_noise, void* stream) {
     GatherShards none;
     memset(&none, 0, sizeof(none));
+    static const bool force_table = getenv("GSE_DEBUG_PREDICT_TABLE") != NULL;     // A/B of the sharded read path on one GPU
+    if (force_table && idx_dev != NULL) {
+        none.nseg = 1;
+        none.seg_row[0] = 0; none.seg_row[1] = n;
+        none.state[0] = x_src_dev; none.ld[0] = ld_src;
+        none.home_state = x_src_dev; none.home_ld = ld_src; none.home_row0 = 0; none.home_row1 = n;
+        none.home_base = x_src_dev; none.home_lo = 0; none.home_hi = (int)n;
+        return launch_predict(ctx, NULL, 0, idx_dev, &none, true, x_dst_dev, ld_dst, n, u, dt, n_sub, seed, step, index0,
+                              noise_dev, ld_noise, stream);
+    }
     return launch_predict(ctx, x_src_dev, ld_src, idx_dev, &none, false, x_dst_dev, ld_dst, n, u, dt, n_sub, seed, step,
                           index0, noise_dev, ld_noise, stream);
 }
