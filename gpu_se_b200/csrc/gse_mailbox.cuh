@@ -64,6 +64,55 @@ __device__ __forceinline__ void mbox_exchange(const MailboxTable& mb, int rank, 
     }
 }
 
+// barrier without a payload: "everything I wrote before my system-scope fence is out" / wait until every peer has said
+// the same.  The CALLER issues the one __threadfence_system() before it; nothing is read afterwards, so no acquire fence.
+__device__ __forceinline__ void mbox_signal_wait(const MailboxTable& mb, int rank, int nshards, unsigned int epoch, int lane,
+                                                 unsigned int* err) {
+    if (lane < nshards) {
+        *(volatile unsigned int*)(mbox_slot(mb, lane, rank, epoch) + MBOX_FLAG_WORD) = epoch;
+        volatile unsigned long long* src = mbox_slot(mb, rank, lane, epoch);
+        const unsigned long long t0 = mbox_timer_ns();
+        unsigned int spins = 0;
+        while (*(volatile unsigned int*)(src + MBOX_FLAG_WORD) != epoch) {
+            __nanosleep(20);
+            if ((++spins & 1023u) == 0u && mbox_timer_ns() - t0 > GSE_MBOX_TIMEOUT_NS) {
+                if (err) atomicOr(err, GSE_ERR_PEER_TIMEOUT);
+                break;
+            }
+        }
+    }
+}
+
+// one 64-bit value per shard WITHOUT a fence: the value travels as two words that carry the epoch in their upper halves
+// (slot words 61 and 62, written by nothing else), each a single 8-byte store -- a reader that sees the epoch in both has
+// the value.  Saves the two system-scope fences of the generic exchange on the critical path of the fused resample.
+#define MBOX_TAGGED_WORD 61
+__device__ __forceinline__ void mbox_exchange_tagged(const MailboxTable& mb, int rank, int nshards, unsigned int epoch,
+                                                     unsigned long long value, int lane, unsigned long long& r0,
+                                                     unsigned int* err) {
+    r0 = 0;
+    if (lane < nshards) {
+        volatile unsigned long long* dst = mbox_slot(mb, lane, rank, epoch) + MBOX_TAGGED_WORD;
+        const unsigned long long tag = (unsigned long long)epoch << 32;
+        dst[0] = tag | (value & 0xffffffffull);
+        dst[1] = tag | (value >> 32);
+        volatile unsigned long long* src = mbox_slot(mb, rank, lane, epoch) + MBOX_TAGGED_WORD;
+        const unsigned long long t0 = mbox_timer_ns();
+        unsigned int spins = 0;
+        unsigned long long a = src[0], b = src[1];
+        while ((unsigned int)(a >> 32) != epoch || (unsigned int)(b >> 32) != epoch) {
+            __nanosleep(20);
+            if ((++spins & 1023u) == 0u && mbox_timer_ns() - t0 > GSE_MBOX_TIMEOUT_NS) {
+                if (err) atomicOr(err, GSE_ERR_PEER_TIMEOUT);
+                return;
+            }
+            a = src[0];
+            b = src[1];
+        }
+        r0 = (b << 32) | (a & 0xffffffffull);
+    }
+}
+
 // record of nwords <= MBOX_FLAG_WORD words, one warp: the warp writes the record to every peer in turn, then lane t
 // waits for peer t.  Afterwards the records of all shards sit in this rank's own mailbox (mbox_slot(mb, rank, t, epoch)).
 __device__ __forceinline__ void mbox_exchange_block(const MailboxTable& mb, int rank, int nshards, unsigned int epoch,

@@ -297,9 +297,10 @@ struct WarpFill {
         if (SHARDED) {
             // the window usually lies inside one shard's slots: two coalesced 128-bit stores into that shard's buffer
             // (over NVLink when it is a peer's); windows across a shard boundary or the sub-run's ends go element-wise
+            // (the home shard's bounds and buffer are kernel parameters: constant-bank operands, no shared-memory reads)
             const bool whole = wb >= mlo && wb + RF_WIN <= mhi;
-            if (whole && wb >= st->home_lo && wb + RF_WIN <= st->home_hi) {
-                int32_t* o = st->home_idx + (wb - st->home_lo) + 4 * lane;
+            if (whole && wb >= fa.out_home_lo && wb + RF_WIN <= fa.out_home_hi) {
+                int32_t* o = fa.idx_out + (wb - fa.out_home_lo) + 4 * lane;
                 *reinterpret_cast<int4*>(o) = a;
                 *reinterpret_cast<int4*>(o + 128) = b;
                 wb += RF_WIN;
@@ -535,8 +536,8 @@ k_resample_fused(const __grid_constant__ FusedArgs a) {
         if (SHARDED) {
             // the shards' totals cross NVLink here: exclusive offset of this shard and the global total
             if (wid == 0) {
-                unsigned long long r0, r1;
-                mbox_exchange(a.mb, a.rank, a.nshards, a.epoch_totals, local_total, 0ull, lane, r0, r1, a.err);
+                unsigned long long r0;
+                mbox_exchange_tagged(a.mb, a.rank, a.nshards, a.epoch_totals, local_total, lane, r0, a.err);
                 const uint64_t incl = warp_inclusive_scan_u64(r0, lane);
                 const uint64_t mine = __shfl_sync(0xffffffffu, incl - r0, a.rank);
                 const uint64_t all = __shfl_sync(0xffffffffu, incl, a.nshards - 1);
@@ -685,8 +686,7 @@ k_resample_fused(const __grid_constant__ FusedArgs a) {
             // and wait until they have said the same: when this kernel ends, this shard's index buffer is complete.
             if (wid == 0) {
                 __threadfence_system();
-                unsigned long long r0, r1;
-                mbox_exchange(a.mb, a.rank, a.nshards, a.epoch_done, 1ull, 0ull, lane, r0, r1, a.err);
+                mbox_signal_wait(a.mb, a.rank, a.nshards, a.epoch_done, lane, a.err);
             }
             __syncthreads();
         }

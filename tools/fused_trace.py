@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Per-CTA phase timing of the fused resample kernel (GSE_FUSED_TRACE=1): where the grid-wide waits go.
 
-    GSE_FUSED_TRACE=1 python tools/fused_trace.py [log2n]
+    GSE_FUSED_TRACE=1 python tools/fused_trace.py [log2n] [--sharded]     (--sharded: the one-rank sharded driver)
 """
 import ctypes
 import os
@@ -21,14 +21,26 @@ from gpu_se_b200.model.BioreactorModel import X_STEADY  # noqa: E402
 
 
 def main():
-    log2n = int(sys.argv[1]) if len(sys.argv) > 1 else 24
+    sharded = "--sharded" in sys.argv
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    log2n = int(args[0]) if args else 24
     n = 1 << log2n
     sm, sc = numpy.zeros((2, 5)), numpy.array([numpy.diag([1e-4, 1e-7, 1e-3, 1e-3, 1e-7]),
                                                numpy.diag([1e-3, 1e-6, 1e-2, 1e-2, 1e-6])])
     state = g.MultivariateGaussianSum(sm, sc, [0.75, 0.25])
     meas = g.MultivariateGaussianSum([[1e-1, 0], [0, -1e-1]], [[[6e-2, 0], [0, 8e-2]], [[500, 100], [100, 700]]], [0.85, 0.15])
     x0 = g.MultivariateGaussianSum(sm + numpy.array(X_STEADY)[None, :], sc, [0.75, 0.25])
-    pf = g.ParticleFilter(g.Bioreactor.homeostatic_DEs, g.Bioreactor.static_outputs, n, x0, state, meas, seed=1234)
+    if sharded:
+        import torch.distributed as dist
+        from gpu_se_b200.sharded import ShardedParticleFilter
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29577")
+        torch.cuda.set_device(0)
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+        pf = ShardedParticleFilter(g.Bioreactor.homeostatic_DEs, g.Bioreactor.static_outputs, n, x0, state, meas,
+                                   device=torch.device("cuda", 0), seed=1234)
+    else:
+        pf = g.ParticleFilter(g.Bioreactor.homeostatic_DEs, g.Bioreactor.static_outputs, n, x0, state, meas, seed=1234)
     us, zs = bench.trajectory(12, seed=7)
     buf = numpy.zeros(8 * 4096, dtype=numpy.uint64)
     for k in range(12):
@@ -59,6 +71,8 @@ def main():
               "phase3 mean %.1f min %.1f max %.1f | phase1 done at mean %.1f max %.1f | phase3 done at mean %.1f max %.1f us"
               % (k, len(t), rel[:, 0].max(), d1.mean(), d1.max(), d2.mean(), d2.max(), d3.mean(), d3.min(), d3.max(),
                  rel[:, 1].mean(), rel[:, 1].max(), rel[:, 3].mean(), rel[:, 3].max()))
+    if sharded:
+        pf.close()
 
 
 if __name__ == "__main__":
