@@ -52,8 +52,10 @@ def workload_name(log2n):
 
 
 # DRAM traffic per launch of each kernel at 2^24 particles (dram__bytes_read.sum + dram__bytes_write.sum of
-# the committed `ncu --set full` capture, profiles/r1_final_pf_step_2p24_ncu_full.csv), in bytes per row
-NCU_TRAFFIC_BYTES_PER_ROW = {"predict": (335.75e6 + 302.81e6) / 2 ** 24, "update": (134.23e6 + 30.44e6) / 2 ** 24,
+# the committed `ncu --set full` capture, profiles/r2_pf_step_2p24_ncu_full.csv; scan / search: the two-stage path,
+# profiles/r1_final_pf_step_2p24_ncu_full.csv), in bytes per row
+NCU_TRAFFIC_BYTES_PER_ROW = {"predict": (335.63e6 + 285.28e6) / 2 ** 24, "update": (134.24e6 + 31.28e6) / 2 ** 24,
+                             "resample": (91.94e6 + 21.66e6) / 2 ** 24,
                              "scan": (110.59e6 + 84.81e6) / 2 ** 24,
                              "search": (72.14e6 + 1.71e6 + 134.33e6 + 46.80e6) / 2 ** 24}
 
@@ -500,7 +502,7 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,
                      "traffic": (NCU_TRAFFIC_BYTES_PER_ROW[dom] * n_local if dom in NCU_TRAFFIC_BYTES_PER_ROW else None),
-                     "traffic_source": "ncu --set full capture at 2^24 rows (profiles/r1_final_pf_step_2p24_ncu_full.csv), "
+                     "traffic_source": "ncu --set full capture at 2^24 rows (profiles/r2_pf_step_2p24_ncu_full.csv), "
                                        "scaled by rows; per launch of the stage's kernels",
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_particle": STAGE_BYTES.get(dom),
@@ -599,7 +601,7 @@ def gsf_block(g, dev, pdfs, peak, with_cpu):
     n = big["components"]
     st = big.get("stages", {})
     hbm_ms = {k: GSF_STAGE_BYTES[k] * n / (peak * 1e9) * 1e3 for k in GSF_STAGE_BYTES}
-    # issue-slot floor: warp-instructions per component measured with ncu (profiles/r2_gsf_2p20_ncu.csv) at one
+    # issue-slot floor: warp-instructions per component measured with ncu (profiles/r2_gsf_2p20_ncu_full.csv) at one
     # instruction per SM sub-partition and clock: 148 SMs x 4 x 1.965 GHz
     issue_ms = {k: GSF_WARP_INSTR_PER_COMPONENT[k] * n / (148 * 4 * 1.965e9) * 1e3 for k in GSF_WARP_INSTR_PER_COMPONENT}
     bound_ms = {k: max(hbm_ms[k], issue_ms.get(k, 0.0)) for k in hbm_ms}
@@ -620,9 +622,9 @@ def gsf_block(g, dev, pdfs, peak, with_cpu):
     return block
 
 
-# warp-instructions executed per component (smsp__inst_executed.sum / components, ncu at 2^20): filled from
-# profiles/r2_gsf_2p20_ncu.csv
-GSF_WARP_INSTR_PER_COMPONENT = {"predict": 84.0, "update": 40.0}
+# warp-instructions executed per component (smsp__inst_executed.sum / components, ncu at 2^20:
+# profiles/r2_gsf_2p20_ncu_full.csv -- 78.68 M and 31.73 M warp-instructions for 2^20 components)
+GSF_WARP_INSTR_PER_COMPONENT = {"predict": 75.03, "update": 30.26}
 
 
 def sharded_parity(g, dev, world, rank, n=(1 << 20) + 8):
