@@ -9,7 +9,7 @@ import os
 
 GSE_NX, GSE_NU, GSE_NY, GSE_NSIGMA, GSE_NCOV, GSE_MAX_ND = 5, 2, 2, 11, 15, 8
 GSE_MODEL_BIOREACTOR = 1
-GSE_ABI_VERSION = 6
+GSE_ABI_VERSION = 7
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgse_b200.so")
 
@@ -72,6 +72,8 @@ SIGNATURES = {
                                            ctypes.c_uint, ctypes.c_uint, c_vp, c_vp, c_i64, c_vp, c_int, c_vp]),
     "gse_resample_search_f64": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_dbl, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "gse_ctx_errors": (ctypes.c_uint, [c_vp, c_int]),
+    "gse_ctx_result_block": (c_int, [c_vp, ctypes.POINTER(c_dbl_p), ctypes.POINTER(c_dbl_p)]),
+    "gse_ctx_wait": (c_int, [c_vp, c_vp, ctypes.POINTER(ctypes.c_uint)]),
     "gse_gather_rows": (c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_vp]),
     "gse_peer_alloc": (c_int, [c_int, c_i64, ctypes.POINTER(c_vp), ctypes.c_char_p]),
     "gse_peer_free": (c_int, [c_int, c_vp]),
@@ -89,7 +91,8 @@ SIGNATURES = {
     "gse_pf_moments_sharded": (c_int, [c_vp, c_shards_p, c_vp, c_i64, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]),
     "gse_peer_allgather_stats": (c_int, [c_vp, ctypes.POINTER(c_vp), c_int, c_int, ctypes.c_uint, c_vp, c_vp]),
     "gse_peer_allgather_totals": (c_int, [c_vp, ctypes.POINTER(c_vp), c_int, c_int, ctypes.c_uint, c_vp, c_vp, c_vp]),
-    "gse_peer_allgather_moments": (c_int, [c_vp, ctypes.POINTER(c_vp), c_int, c_int, ctypes.c_uint, c_vp, c_vp]),
+    "gse_peer_allgather_moments": (c_int, [c_vp, ctypes.POINTER(c_vp), c_int, c_int, ctypes.c_uint, c_vp, c_vp, c_vp,
+                                           c_vp]),
     "gse_ctx_upload_step_params": (c_int, [c_vp, ctypes.POINTER(gse_step_params), c_vp]),
     "gse_ctx_use_step_params": (c_int, [c_vp, c_int]),
     "gse_merge_stats": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp]),
@@ -131,12 +134,20 @@ def check(status):
         raise GseError("libgse_b200 call failed (status %d): %s" % (status, lib.gse_last_error().decode()))
 
 
+_double2 = ctypes.c_double * 2
+
+
 def as_double2(v):
+    try:                                  # the usual case -- a length-2 vector -- without a trip through numpy
+        if len(v) == 2 and getattr(v, "ndim", 1) == 1:
+            return _double2(float(v[0]), float(v[1]))
+    except TypeError:
+        pass
     import numpy
-    a = numpy.ascontiguousarray(numpy.asarray(v, dtype=numpy.float64).ravel())
+    a = numpy.asarray(v, dtype=numpy.float64).ravel()
     if a.size != 2:
         raise ValueError("expected 2 values, got %d" % a.size)
-    return (ctypes.c_double * 2)(float(a[0]), float(a[1]))
+    return _double2(float(a[0]), float(a[1]))
 
 
 def make_mixture(means, covariances, weights):

@@ -275,10 +275,15 @@ extern "C" int gse_ctx_create(int device, int model_id, int64_t n_max, const gse
         else cudaMemset(c->fused_trace, 0, sizeof(unsigned long long) * 8 * 4096);
     }
     // device-error word: host-mapped so that reading it never needs a copy or a synchronisation of its own
-    e = cudaHostAlloc((void**)&c->err_host, 64, cudaHostAllocMapped);
+    // (the same block holds the result area of gse_ctx_result_block: error word at byte 0, 64 doubles at byte 64)
+    e = cudaHostAlloc((void**)&c->err_host, 64 + 64 * sizeof(double), cudaHostAllocMapped);
     if (e == cudaSuccess) {
-        memset(c->err_host, 0, 64);
+        memset(c->err_host, 0, 64 + 64 * sizeof(double));
         e = cudaHostGetDevicePointer((void**)&c->err_dev, c->err_host, 0);
+    }
+    if (e == cudaSuccess) {
+        c->result_host = (double*)((char*)c->err_host + 64);
+        c->result_dev = (double*)((char*)c->err_dev + 64);
     }
     if (e != cudaSuccess) {
         gse_set_error("allocating the device-error word failed: %s", cudaGetErrorString(e));
@@ -402,6 +407,22 @@ extern "C" unsigned int gse_ctx_errors(gse_ctx* ctx, int clear) {
         if (clear) *(volatile unsigned int*)ctx->err_host = 0u;
     }
     return bits;
+}
+
+extern "C" int gse_ctx_result_block(gse_ctx* ctx, double** host_out, double** dev_out) {
+    GSE_REQUIRE(ctx != NULL && host_out != NULL && dev_out != NULL, "ctx / out is NULL");
+    *host_out = ctx->result_host;
+    *dev_out = ctx->result_dev;
+    return GSE_OK;
+}
+
+extern "C" int gse_ctx_wait(gse_ctx* ctx, void* stream, unsigned int* errors_out) {
+    GSE_REQUIRE(ctx != NULL, "ctx is NULL");
+    gse_device_guard guard(ctx->device);
+    GSE_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    const unsigned int bits = gse_ctx_errors(ctx, 1);
+    if (errors_out) *errors_out = bits;
+    return GSE_OK;
 }
 
 // Host evaluation of the device's output-count predicate (see gse_common.cuh): number of outputs

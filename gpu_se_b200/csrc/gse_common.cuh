@@ -115,6 +115,8 @@ struct gse_ctx {
     int fused_minb;           // CTAs per SM the fused kernel is compiled for (3; GSE_FUSED_MINB=4 to compare)
     unsigned int* err_host;   // device-error word: pinned, mapped host memory the kernels OR their GSE_ERR_* bits into
     unsigned int* err_dev;    // its device alias
+    double* result_host;      // 64 doubles in the same mapped block: kernels may write a moment block straight to the host
+    double* result_dev;       // its device alias
     int64_t* part;            // merge-path split points
     int64_t* range;           // [k_lo, k_hi): sources that interleave with a shard's outputs
     const gse_step_params* step_params;   // device block overriding the per-step scalars (CUDA-graph replay), or NULL

@@ -623,8 +623,8 @@ k_mbox_offsets(const __grid_constant__ MailboxTable mb, int rank, int nshards, u
 // the extra block (GS-UKF: sum w P) is a plain sum.  Every rank ends up with the same 48 doubles.
 #define MOM_WORDS 48
 __global__ void __launch_bounds__(32)
-k_mbox_moments(const __grid_constant__ MailboxTable mb, int rank, int nshards, unsigned int epoch, double* mom,
-               unsigned int* err) {
+k_mbox_moments(const __grid_constant__ MailboxTable mb, int rank, int nshards, unsigned int epoch, const double* mom,
+               const double* __restrict__ stats, double* out, unsigned int* err) {
     const int lane = threadIdx.x;
     mbox_exchange_block(mb, rank, nshards, epoch, reinterpret_cast<const unsigned long long*>(mom), MOM_WORDS, lane, err);
     if (lane != 0) return;
@@ -645,9 +645,10 @@ k_mbox_moments(const __grid_constant__ MailboxTable mb, int rank, int nshards, u
         S0 += m[0];
         for (int k = 0; k < 15; ++k) X[k] += m[26 + k];
     }
-    mom[0] = S0;
-    for (int j = 0; j < 5; ++j) { mom[1 + j] = S1[j]; mom[21 + j] = p[j]; }
-    for (int k = 0; k < 15; ++k) { mom[6 + k] = S2[k]; mom[26 + k] = X[k]; }
+    out[0] = S0;
+    for (int j = 0; j < 5; ++j) { out[1 + j] = S1[j]; out[21 + j] = p[j]; }
+    for (int k = 0; k < 15; ++k) { out[6 + k] = S2[k]; out[26 + k] = X[k]; }
+    if (stats) { out[41] = stats[0]; out[42] = stats[1]; }          // the global (M, S) ride along in the same read-back
 }
 
 extern "C" int gse_peer_allgather_stats(gse_ctx* ctx, void* const mailboxes[GSE_MAX_SHARDS], int rank, int nshards,
@@ -676,13 +677,15 @@ extern "C" int gse_peer_allgather_totals(gse_ctx* ctx, void* const mailboxes[GSE
 }
 
 extern "C" int gse_peer_allgather_moments(gse_ctx* ctx, void* const mailboxes[GSE_MAX_SHARDS], int rank, int nshards,
-                                          unsigned int epoch, double* mom_dev, void* stream) {
+                                          unsigned int epoch, double* mom_dev, const double* stats_dev, double* out_dev,
+                                          void* stream) {
     GSE_REQUIRE(ctx != NULL && mom_dev != NULL && epoch != 0, "bad arguments");
+    if (!out_dev) out_dev = mom_dev;
     gse_device_guard guard(ctx->device);
     MailboxTable mb;
     int rc = gse_build_mailboxes(mailboxes, rank, nshards, &mb);
     if (rc) return rc;
-    k_mbox_moments<<<1, 32, 0, (cudaStream_t)stream>>>(mb, rank, nshards, epoch, mom_dev, ctx->err_dev);
+    k_mbox_moments<<<1, 32, 0, (cudaStream_t)stream>>>(mb, rank, nshards, epoch, mom_dev, stats_dev, out_dev, ctx->err_dev);
     GSE_CHECK_LAUNCH(ctx);
     return GSE_OK;
 }

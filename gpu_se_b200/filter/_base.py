@@ -31,6 +31,7 @@ z, r, the Philox step counter) live in a 64-byte device block the kernels read
 calls eagerly first, so results are bit-identical with and without graphs.
 """
 import ctypes
+import math
 
 import numpy
 import torch
@@ -58,15 +59,31 @@ class Context:
                                                ctypes.byref(state), ctypes.byref(meas), ctypes.byref(handle)))
         self.handle = handle
         self.n_max = int(n_max)
+        # 64 doubles of host-mapped memory a kernel can leave a moment block in (no copy of its own on the way back)
+        host, devp = _lib.c_dbl_p(), _lib.c_dbl_p()
+        _lib.check(_lib.lib.gse_ctx_result_block(handle, ctypes.byref(host), ctypes.byref(devp)))
+        self.result_np = numpy.ctypeslib.as_array(host, shape=(64,))
+        self.result_dev = ctypes.cast(devp, ctypes.c_void_p).value
+        self._err_bits = ctypes.c_uint(0)
 
     @property
     def launches(self):
         return int(_lib.lib.gse_launch_count(self.handle))
 
+    def wait(self, stream):
+        """Synchronise ``stream`` and raise what ``check_device_errors`` would (one library call for both)."""
+        _lib.check(_lib.lib.gse_ctx_wait(self.handle, stream, ctypes.byref(self._err_bits)))
+        if self._err_bits.value:
+            self._raise_device_errors(self._err_bits.value)
+
     def check_device_errors(self):
         """Raise if a kernel of this context flagged an error since the last check (include/gse.h GSE_ERR_*).
         Call after a synchronisation: the word lives in host-mapped memory and is read without one."""
         bits = int(_lib.lib.gse_ctx_errors(self.handle, 1))
+        if bits:
+            self._raise_device_errors(bits)
+
+    def _raise_device_errors(self, bits):
         if bits:
             msg = _lib.lib.gse_last_error().decode()
             if bits & (_lib.GSE_ERR_CHOLESKY | _lib.GSE_ERR_SINGULAR_PYY):
@@ -77,6 +94,7 @@ class Context:
 
     def close(self):
         if getattr(self, "handle", None):
+            self.result_np = None                 # a view of memory the library frees now
             _lib.lib.gse_ctx_destroy(self.handle)
             self.handle = None
 
@@ -147,7 +165,7 @@ class WeightedEnsemble:
         # kernel once the filter has seen the pattern (it needs no second pass over the ancestor index)
         self._est_hint = False         # the caller reads the estimate of the resampled population
         self._fresh_resample = False   # nothing has touched the population since the last resample
-        self._mom_from_resample = False    # self._mom holds that estimate (device side)
+        self._mom_from_resample = False    # the context's host-mapped result block holds that estimate
         self._mom_unused = False       # ... and nobody has asked for it yet
         self._seed = int(seed) if seed is not None else int(numpy.random.randint(0, 2 ** 31 - 1))
         self._step = 0
@@ -392,7 +410,7 @@ class WeightedEnsemble:
             _lib.check(_lib.lib.gse_resample_fused(
                 self._ctx.handle, ll, base, stats.data_ptr(), n, r, n, 0, n, 0, self._idx.data_ptr(),
                 self._offtot.data_ptr() + 8, self._state.data_ptr() if want_mean else None, self._ld,
-                self._mom.data_ptr() if want_mean else None, int(stats_done), self._stream()))
+                self._ctx.result_dev if want_mean else None, int(stats_done), self._stream()))      # estimate -> host-mapped block
         else:
             self._scan()
             if self._stage_hook is not None:
@@ -435,21 +453,24 @@ class WeightedEnsemble:
             if self._fresh_resample and not full:
                 self._est_hint = True
             if self._mom_from_resample and not full:
-                self._mom_unused = False                    # the resample kernel left the estimate (and M, S) in self._mom
+                # the resample kernel has written the estimate (and M, S) straight into the context's host-mapped
+                # result block: nothing to launch, nothing to copy -- wait for the stream and read it
+                self._mom_unused = False
+                self._ctx.wait(self._stream())
+                self._mom_np = self._ctx.result_np[:48].copy()
             else:
                 self._launch_moments(mean_only=not full)
                 self._mom[41:43].copy_(self._stats[0:2])    # M, S ride along in the same read-back
+                self._mom_host.copy_(self._mom, non_blocking=True)
+                self._ctx.wait(self._stream())
+                self._mom_np = self._mom_host.numpy().copy()
             self._mom_full = full
-            self._mom_host.copy_(self._mom, non_blocking=True)
-            torch.cuda.current_stream(self.device).synchronize()
-            self._ctx.check_device_errors()
-            self._mom_np = self._mom_host.numpy().copy()
             self._mom_valid = True
         return self._mom_np
 
     def _weight_prefactor(self, mom):
         """A with  true weight_k = A * w_k,  w_k = base_k * exp(loglik_k - M)  the kernel's weights."""
-        return self._base_scale * float(numpy.exp(self._M_host(mom)))
+        return self._base_scale * math.exp(self._M_host(mom))
 
     def _M_host(self, mom):
         return float(mom[41])
@@ -466,7 +487,7 @@ class WeightedEnsemble:
 
     def _estimate_parts(self, need_cov=False):
         mom = self._moments(need_cov)
-        S0, S1, S2 = mom[0], mom[1:6], self._unpack_sym(mom[6:21])
+        S0, S1, S2 = mom[0], mom[1:6], (self._unpack_sym(mom[6:21]) if need_cov else None)
         p = mom[21:26]
         A = self._weight_prefactor(mom)
         return mom, S0, S1, S2, p, A

@@ -473,16 +473,22 @@ class _ShardedEnsemble:
         else:
             self._launch_local_moments(mean_only)
         if self.exchange == "peer":
-            # the shards' moment blocks cross NVLink inside one single-warp kernel that also merges them
+            # the shards' moment blocks cross NVLink inside one single-warp kernel that also merges them and leaves the
+            # result (with the global M, S) in the context's host-mapped result block: no copy of its own on the way back
+            ctx = loc._ctx
             if self.world > 1:
-                _lib.check(_lib.lib.gse_peer_allgather_moments(loc._ctx.handle, self._boxes, self.rank, self.world,
-                                                               self._next_epoch(), loc._mom.data_ptr(), loc._stream()))
-            loc._mom[41:43].copy_(loc._stats[0:2])
-            loc._mom_host.copy_(loc._mom, non_blocking=True)
-            torch.cuda.current_stream(self.device).synchronize()
-            loc._ctx.check_device_errors()
-            mom = loc._mom_host.numpy().copy()
-            S0, S1, S2, p = mom[0], mom[1:6].copy(), loc._unpack_sym(mom[6:21]), mom[21:26].copy()
+                _lib.check(_lib.lib.gse_peer_allgather_moments(ctx.handle, self._boxes, self.rank, self.world,
+                                                               self._next_epoch(), loc._mom.data_ptr(),
+                                                               loc._stats.data_ptr(), ctx.result_dev, loc._stream()))
+                ctx.wait(loc._stream())
+                mom = ctx.result_np[:48].copy()
+            else:
+                loc._mom[41:43].copy_(loc._stats[0:2])
+                loc._mom_host.copy_(loc._mom, non_blocking=True)
+                ctx.wait(loc._stream())
+                mom = loc._mom_host.numpy().copy()
+            S0, S1, p = mom[0], mom[1:6].copy(), mom[21:26].copy()
+            S2 = loc._unpack_sym(mom[6:21]) if not mean_only else None
         else:
             loc._mom[41:43].copy_(loc._stats[0:2])
             allm = [torch.empty_like(loc._mom) for _ in range(self.world)]

@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define GSE_ABI_VERSION 6
+#define GSE_ABI_VERSION 7
 
 #define GSE_NX 5        /* states  (Cg, Cx, Cfa, Ce, Ch)   model/BioreactorModel.py:191 */
 #define GSE_NU 2        /* inputs  (Fg_in, Fm_in)          model/BioreactorModel.py:195 */
@@ -105,6 +105,16 @@ int gse_ctx_destroy(gse_ctx* ctx);
 /* The context's device-error word (GSE_ERR_* bits, 0 = none); clear != 0 resets it.  Does not synchronise: call it
  * after the stream the kernels ran on has been synchronised. */
 unsigned int gse_ctx_errors(gse_ctx* ctx, int clear);
+
+/* A 64-double result area in host-mapped memory owned by the context: `*dev_out` may be passed wherever a kernel takes
+ * a moments pointer (gse_resample_fused's `moments_dev`), the block then lands in `*host_out` without a copy of its
+ * own -- the read-back of `point_estimate()` (particle.py:318-320) in the filter loop.  Valid once the stream has been
+ * synchronised (gse_ctx_wait). */
+int gse_ctx_result_block(gse_ctx* ctx, double** host_out, double** dev_out);
+
+/* cudaStreamSynchronize(stream) + gse_ctx_errors(ctx, clear = 1) in one call; `errors_out` (may be NULL) receives the
+ * GSE_ERR_* bits. */
+int gse_ctx_wait(gse_ctx* ctx, void* stream, unsigned int* errors_out);
 
 /* Per-step scalars in DEVICE memory.  While a context has a parameter block attached
  * (gse_ctx_set_step_params), every launch made through it reads u, dt, z, r and the Philox step
@@ -317,11 +327,14 @@ int gse_peer_allgather_totals(gse_ctx* ctx, void* const mailboxes[GSE_MAX_SHARDS
                               unsigned int epoch, const uint64_t* total_dev, uint64_t* offsets_dev,
                               void* stream);
 
-/*   _moments: in/out mom_dev[0..47] = this shard's moment block (gse_pf_moments / gse_gsf_moments layout) -> the
- *             moments of the whole population about shard 0's pivot, merged in shard order: identical on every rank.
+/*   _moments: mom_dev[0..47] = this shard's moment block (gse_pf_moments / gse_gsf_moments layout) -> out_dev[0..40]
+ *             (NULL: mom_dev itself) = the moments of the whole population about shard 0's pivot, merged in shard
+ *             order: identical on every rank.  stats_dev (may be NULL): the global (M, S) are copied to out_dev[41..42].
+ *             out_dev may be the context's host-mapped result block (gse_ctx_result_block).
  * The waits are bounded (4 s): a peer that never arrives sets GSE_ERR_PEER_TIMEOUT in the context's error word. */
 int gse_peer_allgather_moments(gse_ctx* ctx, void* const mailboxes[GSE_MAX_SHARDS], int rank, int nshards,
-                               unsigned int epoch, double* mom_dev, void* stream);
+                               unsigned int epoch, double* mom_dev, const double* stats_dev, double* out_dev,
+                               void* stream);
 
 /* stats_dev[0..1] = (max_s M_s, sum_s S_s exp(M_s - M)) from the nshards all-gathered pairs
  * pairs_dev[2 s .. 2 s + 1] = (M_s, S_s) written by each shard's update kernel. */

@@ -1,0 +1,6 @@
+# session 2, run 5 (1 GPU): batched mean-row reads in the fused resample (MEAN kernels): tests + e2e stage times
+cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_resample.py tests/test_gpu_sharded.py -q -m gpu -k "estimate or world1" 2>&1 | tail -4
+python tools/e2e_stages.py 2>&1 | tail -4
+python tools/e2e_stages.py --no-events 2>&1 | tail -3
+python tools/e2e_stages.py --log2n 20 2>&1 | tail -4
