@@ -249,6 +249,10 @@ extern "C" int gse_ctx_create(int device, int model_id, int64_t n_max, const gse
         const char* v = getenv("GSE_UPDATE_CTAS");
         c->update_ctas_per_sm = (v && atoi(v) >= 1 && atoi(v) <= 32) ? atoi(v) : 5;
     }
+    {
+        const char* v = getenv("GSE_UPDATE_PIPE");
+        c->update_pipe = (v && atoi(v) == 0) ? 0 : 1;
+    }
     c->scan_resident_blocks = 0;
     {
         const char* mode = getenv("GSE_SCAN");
@@ -261,6 +265,10 @@ extern "C" int gse_ctx_create(int device, int model_id, int64_t n_max, const gse
     {
         const char* v = getenv("GSE_GSF_MINB");
         c->gsf_minb = (v && (atoi(v) == 3 || atoi(v) == 4 || atoi(v) == 5 || atoi(v) == 6)) ? atoi(v) : 0;    // 0: per-kernel defaults
+    }
+    {
+        const char* v = getenv("GSE_GSF_UPDATE_WAVES");           // tuning knob: grid of the GS-UKF update kernel = waves x resident CTAs
+        c->gsf_update_waves = (v && atoi(v) >= 1 && atoi(v) <= 64) ? atoi(v) : 1;
     }
     {
         const char* v = getenv("GSE_PREDICT_MINB");               // tuning knob: CTAs per SM of the predict kernel

@@ -103,7 +103,9 @@ struct gse_ctx {
     uint64_t* tile_status;    // single-pass kernels: one status word per CTA (look-back scan, fused resample)
     int64_t scan_tiles_prev;  // tiles the previous look-back launch rewrote (0: none yet)
     int scan_resident_blocks; // co-resident CTAs of the look-back kernel on this device (0: not queried yet)
-    int update_ctas_per_sm;   // persistent grid of the update kernel (8; GSE_UPDATE_CTAS overrides, for tuning)
+    int update_ctas_per_sm;   // persistent grid of the update kernel (5; GSE_UPDATE_CTAS overrides, for tuning)
+    int update_pipe;          // update kernel with the next iteration's loads in flight (GSE_UPDATE_PIPE=0 disables)
+    int gsf_update_waves;     // persistent grid of the GS-UKF update kernel, in waves of resident CTAs (GSE_GSF_UPDATE_WAVES)
     int scan_single_pass;     // use the look-back scan for loglik-only weights (GSE_SCAN=twopass disables)
     uint64_t* fused_status;   // fused resample: one aggregate word per CTA, zero between launches
     int4* heavy_queue;        // fused resample: runs of one heavy source handed to the whole grid (start, end, ancestor)

@@ -283,10 +283,11 @@ k_gsf_update(float* __restrict__ mean, float* __restrict__ cov, int64_t ld, int6
              float* loglik, double z0, double z1, const __grid_constant__ MixDensity2 md, float* block_max, float* block_sum,
              unsigned int* ticket, double* stats, const gse_step_params* __restrict__ params, unsigned int* err) {
     if (params) { z0 = params->z[0]; z1 = params->z[1]; }
-    const int64_t i = (int64_t)blockIdx.x * GSF_THREADS + threadIdx.x;
-    float vals[1] = {0.0f};
-    bool valid[1] = {false};
-    if (i < n) {
+    // persistent grid: a CTA walks over tiles of GSF_THREADS components and merges its (max, sum exp) ONCE at the end.
+    // (One CTA per tile spent a fifth of its few microseconds in the five barriers, the fence and the ticket's round
+    // trip of block_merge_max_sumexp: 20 % of the stall samples at 2^20 components.)
+    MaxSumExp acc;
+    for (int64_t i = (int64_t)blockIdx.x * GSF_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * GSF_THREADS) {
         float m[5], P[15], L[15];
 #pragma unroll
         for (int j = 0; j < 5; ++j) m[j] = mean[j * ld + i];
@@ -385,11 +386,12 @@ k_gsf_update(float* __restrict__ mean, float* __restrict__ cov, int64_t ld, int6
         // global update: weights *= pdf(z - g(mean))  (:141-149)
         const double ge0 = z0 - (double)output_glucose(mn[0]);
         const double ge1 = z1 - (double)output_fa(mn[2]);
-        vals[0] = (float)((loglik_in ? (double)loglik_in[i] : 0.0) + meas_logpdf(md, ge0, ge1));
-        valid[0] = true;
+        const float vals[1] = {(float)((loglik_in ? (double)loglik_in[i] : 0.0) + meas_logpdf(md, ge0, ge1))};
+        const bool valid[1] = {true};
         loglik[i] = vals[0];
+        acc.add<1>(vals, valid);
     }
-    block_max_sumexp_finalize<GSF_THREADS, 1>(vals, valid, block_max, block_sum, ticket, stats);
+    block_merge_max_sumexp<GSF_THREADS>(acc.m, acc.s, block_max, block_sum, ticket, stats);
 }
 
 extern "C" int gse_gsf_update(gse_ctx* ctx, float* mean_dev, float* cov_dev, int64_t ld, int64_t n,
@@ -399,18 +401,22 @@ extern "C" int gse_gsf_update(gse_ctx* ctx, float* mean_dev, float* cov_dev, int
     gse_device_guard guard(ctx->device);
     GSE_REQUIRE(n >= 1 && n <= ctx->n_max && ld >= n, "n / ld out of range");
     (void)u;
-    const unsigned blocks = (unsigned)gse_div_up(n, GSF_THREADS);
-    GSE_REQUIRE((int64_t)blocks <= ctx->max_blocks, "workspace too small");
+    const int64_t tiles = gse_div_up(n, GSF_THREADS);
+    GSE_REQUIRE(tiles <= ctx->max_blocks, "workspace too small");
+    const int minb = (ctx->gsf_minb >= 3 && ctx->gsf_minb <= 6) ? ctx->gsf_minb : 4;
+    const int64_t resident = (int64_t)ctx->num_sms * minb * ctx->gsf_update_waves;
+    const unsigned blocks = (unsigned)(tiles < resident ? tiles : resident);
 #define LAUNCH_G2(MB)                                                                                              \
     k_gsf_update<MB><<<blocks, GSF_THREADS, 0, (cudaStream_t)stream>>>(mean_dev, cov_dev, ld, n, loglik_in_dev, loglik_dev, \
                                                                        z[0], z[1], ctx->meas_density, ctx->block_max,      \
                                                                        ctx->block_sum, ctx->ticket, stats_dev,             \
                                                                        ctx->step_params, ctx->err_dev)
-    // measured at 2^20 components (us): 3 CTAs/SM 95, 4: 82, 5: 76, 6: 71 (80 registers)
-    if (ctx->gsf_minb == 5) LAUNCH_G2(5);
-    else if (ctx->gsf_minb == 4) LAUNCH_G2(4);
-    else if (ctx->gsf_minb == 3) LAUNCH_G2(3);
-    else LAUNCH_G2(6);
+    // measured at 2^20 components (us), persistent grid of one wave: 3 CTAs/SM 69, 4: 64 (128 registers, no spills), 5: 68,
+    // 6: 74 (80 registers, spills); two waves: +1.5.  (One CTA per tile, round 1: 95 / 82 / 76 / 71.)
+    if (minb == 5) LAUNCH_G2(5);
+    else if (minb == 6) LAUNCH_G2(6);
+    else if (minb == 3) LAUNCH_G2(3);
+    else LAUNCH_G2(4);
 #undef LAUNCH_G2
     GSE_CHECK_LAUNCH(ctx);
     return GSE_OK;
