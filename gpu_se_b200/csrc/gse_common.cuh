@@ -166,6 +166,7 @@ struct GatherShards {
     int64_t home_ld, home_row0, home_row1;
     const float* home_base;        // home_state - home_row0: row k of the home shard is home_base[k] (k a GLOBAL index)
     int home_lo, home_hi;          // home_row0 / home_row1 as int32 (ancestor indices are int32)
+    int ends_first;                // block order of the gathering kernels: both ends of the shard first (see k_pf_predict)
 };
 
 static inline int gse_build_gather_shards(const gse_shards* sh, const void* dst, GatherShards* g) {
@@ -186,6 +187,10 @@ static inline int gse_build_gather_shards(const gse_shards* sh, const void* dst,
     g->home_base = (const float*)((uintptr_t)g->home_state - (uintptr_t)g->home_row0 * sizeof(float));
     g->home_lo = (int)g->home_row0;
     g->home_hi = (int)g->home_row1;
+    {
+        const char* v = getenv("GSE_PREDICT_ENDS_FIRST");
+        g->ends_first = (sh->nshards > 1 && !(v && atoi(v) == 0)) ? 1 : 0;     // measured at 2 x 2^24 rows: 140.4 -> 136.7 us
+    }
     return GSE_OK;
 }
 

@@ -92,7 +92,12 @@ k_pf_predict(const float* xs, int64_t lds, const int32_t* __restrict__ idx, cons
              const __grid_constant__ MixDensity2f md) {
     constexpr bool FUSE = FUSE_ND >= 0;
     const GatherShards& shards = shards_arg;
-    const int64_t g = (int64_t)blockIdx.x * PF_THREADS + threadIdx.x;
+    // Sharded: the rows whose ancestors live on another GPU sit at the two ENDS of the shard (the ancestor index is
+    // non-decreasing).  In launch order the high end runs last, and the kernel's tail then waits out NVLink round
+    // trips; with ends_first the blocks alternate between the two ends and finish in the all-local middle.
+    unsigned int vblock = blockIdx.x;
+    if (GMODE == 2 && shards.ends_first) vblock = (vblock & 1u) ? gridDim.x - 1u - (vblock >> 1) : (vblock >> 1);
+    const int64_t g = (int64_t)vblock * PF_THREADS + threadIdx.x;
     // (fused: every thread reaches the block reduction; a thread past the end recomputes the last group and stores nothing)
     const bool active = g * ROWS_PER_THREAD < n;
     if (!FUSE && !active) return;
@@ -657,27 +662,42 @@ k_mbox_moments(const __grid_constant__ MailboxTable mb, int rank, int nshards, u
                const double* __restrict__ stats, double* out, unsigned int* err) {
     const int lane = threadIdx.x;
     mbox_exchange_block(mb, rank, nshards, epoch, reinterpret_cast<const unsigned long long*>(mom), MOM_WORDS, lane, err);
-    if (lane != 0) return;
-    double S0 = 0.0, S1[5] = {0, 0, 0, 0, 0}, S2[15], X[15], p[5];
-    for (int k = 0; k < 15; ++k) { S2[k] = 0.0; X[k] = 0.0; }
-    for (int t = 0; t < nshards; ++t) {
-        volatile unsigned long long* src = mbox_slot(mb, rank, t, epoch);
-        double m[41];
-        for (int k = 0; k < 41; ++k) m[k] = __longlong_as_double((long long)src[k]);
-        if (t == 0) for (int j = 0; j < 5; ++j) p[j] = m[21 + j];
-        double d[5];
-        for (int j = 0; j < 5; ++j) d[j] = m[21 + j] - p[j];
+    // lane t reads shard t's block and moves it to shard 0's pivot (one round trip to the mailbox for all shards, not
+    // one per shard); the sums then run over the lanes in shard order, the same on every rank
+    const int t = lane < nshards ? lane : 0;
+    volatile unsigned long long* src = mbox_slot(mb, rank, t, epoch);
+    double m[41];
+#pragma unroll
+    for (int k = 0; k < 41; ++k) m[k] = __longlong_as_double((long long)src[k]);
+    double c[36];                                            // S0, S1[5], S2[15], X[15] of this shard about the common pivot
+    double d[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) d[j] = m[21 + j] - __shfl_sync(0xffffffffu, m[21 + j], 0);
+    c[0] = m[0];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) c[1 + j] = m[1 + j] + m[0] * d[j];
+    {
         int q = 0;
+#pragma unroll
         for (int i = 0; i < 5; ++i)
+#pragma unroll
             for (int j = 0; j <= i; ++j, ++q)
-                S2[q] += m[6 + q] + m[1 + i] * d[j] + d[i] * m[1 + j] + m[0] * d[i] * d[j];
-        for (int j = 0; j < 5; ++j) S1[j] += m[1 + j] + m[0] * d[j];
-        S0 += m[0];
-        for (int k = 0; k < 15; ++k) X[k] += m[26 + k];
+                c[6 + q] = m[6 + q] + m[1 + i] * d[j] + d[i] * m[1 + j] + m[0] * d[i] * d[j];
     }
-    out[0] = S0;
-    for (int j = 0; j < 5; ++j) { out[1 + j] = S1[j]; out[21 + j] = p[j]; }
-    for (int k = 0; k < 15; ++k) { out[6 + k] = S2[k]; out[26 + k] = X[k]; }
+#pragma unroll
+    for (int k = 0; k < 15; ++k) c[21 + k] = m[26 + k];
+#pragma unroll
+    for (int k = 0; k < 36; ++k) {
+        double tot = 0.0;
+        for (int u = 0; u < nshards; ++u) tot += __shfl_sync(0xffffffffu, c[k], u);      // fixed (shard) order
+        c[k] = tot;
+    }
+    if (lane != 0) return;
+    out[0] = c[0];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) { out[1 + j] = c[1 + j]; out[21 + j] = m[21 + j]; }     // lane 0 holds shard 0: its pivot
+#pragma unroll
+    for (int k = 0; k < 15; ++k) { out[6 + k] = c[6 + k]; out[26 + k] = c[21 + k]; }
     if (stats) { out[41] = stats[0]; out[42] = stats[1]; }          // the global (M, S) ride along in the same read-back
 }
 
