@@ -12,8 +12,8 @@ with the global systematic resample of gpu_se_b200/sharded.py (weak scaling).
 Prints ONE JSON line (rank 0).  `value` is device-timed with the particles resident in HBM; `e2e`
 goes through the public predict/update/resample/point_estimate API with host u, z and the
 estimate read back every step; `roofline` is the dominant kernel against the measured HBM peak;
-`cpu_baseline` is the loop-faithful oracle port (the reference's per-particle Python algorithm)
-timed on the host.  `--impl reference` times that port alone.
+`cpu_baseline` is the reference's own `filter.ParticleFilter` (the unmodified copy under oracle/_ref)
+timed on one host core; `--impl reference` times it alone (the oracle port only if the copy is absent).
 """
 import argparse
 import json
@@ -44,6 +44,32 @@ U_NOMINAL = numpy.array([0.06, 0.2])
 STAGE_BYTES = {"predict": 44, "update": 12, "predict+update": 48, "resample": 8, "scan": 12, "search": 12}
 # sharded run: the same, plus the all-gather of the shard totals ("offsets", no HBM traffic to speak of)
 STAGE_BYTES_SHARDED = {"predict": 44, "update": 12, "predict+update": 48, "resample": 8}
+
+
+NCU_CAPTURE = os.path.join(ROOT, "profiles", "r2_pf_step_2p24_ncu_full.csv")
+NCU_KERNEL_OF_STAGE = {"predict": "k_pf_predict", "update": "k_pf_update", "resample": "k_resample_fused"}
+
+
+def ncu_traffic_bytes_per_row():
+    """(bytes per row by stage, source) from the committed ncu capture of this command at 2^24 rows: the mean of
+    dram__bytes_read.sum + dram__bytes_write.sum over the captured launches of the stage's kernel.  Falls back to the
+    constants above (copied from the same capture) for stages the file does not hold."""
+    import csv
+    out, src = dict(NCU_TRAFFIC_BYTES_PER_ROW), "constants copied from profiles/r2_pf_step_2p24_ncu_full.csv"
+    try:
+        rows = list(csv.reader(open(NCU_CAPTURE)))
+        hdr = rows[0]
+        ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        ur, uw = scale[rows[1][ir]], scale[rows[1][iw]]
+        for stage, kern in NCU_KERNEL_OF_STAGE.items():
+            v = [float(r[ir]) * ur + float(r[iw]) * uw for r in rows[2:] if len(r) == len(hdr) and kern in r[0]]
+            if v:
+                out[stage] = sum(v) / len(v) / 2 ** 24
+        src = "read from profiles/r2_pf_step_2p24_ncu_full.csv"
+    except (OSError, ValueError, KeyError):
+        pass
+    return out, src
 
 
 def workload_name(log2n):
@@ -140,7 +166,6 @@ class ClockSampler:
     def stop(self, t0, t1):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -156,7 +181,7 @@ class ClockSampler:
                 clk, cmax = float(parts[1]), float(parts[2])
             except ValueError:
                 continue
-            if t0 - 0.05 <= t <= t1 + 0.2:
+            if t0 - 0.05 <= t <= t1 + 0.01:
                 sm.append(clk)
                 mx.append(cmax)
                 for name, val in zip(names, parts[5:9]):
@@ -424,8 +449,25 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.25)
-    barrier()                                   # after the sampler warm-up: every rank enters the timed region together
+
+    def fill_until_sample(timeout):
+        """Keep the sampled GPU under load (streaming passes over a scratch buffer: nothing of the filter is touched, its
+        trajectory stays what it was) until the clock sampler has just delivered a line.  Every nvidia-smi query stalls
+        the launches of the sampled GPU for a millisecond or two -- 4 % of a 50 ms region, landing in ONE step.  The timed
+        region therefore starts right behind a sample: a region shorter than the sampling period has samples under load
+        on both sides of it and none of these stalls inside; longer regions simply contain them.  Only rank 0 is
+        sampled; the other ranks wait for it in the barrier that follows."""
+        if rank != 0 or sampler.proc is None:
+            return
+        n0, t_begin = len(sampler.lines), time.perf_counter()
+        while len(sampler.lines) == n0 and time.perf_counter() - t_begin < timeout:
+            for _ in range(8):
+                scratch.mul_(1.0)
+            torch.cuda.synchronize(dev)
+
+    scratch = torch.ones(1 << 26, dtype=torch.float32, device=dev) if rank == 0 else None      # 256 MB: larger than L2
+    fill_until_sample(1.0)
+    barrier()                                   # every rank enters the timed region together
     launches0 = pf._ctx.launches
     t_wall0 = time.perf_counter()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -439,7 +481,9 @@ def run_ours(args):
     t_wall1 = time.perf_counter()
     launches = pf._ctx.launches - launches0
     dev_ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    fill_until_sample(0.5)                      # ... and the sample that closes the bracket is taken under load as well
+    torch.cuda.synchronize(dev)
+    clocks = sampler.stop(t_wall0, time.perf_counter()) if rank == 0 else None
 
     # per-stage durations
     stage_ms = {}
@@ -476,6 +520,7 @@ def run_ours(args):
         return
 
     peak, peak_src = measured_peak_gbs()
+    traffic_row, traffic_src = ncu_traffic_bytes_per_row()
     STAGE_BYTES = globals()["STAGE_BYTES_SHARDED" if world > 1 else "STAGE_BYTES"]
     if args.workload == "gsf":      # 20 floats per component, lazy resample
         STAGE_BYTES = {"predict": 4 + 80 + 80, "update": 80 + 80 + 4, "resample": 8, "scan": 12, "search": 12}
@@ -501,9 +546,9 @@ def run_ours(args):
                    "l2": "inputs larger than L2 (state %.0f MB per GPU vs 126 MB L2)" % (n_local * 20 / 1e6)},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,
-                     "traffic": (NCU_TRAFFIC_BYTES_PER_ROW[dom] * n_local if dom in NCU_TRAFFIC_BYTES_PER_ROW else None),
-                     "traffic_source": "ncu --set full capture at 2^24 rows (profiles/r2_pf_step_2p24_ncu_full.csv), "
-                                       "scaled by rows; per launch of the stage's kernels",
+                     "traffic": (traffic_row[dom] * n_local if dom in traffic_row else None),
+                     "traffic_source": "ncu --set full capture of this command at 2^24 rows (%s), scaled by rows; "
+                                       "per launch of the stage's kernels" % traffic_src,
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_particle": STAGE_BYTES.get(dom),
                      "whole_step_frac": STEP_BYTES * n_local / (dev_ms / K * 1e-3) / 1e9 / peak,
