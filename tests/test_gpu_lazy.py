@@ -177,3 +177,56 @@ def test_gsukf_lazy_predict_equals_materialised(g):
     b.predict(u, 0.1)
     assert numpy.array_equal(a.means.get(), b.means.get())
     assert numpy.array_equal(a.covariances.get(), b.covariances.get())
+
+
+def test_result_block_and_wait_abi(g):
+    """gse_ctx_result_block / gse_ctx_wait through the C ABI: gse_resample_fused leaves the estimate of the resampled
+    population (particle.py:318-320 right after :296-316) in the context's host-mapped block -- no copy of its own -- and
+    it equals the mean of the gathered rows; the public classes read their estimate the same way."""
+    import ctypes
+    import torch
+    from gpu_se_b200 import _lib
+    from gpu_se_b200.filter._base import Context
+    dev = torch.device("cuda", 0)
+    n, ld = 50001, 50048
+    rng = numpy.random.default_rng(12)
+    ctx = Context(dev, n, None, None)
+    host, devp = _lib.c_dbl_p(), _lib.c_dbl_p()
+    _lib.check(_lib.lib.gse_ctx_result_block(ctx.handle, ctypes.byref(host), ctypes.byref(devp)))
+    assert ctypes.cast(devp, ctypes.c_void_p).value == ctx.result_dev and ctx.result_np.shape == (64,)
+    x = torch.as_tensor(rng.normal(size=(5, ld)).astype(numpy.float32), device=dev)
+    ll = torch.as_tensor((rng.normal(size=ld) * 3).astype(numpy.float32), device=dev)
+    stats = torch.tensor([float(ll[:n].max()), float(torch.exp(ll[:n].double() - ll[:n].max().double()).sum()), 0.0, 0.0],
+                         dtype=torch.float64, device=dev)
+    idx = torch.zeros(ld, dtype=torch.int32, device=dev)
+    total = torch.zeros(1, dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    ctx.result_np[:] = -1.0
+    _lib.check(_lib.lib.gse_resample_fused(ctx.handle, ll.data_ptr(), None, stats.data_ptr(), n, 0.625, n, 0, n, 0,
+                                           idx.data_ptr(), total.data_ptr(), x.data_ptr(), ld, ctx.result_dev, 1, stream))
+    bits = ctypes.c_uint(99)
+    _lib.check(_lib.lib.gse_ctx_wait(ctx.handle, stream, ctypes.byref(bits)))
+    assert bits.value == 0
+    mom = ctx.result_np[:48].copy()
+    anc = idx[:n].cpu().numpy()
+    assert (numpy.diff(anc) >= 0).all() and anc.min() >= 0 and anc.max() < n
+    want = x.cpu().numpy()[:, anc].astype(numpy.float64).sum(axis=1)
+    assert mom[0] == n and numpy.allclose(mom[1:6], want, rtol=1e-12, atol=1e-9)
+    assert (mom[21:26] == 0.0).all() and mom[41] == 0.0 and mom[42] == n          # pivot 0, uniform (M, S)
+    assert stats.cpu().numpy()[:2].tolist() == [0.0, float(n)]                      # reset_stats
+    ctx.wait(stream)                                                                 # the Python wrapper of the same call
+    ctx.close()
+    assert ctx.result_np is None
+    # the classes: point_estimate() straight after resample() comes out of that block and equals the moments kernel's
+    pf = make_pf(g, 30000)
+    u = numpy.array([0.06, 0.2])
+    z = consistent_measurement(u, 0.1, rng)
+    for k in range(3):
+        pf.predict(u, 0.1)
+        pf.update(u, z)
+        pf.resample(r=0.3 + 0.2 * k)
+        est = pf.point_estimate()
+        if k > 0:
+            assert pf._est_hint and not pf._mom_unused
+        ref = pf.particles.get().astype(numpy.float64).mean(axis=0)
+        assert numpy.allclose(est, ref, rtol=1e-6)
