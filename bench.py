@@ -466,7 +466,7 @@ def run_ours(args):
             torch.cuda.synchronize(dev)
 
     scratch = torch.ones(1 << 26, dtype=torch.float32, device=dev) if rank == 0 else None      # 256 MB: larger than L2
-    fill_until_sample(1.0)
+    fill_until_sample(3.0)                      # (nvidia-smi takes a few hundred milliseconds to deliver its first line)
     barrier()                                   # every rank enters the timed region together
     launches0 = pf._ctx.launches
     t_wall0 = time.perf_counter()
