@@ -1,5 +1,6 @@
-"""Shared host-side plumbing of the two filters: the library context, the weight representation
-and the systematic resample (scan -> merge-path partition -> fused search + gather).
+"""Shared host-side plumbing of the two filters: the library context, the weight representation, the systematic
+resample (one fused scan + rank + fill kernel; scan -> merge-path search as the two-stage alternative) and the read-back
+of the estimates.
 
 Weights.  The reference keeps linear-domain weights (float32, float64 after the first resample,
 SURVEY.md quirk Q3) and multiplies pdf values into them, which underflows for informative

@@ -15,7 +15,8 @@ The reference has no multi-GPU path; this is the north-s
   makes every index buffer complete when its kernel completes.  The rows themselves move lazily: the next ``predict``
   / moments kernel pulls row ``idx[i]`` out of whichever GPU holds it.  No NCCL call, no host synchronisation.
 * estimates: every rank reduces its shard to a 48-double moment block; the blocks are all-gathered through the
-  mailboxes and merged on the device (``gse_peer_allgather_moments``), then one 384-byte read-back.
+  mailboxes and merged on the device (``gse_peer_allgather_moments``) straight into the context's host-mapped result
+  block: the read-back is one stream synchronisation, no copy.
 
   ``exchange="slabs"`` is the host-planned alternative for GPUs without peer access (and the cross-check of the peer
   path): all-gather of the totals over NCCL -> closed-form output ranges per source shard
