@@ -95,3 +95,24 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_docs_quote_the_current_abi():
+    """DESIGN.md states the ABI version and the number of entry points: keep both in step with include/gse.h."""
+    from gpu_se_b200 import _lib
+    design = open(os.path.join(ROOT, "DESIGN.md")).read()
+    m = re.search(r"ABI v(\d+), (\d+) `extern \"C\"` entry points", design)
+    assert m, "DESIGN.md section 0 no longer states the ABI version / entry-point count"
+    assert int(m.group(1)) == _lib.GSE_ABI_VERSION
+    assert int(m.group(2)) == len(declared_functions())
+    header = open(os.path.join(ROOT, "include", "gse.h")).read()
+    assert re.search(r"#define GSE_ABI_VERSION %d\b" % _lib.GSE_ABI_VERSION, header)
+    # every entry point is attributed to the reference interface it replaces (or marked new) in INTEGRATION.md
+    integration = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    groups = {"gse_peer_alloc": "gse_peer_alloc/open/close/free", "gse_peer_open": "gse_peer_alloc/open/close/free",
+              "gse_peer_close": "gse_peer_alloc/open/close/free", "gse_peer_free": "gse_peer_alloc/open/close/free",
+              "gse_peer_allgather_stats": "gse_peer_allgather_stats/_totals/_moments",
+              "gse_peer_allgather_totals": "gse_peer_allgather_stats/_totals/_moments",
+              "gse_peer_allgather_moments": "gse_peer_allgather_stats/_totals/_moments"}
+    missing = [n for n in declared_functions() if n not in integration and groups.get(n, "\0") not in integration]
+    assert not missing, "INTEGRATION.md does not mention: %s" % ", ".join(missing)
