@@ -65,3 +65,18 @@ def test_as_double2_accepts_what_the_reference_callers_pass():
     for bad in ([1.0], [1.0, 2.0, 3.0], numpy.zeros((2, 2)), 1.0):
         with pytest.raises((ValueError, TypeError)):
             _lib.as_double2(bad)
+
+
+def test_every_cited_profile_exists():
+    """DESIGN.md / BASELINE.md / README.md / bench.py cite files under profiles/ as evidence: none of them may dangle."""
+    import glob
+    import re
+    cited = set()
+    for doc in ("DESIGN.md", "BASELINE.md", "README.md", "INTEGRATION.md", "bench.py"):
+        text = open(os.path.join(ROOT, doc)).read()
+        cited |= set(re.findall(r"profiles/([A-Za-z0-9_.*-]+\.(?:json|csv|txt))", text))
+        # the tables name files without the directory once it is clear from the context: `r2_launches.csv`
+        cited |= set(re.findall(r"`(r[12]_[A-Za-z0-9_.*-]+\.(?:json|csv|txt))`", text))
+    assert len(cited) >= 10
+    missing = sorted(c for c in cited if not glob.glob(os.path.join(ROOT, "profiles", c)))
+    assert not missing, "cited but not under profiles/: %s" % ", ".join(missing)
